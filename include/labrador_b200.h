@@ -1,0 +1,198 @@
+/*
+ * labrador_b200.h -- C ABI of the B200-native LaBRADOR prover hot path (liblabrador_b200.so).
+ *
+ * This is the drop-in boundary for RatioAeterna/LaBRADOR-SNARK's prover path.  The reference has
+ * no FFI today (pure Rust); each entry point below names the reference item it
+ * replaces (paths relative to the reference repo).  INTEGRATION.md shows the Rust `extern "C"`
+ * block and the wrapper that keeps the reference's own names (Rq, CRS, Prover::proof_gen, ...).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types.  Every function returns a lab_status
+ *     and never unwinds.  lab_last_error(ctx) gives the message for the last failure on ctx.
+ *   - a polynomial of R_q = Z_q[X]/(X^64+1), q = 8191, is uint32_t[64] of canonical
+ *     representatives in [0,q) (dense form of the reference's trimmed Vec<Zq>, algebraic.rs:303-376).
+ *   - witness S: uint32_t[R][N][64], s_i contiguous (reference: Array2<Rq> (N x R), column i,
+ *     proofgen.rs:45).  phi: same layout.  a, g, h: uint32_t[R][R][64].  T: uint32_t[R][rows][64].
+ *   - functions without a _dev suffix take HOST pointers and do their own H2D/D2H on the ctx
+ *     stream and synchronise before returning.  *_dev functions take DEVICE pointers (memory
+ *     from lab_malloc or any CUDA allocation on the ctx device), enqueue on the ctx stream and
+ *     do NOT synchronise (call lab_sync).
+ *   - a ctx is single-owner (one stream, one device, scratch memory); distinct ctxs are
+ *     independent and may be used from different threads.  There is no global mutable state
+ *     (the reference's NTT_ENABLED / MOD_SUSPENSION globals, constants.rs:200-201, have no
+ *     equivalent: arithmetic is always the exact integer semantics).
+ *   - there is no CPU fallback: without a CUDA device lab_ctx_create fails with LAB_ERR_CUDA.
+ */
+#ifndef LABRADOR_B200_H
+#define LABRADOR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LAB_D 64                 /* constants.rs:15 */
+#define LAB_Q 8191u              /* constants.rs:195 */
+#define LAB_JL_ROWS 256          /* verification.rs:559 */
+
+typedef enum {
+    LAB_OK = 0,
+    LAB_ERR_JL_REJECTED = 1,     /* panic!("failed JL...")            proofgen.rs:175-176 */
+    LAB_ERR_BPP_CHECK = 2,       /* verify_b_prime_prime assert       verification.rs:550 */
+    LAB_ERR_SHAPE = 3,           /* length asserts                    util.rs:262,275,299,497,512 */
+    LAB_ERR_PARAMS = 4,          /* degenerate RuntimeConstants (B<2, T<=0: the reference spins or
+                                    panics) or invalid arguments */
+    LAB_ERR_CUDA = 5,            /* CUDA runtime failure / no device */
+    LAB_ERR_ALLOC = 6
+} lab_status;
+
+/* RuntimeConstants (constants.rs:205-265), same field names */
+typedef struct {
+    uint64_t N, R;
+    int64_t BETA_BOUND;
+    double STD;
+    int64_t B, T_1, B_1, T_2, B_2;
+    double GAMMA, GAMMA_1, GAMMA_2, BETA_PRIME;
+    uint64_t KAPPA, KAPPA_1, KAPPA_2;
+    int degenerate;
+} lab_constants;
+
+typedef struct lab_ctx lab_ctx;
+
+/* ---- context ---- */
+int lab_ctx_create(int device, lab_ctx **out);
+void lab_ctx_destroy(lab_ctx *ctx);
+const char *lab_last_error(const lab_ctx *ctx);          /* ctx may be NULL: last create error */
+int lab_sync(lab_ctx *ctx);
+int lab_malloc(lab_ctx *ctx, size_t bytes, void **dptr);
+int lab_free(lab_ctx *ctx, void *dptr);
+int lab_memcpy_h2d(lab_ctx *ctx, void *dst, const void *src, size_t bytes);   /* async on ctx stream */
+int lab_memcpy_d2h(lab_ctx *ctx, void *dst, const void *src, size_t bytes);   /* async on ctx stream */
+void *lab_stream(lab_ctx *ctx);                           /* cudaStream_t, for event timing */
+uint64_t lab_kernel_launches(const lab_ctx *ctx);         /* kernels launched on this ctx so far */
+int lab_version(void);
+/* CUDA-event stopwatch on the ctx stream (events bracket whatever is enqueued between the calls) */
+int lab_timer_start(lab_ctx *ctx);
+int lab_timer_stop(lab_ctx *ctx, double *elapsed_ms);     /* synchronises on the stop event */
+
+/* RuntimeConstants::new(N, R)  (constants.rs:234-264). Returns LAB_ERR_PARAMS (and fills out,
+ * degenerate = 1) where the reference's formulas leave the range in which it terminates. */
+int lab_runtime_constants(uint64_t N, uint64_t R, lab_constants *out);
+
+/* ---- ring primitives: Rq::multiply / &Rq * &Rq (algebraic.rs:379-404, 517-523) ---- */
+/* Forward transform R_q -> F_{q^2}^32.  out[p][2j], out[p][2j+1] = (re, im) of f_p(zeta^{e_j});
+ * lab_ntt_slot_exponents gives e_j; zeta = 2620 + 936 i.  Replaces the per-call
+ * PLAN.negacyclic_polymul forward step (algebraic.rs:396, constants.rs:197). */
+int lab_ntt_fwd_batch(lab_ctx *ctx, const uint32_t *in, uint32_t *out, size_t n_polys);
+int lab_ntt_inv_batch(lab_ctx *ctx, const uint32_t *in, uint32_t *out, size_t n_polys);
+int lab_polymul_batch(lab_ctx *ctx, const uint32_t *a, const uint32_t *b, uint32_t *c, size_t n_polys);
+int lab_ntt_fwd_batch_dev(lab_ctx *ctx, const uint32_t *in, uint32_t *out, size_t n_polys);
+int lab_ntt_inv_batch_dev(lab_ctx *ctx, const uint32_t *in, uint32_t *out, size_t n_polys);
+int lab_polymul_batch_dev(lab_ctx *ctx, const uint32_t *a, const uint32_t *b, uint32_t *c, size_t n_polys);
+void lab_ntt_slot_exponents(int out[32]);
+/* polynomial_vec_inner_product (util.rs:496-509), batched: out[b] = <v1[b][0..len), v2[b][0..len)> */
+int lab_inner_product_batch(lab_ctx *ctx, const uint32_t *v1, const uint32_t *v2, size_t n_vecs, size_t len, uint32_t *out);
+/* decompose_polynomial (util.rs:389-442): out[k][p][64], k < exp */
+int lab_decompose(lab_ctx *ctx, const uint32_t *in, size_t n_polys, int64_t base, int64_t exp, uint32_t *out);
+/* poly_norm / vec_poly_norm_squared (util.rs:188-202) as an exact integer */
+int lab_norm_sq(lab_ctx *ctx, const uint32_t *in, size_t n_coeffs, uint64_t *out);
+int lab_norm_sq_dev(lab_ctx *ctx, const uint32_t *in, size_t n_coeffs, uint64_t *out_host);
+/* sigma_inv_vec (util.rs:107-137) */
+int lab_sigma_inv(lab_ctx *ctx, const uint32_t *in, size_t n_polys, uint32_t *out);
+
+/* ---- CRS (structs.rs:27-190) ---- */
+/* n_polys consecutive polynomials whose first coefficient sits at counter base_seed + start
+ * (fetch_next_n / random_oracle_gen / generate_random_coeff, structs.rs:35-45,147-171) */
+int lab_crs_expand(lab_ctx *ctx, const uint8_t seed[32], uint64_t start_lo, uint64_t start_hi, size_t n_polys, uint32_t *out);
+int lab_crs_expand_dev(lab_ctx *ctx, const uint8_t seed[32], uint64_t start_lo, uint64_t start_hi, size_t n_polys, uint32_t *out);
+/* fetch_A_row / fetch_B_ik_row / fetch_C_ijk / fetch_D_ijk (structs.rs:55-144); which = 'A','B','C','D' */
+int lab_crs_fetch(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], int which,
+                  uint64_t i, uint64_t j, uint64_t k, uint64_t row, uint32_t *out);
+/* counter offset of the same (for callers that shard rows themselves) */
+int lab_crs_offset(const lab_constants *c, int which, uint64_t i, uint64_t j, uint64_t k, uint64_t row, uint64_t *lo, uint64_t *hi);
+
+/* ---- prover stages (proofgen.rs) ---- */
+/* S1 inner Ajtai commitments t_i[row] = <A_row, s_i> for rows [row0,row0+nrows) (proofgen.rs:41-49).
+ * T: [R][nrows][64].  Row-sharding across GPUs = disjoint [row0,row0+nrows) per rank. */
+int lab_commit_inner(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], const uint32_t *S,
+                     uint64_t row0, uint64_t nrows, uint32_t *T);
+/* S2 garbage polynomials g_ij = <s_i, s_j>, all R^2 (proofgen.rs:59-70) */
+int lab_gram(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, uint32_t *G);
+/* S4 one JL attempt: p = sum_i Pi_i * coeffs(s_i) exact (proofgen.rs:429-457; util.rs:511-526).
+ * pi: int8[R][256][N*64] in {-1,0,1}.  accepted receives Verifier::valid_projection (verification.rs:568-579). */
+int lab_jl_project(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, const int8_t *pi, int64_t p[LAB_JL_ROWS], int *accepted);
+/* S3 u_1 = sum B_ik dig_k(t_i) + sum_{i<=j} dig_k(g_ij) C_ijk (proofgen.rs:101-153) */
+int lab_commit_outer_u1(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], const uint32_t *T, const uint32_t *G, uint32_t *u1);
+/* S8 u_2 = sum_{i<=j,k<T_1} dig_k(h_ij) D_ijk (proofgen.rs:364-378) */
+int lab_commit_outer_u2(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], const uint32_t *H, uint32_t *u2);
+/* S5 phi''_i = psi phi_i + sum_j omega_j sigma_inv(pi_i^(j)) (proofgen.rs:225-256) */
+int lab_aggregate_phi(lab_ctx *ctx, const lab_constants *c, const uint32_t *phi, const int8_t *pi, uint32_t psi,
+                      const uint32_t omega[LAB_JL_ROWS], uint32_t *phi_pp);
+/* S7 h_ij = (<phi_i,s_j> + <phi_j,s_i>) / 2 (proofgen.rs:320-358) */
+int lab_h_gram(lab_ctx *ctx, const lab_constants *c, const uint32_t *phi_final, const uint32_t *S, uint32_t *H);
+/* S9 z = sum_i c_i s_i (proofgen.rs:380-399) */
+int lab_amortize_z(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, const uint32_t *ch, uint32_t *z);
+
+/* ---- whole proof: Prover::proof_gen (proofgen.rs:30-427) ---- */
+typedef struct {                 /* State (structs.rs:269-286) with K = L = 1 */
+    const uint32_t *phi;         /* [R][N][64] */
+    const uint32_t *a;           /* [R][R][64] symmetric */
+    const uint32_t *b;           /* [64]; b' = b[0] */
+} lab_state;
+
+/* Verifier randomness in the order proof_gen consumes it.  The reference
+ * draws these from thread_rng inside Verifier (verification.rs:441-513,553-566); for bit-exact
+ * parity they are injected. */
+typedef struct {
+    const int8_t *pi;            /* [n_attempts][R][256][N*64] */
+    int n_attempts;              /* 1..6 */
+    uint32_t psi;
+    const uint32_t *omega;       /* [256] */
+    const uint32_t *alpha;       /* [64] */
+    const uint32_t *beta;        /* [64] */
+    const uint32_t *c;           /* [R][64] */
+} lab_challenges;
+
+/* Transcript (structs.rs:192-209), dense; buffers caller-allocated (host). pi_i_all is the accepted
+ * attempt of lab_challenges.pi (lifted -1 -> q-1 by the wrapper), psi/omega/alpha/beta/c are the inputs. */
+typedef struct {
+    uint32_t *u_1;               /* [KAPPA_1][64] */
+    int jl_attempt;
+    int64_t *projection_int;     /* [256] */
+    uint32_t *projection;        /* [256] mod q */
+    uint32_t *b_prime_prime;     /* [64] */
+    uint32_t *u_2;               /* [KAPPA_2][64] */
+    uint32_t *z;                 /* [N][64] */
+    uint32_t *t;                 /* [R][KAPPA][64] */
+    uint32_t *g;                 /* [R][R][64] */
+    uint32_t *h;                 /* [R][R][64] */
+    uint32_t *phi_final;         /* [R][N][64] (extra, may be NULL) */
+    uint64_t norm_sum;           /* exact integer of the verifier's Check 14 (verification.rs:231-267) */
+} lab_transcript;
+
+int lab_prove(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], const uint32_t *S,
+              const lab_state *st, const lab_challenges *ch, lab_transcript *out);
+
+/* Batched independent proofs (BASELINE config 5): statement b uses seeds[b] (32 bytes each) or
+ * seeds[0] when shared_crs != 0.  Arrays are the single-proof layouts concatenated. */
+int lab_prove_batch(lab_ctx *ctx, const lab_constants *c, size_t n_statements, const uint8_t *seeds, int shared_crs,
+                    const uint32_t *S, const lab_state *st, const lab_challenges *ch, lab_transcript *out);
+
+/* ---- device-resident stage API (inputs already in HBM; used for sharded / pipelined proving) ---- */
+/* S_dev: uint32_t[R][N][64] on device.  Prepares the transformed witness inside ctx. */
+int lab_witness_load_dev(lab_ctx *ctx, const lab_constants *c, const uint32_t *S_dev);
+/* rows [row0,row0+nrows) of T for the loaded witness; T_dev: [R][nrows][64] */
+int lab_commit_inner_dev(lab_ctx *ctx, const uint8_t seed[32], uint64_t row0, uint64_t nrows, uint32_t *T_dev);
+int lab_gram_dev(lab_ctx *ctx, uint32_t *G_dev);
+/* i in [i0,i0+ni): partial projection of those witness vectors; p_dev: int64[256] (overwritten) */
+int lab_jl_project_dev(lab_ctx *ctx, const int8_t *pi_dev, uint64_t i0, uint64_t ni, int64_t *p_dev);
+/* z restricted to witness vectors [i0,i0+ni) as exact int64 partial sums are not needed: z is mod q;
+ * z_dev: [N][64] canonical partial (sum over the given i range) */
+int lab_amortize_z_dev(lab_ctx *ctx, const uint32_t *ch_dev, uint64_t i0, uint64_t ni, uint32_t *z_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,869 @@
+// liblabrador_b200.so -- C ABI (include/labrador_b200.h) and host orchestration of the prover path.
+// Host logic restates proofgen.rs:30-427 stage by stage on top of the kernels in lab_kernels.cuh.
+// There is NO CPU fallback: every entry point needs a CUDA device and fails with LAB_ERR_CUDA otherwise.
+#include "../../include/labrador_b200.h"
+#include "lab_kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace lab;
+typedef unsigned __int128 u128;
+
+static thread_local std::string g_create_err;
+
+struct lab_ctx {
+    int device = 0;
+    int sms = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    // bump arena for per-call scratch
+    char *arena = nullptr;
+    size_t arena_size = 0, arena_off = 0, arena_want = 0;
+    std::vector<void *> overflow;
+    // resident witness (device-stage API)
+    lab_constants wc{};
+    const uint32_t *S_dev = nullptr;   // caller-owned
+    uint32_t *What = nullptr;          // owned, [N][R][32]
+    size_t What_bytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return LAB_ERR_CUDA;                                                                     \
+        }                                                                                            \
+    } while (0)
+#define TRY(call)                                                                                    \
+    do {                                                                                             \
+        int s_ = (call);                                                                             \
+        if (s_ != LAB_OK) return s_;                                                                 \
+    } while (0)
+#define FAIL(code, msg)                                                                              \
+    do {                                                                                             \
+        ctx->err = (msg);                                                                            \
+        return (code);                                                                               \
+    } while (0)
+#define LAUNCH(kern, grid, block, ...)                                                               \
+    do {                                                                                             \
+        kern<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__);                                      \
+        ctx->launches++;                                                                             \
+        CK(cudaGetLastError());                                                                      \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// arena
+// ---------------------------------------------------------------------------------------------
+static void arena_reset(lab_ctx *ctx) {
+    for (void *p : ctx->overflow) cudaFree(p);
+    ctx->overflow.clear();
+    if (ctx->arena_want > ctx->arena_size) {
+        if (ctx->arena) cudaFree(ctx->arena);
+        ctx->arena = nullptr;
+        ctx->arena_size = 0;
+        size_t want = ctx->arena_want + (ctx->arena_want >> 3) + (1 << 20);
+        if (cudaMalloc(&ctx->arena, want) == cudaSuccess) ctx->arena_size = want;
+        else cudaGetLastError();
+    }
+    ctx->arena_off = 0;
+    ctx->arena_want = 0;
+}
+template <typename T>
+static int arena_alloc(lab_ctx *ctx, size_t count, T **out) {
+    size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    ctx->arena_want += bytes;
+    if (ctx->arena_off + bytes <= ctx->arena_size) {
+        *out = reinterpret_cast<T *>(ctx->arena + ctx->arena_off);
+        ctx->arena_off += bytes;
+        return LAB_OK;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        ctx->err = "device allocation of " + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e);
+        return LAB_ERR_ALLOC;
+    }
+    ctx->overflow.push_back(p);
+    *out = reinterpret_cast<T *>(p);
+    return LAB_OK;
+}
+struct CallScope {   // every host-pointer API call: fresh arena, bound device
+    lab_ctx *ctx;
+    explicit CallScope(lab_ctx *c) : ctx(c) { cudaSetDevice(c->device); arena_reset(c); }
+};
+
+static LabSeed make_seed(const uint8_t seed[32]) {
+    LabSeed s;
+    for (int l = 0; l < 4; l++) {
+        uint64_t v = 0;
+        for (int b = 0; b < 8; b++) v = (v << 8) | seed[(3 - l) * 8 + b];
+        s.limb[l] = v;
+    }
+    return s;
+}
+static unsigned grid_for(size_t work_items, unsigned per_block, unsigned cap) {
+    size_t g = (work_items + per_block - 1) / per_block;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (unsigned)g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+extern "C" int lab_version(void) { return 100; }
+
+extern "C" int lab_ctx_create(int device, lab_ctx **out) {
+    if (!out) return LAB_ERR_PARAMS;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        g_create_err = std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0") +
+                       "); liblabrador_b200 has no CPU fallback";
+        cudaGetLastError();
+        return LAB_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { g_create_err = "device index out of range"; return LAB_ERR_PARAMS; }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_err = cudaGetErrorString(e); return LAB_ERR_CUDA; }
+    lab_ctx *ctx = new lab_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sms = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_err = cudaGetErrorString(e);
+        delete ctx;
+        return LAB_ERR_CUDA;
+    }
+    *out = ctx;
+    return LAB_OK;
+}
+extern "C" void lab_ctx_destroy(lab_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (void *p : ctx->overflow) cudaFree(p);
+    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->What) cudaFree(ctx->What);
+    if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+extern "C" const char *lab_last_error(const lab_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+extern "C" int lab_sync(lab_ctx *ctx) { CK(cudaStreamSynchronize(ctx->stream)); return LAB_OK; }
+extern "C" int lab_malloc(lab_ctx *ctx, size_t bytes, void **dptr) {
+    cudaSetDevice(ctx->device);
+    CK(cudaMalloc(dptr, bytes ? bytes : 1));
+    return LAB_OK;
+}
+extern "C" int lab_free(lab_ctx *ctx, void *dptr) { cudaSetDevice(ctx->device); CK(cudaFree(dptr)); return LAB_OK; }
+extern "C" int lab_memcpy_h2d(lab_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return LAB_OK;
+}
+extern "C" int lab_memcpy_d2h(lab_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return LAB_OK;
+}
+extern "C" int lab_timer_start(lab_ctx *ctx) {
+    if (!ctx->ev0) { CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1)); }
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    return LAB_OK;
+}
+extern "C" int lab_timer_stop(lab_ctx *ctx, double *elapsed_ms) {
+    if (!ctx->ev0) FAIL(LAB_ERR_PARAMS, "timer not started");
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (elapsed_ms) *elapsed_ms = (double)ms;
+    return LAB_OK;
+}
+extern "C" void *lab_stream(lab_ctx *ctx) { return (void *)ctx->stream; }
+extern "C" uint64_t lab_kernel_launches(const lab_ctx *ctx) { return ctx->launches; }
+
+// ---------------------------------------------------------------------------------------------
+// RuntimeConstants::new (constants.rs:234-264): same f64 operation order, `as i128` saturating casts
+// ---------------------------------------------------------------------------------------------
+static int64_t sat_cast(double x, bool &bad) {
+    if (!(x == x)) { bad = true; return 0; }
+    if (x >= 9.2e18) { bad = true; return INT64_MAX; }
+    if (x <= -9.2e18) { bad = true; return INT64_MIN; }
+    return (int64_t)x;
+}
+extern "C" int lab_runtime_constants(uint64_t N, uint64_t R, lab_constants *o) {
+    if (!o || N == 0 || R == 0) return LAB_ERR_PARAMS;
+    const double TAU = 71.0, q = (double)LAB_Q;
+    bool bad = false;
+    std::memset(o, 0, sizeof *o);
+    o->N = N; o->R = R;
+    o->KAPPA = o->KAPPA_1 = o->KAPPA_2 = N * LAB_D;
+    o->BETA_BOUND = sat_cast(std::floor(std::sqrt(30.0 / 128.0) * q / 125.0), bad);
+    o->STD = (double)o->BETA_BOUND / std::sqrt((double)(R * N * LAB_D));
+    o->B = sat_cast(std::round(std::sqrt(std::sqrt(12. * (double)R * TAU) * o->STD)), bad);
+    o->T_1 = sat_cast(std::round(std::log2(q) / std::log2((double)o->B)), bad);
+    o->B_1 = sat_cast(std::pow(q, 1.0 / (double)o->T_1), bad);
+    o->T_2 = sat_cast(std::round(std::log2(std::sqrt(24. * (double)(N * LAB_D)) * (o->STD * o->STD)) / std::log2((double)o->B)), bad);
+    o->B_2 = sat_cast(std::round(std::pow(std::sqrt((double)(24 * (N * LAB_D))) * (o->STD * o->STD), 1.0 / (double)o->T_2)), bad);
+    const double b1 = (double)o->B_1, b2 = (double)o->B_2, t1 = (double)o->T_1, t2 = (double)o->T_2, r = (double)R;
+    o->GAMMA = (double)(o->BETA_BOUND * o->BETA_BOUND) * TAU;
+    o->GAMMA_1 = ((b1 * b1 * t1) / 12.0) * r * (double)o->KAPPA * (double)LAB_D + ((b2 * b2 * t2) / 12.0) * ((r * r + r) / 2.0) * (double)LAB_D;
+    o->GAMMA_2 = ((b1 * b1 * t1) / 12.0) * ((r * r + r) / 2.0) * (double)LAB_D;
+    const double bb = (double)o->B;
+    o->BETA_PRIME = (2.0 / (bb * bb)) * o->GAMMA + o->GAMMA_1 + o->GAMMA_2;
+    if (bad || o->B < 2 || o->T_1 <= 0 || o->B_1 < 2 || o->T_2 <= 0 || o->B_2 < 2 || o->T_1 > 64 || o->T_2 > 64) o->degenerate = 1;
+    return o->degenerate ? LAB_ERR_PARAMS : LAB_OK;
+}
+
+// CRS offsets (structs.rs:55-144), literal including the overlapping regions
+static u128 off_A(const lab_constants *c, uint64_t row) { return (u128)row * (u128)(c->N * LAB_D); }
+static u128 off_B(const lab_constants *c, uint64_t i, uint64_t k, uint64_t row) {
+    return (u128)(c->KAPPA * c->N * LAB_D) + (u128)(i * (uint64_t)c->T_1 + k) * (u128)(c->KAPPA_1 * c->KAPPA) + (u128)row * (u128)(c->KAPPA * LAB_D);
+}
+static uint64_t sum_pairs(const lab_constants *c, uint64_t i) { return i > 0 ? i * c->R - i * (i - 1) / 2 : 0; }
+static u128 end_B(const lab_constants *c) {
+    return (u128)(c->KAPPA * c->N * LAB_D) + (u128)(c->R * (uint64_t)c->T_1) * (u128)(c->KAPPA_1 * c->KAPPA) * LAB_D;
+}
+static u128 off_C(const lab_constants *c, uint64_t i, uint64_t j, uint64_t k) {
+    return end_B(c) + (u128)(k + (uint64_t)c->T_1 * (sum_pairs(c, i) + (j - i))) * (u128)(c->KAPPA_2 * LAB_D);
+}
+static u128 off_D(const lab_constants *c, uint64_t i, uint64_t j, uint64_t k) {
+    return end_B(c) + (u128)(c->R * (c->R + 1) / 2) * (u128)(c->KAPPA_2 * LAB_D) +
+           (u128)(k + (uint64_t)c->T_1 * (sum_pairs(c, i) + (j - i))) * (u128)(c->KAPPA_2 * LAB_D);
+}
+extern "C" int lab_crs_offset(const lab_constants *c, int which, uint64_t i, uint64_t j, uint64_t k, uint64_t row, uint64_t *lo, uint64_t *hi) {
+    if (!c || !lo || !hi) return LAB_ERR_PARAMS;
+    u128 o;
+    switch (which) {
+        case 'A': o = off_A(c, row); break;
+        case 'B': o = off_B(c, i, k, row); break;
+        case 'C': if (j < i) return LAB_ERR_PARAMS; o = off_C(c, i, j, k); break;
+        case 'D': if (j < i) return LAB_ERR_PARAMS; o = off_D(c, i, j, k); break;
+        default: return LAB_ERR_PARAMS;
+    }
+    *lo = (uint64_t)o; *hi = (uint64_t)(o >> 64);
+    return LAB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-side building blocks (all on ctx->stream, device pointers)
+// ---------------------------------------------------------------------------------------------
+static int d_fwd_hat(lab_ctx *ctx, const uint32_t *in, uint32_t *out, size_t n, size_t inner, size_t outer) {
+    if (!n) return LAB_OK;
+    LAUNCH(k_fwd_hat, grid_for(n, 8, ctx->sms * 16), 256, in, out, n, inner, outer);
+    return LAB_OK;
+}
+static int d_inv_hat(lab_ctx *ctx, const uint32_t *in, uint32_t *out, size_t n) {
+    if (!n) return LAB_OK;
+    LAUNCH(k_inv_hat, grid_for(n, 8, ctx->sms * 16), 256, in, out, n);
+    return LAB_OK;
+}
+static int d_commit_inner(lab_ctx *ctx, const LabSeed &seed, const uint32_t *What, uint64_t N, uint64_t R, uint64_t row0, uint64_t nrows, uint32_t *T) {
+    if (!nrows) return LAB_OK;
+    if (N >= (1ull << 32) || R >= (1ull << 32)) FAIL(LAB_ERR_PARAMS, "N, R must be < 2^32");
+    {   // counters of A stay below 2^64 (structs.rs:62): (row * N + n) * 64
+        u128 last = ((u128)(row0 + nrows) * N + N) * 64;
+        if (last >> 64) FAIL(LAB_ERR_PARAMS, "A counter exceeds 64 bits");
+    }
+    const unsigned grid = (unsigned)((nrows + KA_RT - 1) / KA_RT);
+    const int IC = R > 32 ? 8 : (R > 16 ? 4 : (R > 8 ? 2 : 1));
+    for (uint64_t ib = 0; ib < R; ib += 8ull * IC) {
+        switch (IC) {
+            case 8: LAUNCH(k_commit_inner<8>, grid, 256, seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
+            case 4: LAUNCH(k_commit_inner<4>, grid, 256, seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
+            case 2: LAUNCH(k_commit_inner<2>, grid, 256, seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
+            default: LAUNCH(k_commit_inner<1>, grid, 256, seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
+        }
+    }
+    return LAB_OK;
+}
+
+struct MvSeg {
+    u128 base;
+    uint64_t row_stride, sp, sk;
+    uint32_t nk, count, vec_off;
+};
+// out[x] for x in [x0, x0 + n_rows): builds the item list, runs K_MV and the finishing kernel
+static int d_crs_matvec(lab_ctx *ctx, const LabSeed &seed, const std::vector<MvSeg> &segs, uint64_t x0, uint64_t n_rows,
+                        const uint32_t *V, uint32_t *out) {
+    if (!n_rows) return LAB_OK;
+    uint64_t total_polys = 0;
+    for (const MvSeg &s : segs) total_polys += s.count;
+    if (!total_polys) { CK(cudaMemsetAsync(out, 0, n_rows * 64 * sizeof(uint32_t), ctx->stream)); return LAB_OK; }
+    // chunk so that there are ~24 warps of work per SM sub-partition, chunks between 4 and 2048 polys
+    const uint64_t target_items = (uint64_t)ctx->sms * 4 * 24;
+    uint64_t ch = (total_polys * n_rows + target_items - 1) / target_items;
+    if (ch < 4) ch = 4;
+    if (ch > 2048) ch = 2048;
+    std::vector<MvItem> items;
+    for (const MvSeg &s : segs)
+        for (uint32_t y = 0; y < s.count; y += (uint32_t)ch) {
+            MvItem it;
+            it.base_lo = (uint64_t)s.base; it.base_hi = (uint64_t)(s.base >> 64);
+            it.row_stride = s.row_stride; it.sp = s.sp; it.sk = s.sk; it.nk = s.nk;
+            it.y0 = y; it.cnt = (uint32_t)std::min<uint64_t>(ch, s.count - y); it.vec_off = s.vec_off;
+            items.push_back(it);
+        }
+    const uint32_t ipr = (uint32_t)items.size();
+    MvItem *d_items;
+    uint32_t *partial;
+    TRY(arena_alloc(ctx, items.size(), &d_items));
+    TRY(arena_alloc(ctx, (size_t)n_rows * ipr * 32, &partial));
+    // pageable source: cudaMemcpyAsync copies it to a staging buffer before returning
+    CK(cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(MvItem), cudaMemcpyHostToDevice, ctx->stream));
+    const uint64_t warps = n_rows * ipr;
+    LAUNCH(k_crs_matvec, (unsigned)((warps + 7) / 8), 256, seed, d_items, ipr, n_rows, x0, V, partial);
+    LAUNCH(k_finish_rows, (unsigned)((n_rows + 7) / 8), 256, partial, ipr, n_rows, out);
+    return LAB_OK;
+}
+
+__global__ void k_gather_pairs(const uint32_t *__restrict__ M, uint32_t R, uint32_t *__restrict__ out) {
+    // out[pairidx(i,j)][64] = M[i][j][64] for i <= j in the reference's enumeration order (structs.rs:101-106)
+    uint32_t i = blockIdx.x, j = blockIdx.y;
+    if (j < i) return;
+    uint32_t pidx = (i > 0 ? i * R - i * (i - 1) / 2 : 0) + (j - i);
+    out[(size_t)pidx * 64 + threadIdx.x] = M[((size_t)i * R + j) * 64 + threadIdx.x];
+}
+
+// u_1 (proofgen.rs:101-153) from device T [R][KAPPA][64] and G [R][R][64]
+static int d_outer_u1(lab_ctx *ctx, const lab_constants *c, const LabSeed &seed, const uint32_t *dT, const uint32_t *dG, uint32_t *du1) {
+    const uint64_t R = c->R, K = c->KAPPA, K1 = c->KAPPA_1, K2 = c->KAPPA_2, T1 = (uint64_t)c->T_1, T2 = (uint64_t)c->T_2;
+    const uint64_t npairs = R * (R + 1) / 2;
+    if (R * T1 * K + npairs * T2 >= (1ull << 32)) FAIL(LAB_ERR_PARAMS, "u_1 vector too long for 32-bit indexing");
+    uint32_t *V, *Gp;
+    TRY(arena_alloc(ctx, (R * T1 * K + npairs * T2) * 32, &V));
+    TRY(arena_alloc(ctx, npairs * 64, &Gp));
+    LAUNCH(k_decomp_fwd, grid_for(R * K, 8, ctx->sms * 16), 256, dT, V, (size_t)(R * K), (size_t)K, (uint32_t)c->B_1, (int)T1);
+    LAUNCH(k_gather_pairs, dim3((unsigned)R, (unsigned)R), 64, dG, (uint32_t)R, Gp);
+    LAUNCH(k_decomp_fwd, grid_for(npairs, 8, ctx->sms * 16), 256, Gp, V + R * T1 * K * 32, (size_t)npairs, (size_t)1, (uint32_t)c->B_2, (int)T2);
+    std::vector<MvSeg> segs;
+    for (uint64_t i = 0; i < R; i++)
+        for (uint64_t k = 0; k < T1; k++)
+            segs.push_back(MvSeg{off_B(c, i, k, 0), K * LAB_D, LAB_D, 0, 1u, (uint32_t)K, (uint32_t)((i * T1 + k) * K)});
+    segs.push_back(MvSeg{off_C(c, 0, 0, 0), LAB_D, T1 * K2 * LAB_D, K2 * LAB_D, (uint32_t)T2, (uint32_t)(npairs * T2), (uint32_t)(R * T1 * K)});
+    return d_crs_matvec(ctx, seed, segs, 0, K1, V, du1);
+}
+// u_2 (proofgen.rs:364-378) from device H [R][R][64]
+static int d_outer_u2(lab_ctx *ctx, const lab_constants *c, const LabSeed &seed, const uint32_t *dH, uint32_t *du2) {
+    const uint64_t R = c->R, K2 = c->KAPPA_2, T1 = (uint64_t)c->T_1;
+    const uint64_t npairs = R * (R + 1) / 2;
+    uint32_t *V, *Hp;
+    TRY(arena_alloc(ctx, npairs * T1 * 32, &V));
+    TRY(arena_alloc(ctx, npairs * 64, &Hp));
+    LAUNCH(k_gather_pairs, dim3((unsigned)R, (unsigned)R), 64, dH, (uint32_t)R, Hp);
+    LAUNCH(k_decomp_fwd, grid_for(npairs, 8, ctx->sms * 16), 256, Hp, V, (size_t)npairs, (size_t)1, (uint32_t)c->B_1, (int)T1);
+    std::vector<MvSeg> segs;
+    segs.push_back(MvSeg{off_D(c, 0, 0, 0), LAB_D, T1 * K2 * LAB_D, K2 * LAB_D, (uint32_t)T1, (uint32_t)(npairs * T1), 0u});
+    return d_crs_matvec(ctx, seed, segs, 0, K2, V, du2);
+}
+static int d_gram(lab_ctx *ctx, const uint32_t *What, uint64_t N, uint64_t R, uint32_t *Ghat /* scratch R*R*32 */, uint32_t *dG) {
+    LAUNCH(k_ip_hat, (unsigned)(R * R), 256, What, (size_t)R, (size_t)1, What, (size_t)R, (size_t)1, (size_t)N, (size_t)R, 1u, 0, Ghat);
+    return d_inv_hat(ctx, Ghat, dG, R * R);
+}
+static int d_jl(lab_ctx *ctx, const int8_t *dPi, const uint32_t *dS, uint64_t ND, uint64_t i0, uint64_t ni, unsigned long long *dp) {
+    CK(cudaMemsetAsync(dp, 0, LAB_JL_ROWS * sizeof(unsigned long long), ctx->stream));
+    if (!ni) return LAB_OK;
+    const size_t chunks = (ND + JL_CH - 1) / JL_CH;
+    LAUNCH(k_jl, (unsigned)(ni * chunks), 256, dPi, dS, (size_t)ND, (size_t)i0, dp);
+    return LAB_OK;
+}
+// Verifier::valid_projection (verification.rs:568-579), literal f64: sqrt(sum p^2) <= sqrt(128) * beta
+static bool valid_projection(const lab_constants *c, const int64_t *p) {
+    __int128 ss = 0;
+    for (int j = 0; j < LAB_JL_ROWS; j++) ss += (__int128)p[j] * p[j];
+    return std::sqrt((double)ss) <= std::sqrt(128.) * (double)c->BETA_BOUND;
+}
+static int check_consts(lab_ctx *ctx, const lab_constants *c, bool need_digits) {
+    if (!c || c->N == 0 || c->R == 0) FAIL(LAB_ERR_PARAMS, "bad constants");
+    if (c->KAPPA != c->N * LAB_D || c->KAPPA_1 != c->KAPPA || c->KAPPA_2 != c->KAPPA) FAIL(LAB_ERR_PARAMS, "KAPPA must equal N*D (constants.rs:237-239)");
+    if (need_digits && (c->degenerate || c->B < 2 || c->B_1 < 2 || c->B_2 < 2 || c->T_1 <= 0 || c->T_2 <= 0))
+        FAIL(LAB_ERR_PARAMS, "degenerate RuntimeConstants: decomposition would not terminate in the reference (SURVEY F8)");
+    return LAB_OK;
+}
+template <typename T>
+static int upload(lab_ctx *ctx, const T *host, size_t count, T **dev) {
+    TRY(arena_alloc(ctx, count, dev));
+    CK(cudaMemcpyAsync(*dev, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return LAB_OK;
+}
+template <typename T>
+static int download(lab_ctx *ctx, T *host, const T *dev, size_t count) {
+    CK(cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    return LAB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ring primitives
+// ---------------------------------------------------------------------------------------------
+static const int SLOT_EXP[32] = LAB_SLOT_EXP_INIT;
+extern "C" void lab_ntt_slot_exponents(int out[32]) { std::memcpy(out, SLOT_EXP, sizeof SLOT_EXP); }
+
+extern "C" int lab_ntt_fwd_batch_dev(lab_ctx *ctx, const uint32_t *in, uint32_t *out, size_t n) {
+    if (!n) return LAB_OK;
+    LAUNCH(k_ntt_fwd_regs, grid_for(n, NTT_TPB, ctx->sms * 32), NTT_TPB, in, out, n);
+    return LAB_OK;
+}
+extern "C" int lab_ntt_inv_batch_dev(lab_ctx *ctx, const uint32_t *in, uint32_t *out, size_t n) {
+    if (!n) return LAB_OK;
+    LAUNCH(k_ntt_inv_regs, grid_for(n, NTT_TPB, ctx->sms * 32), NTT_TPB, in, out, n);
+    return LAB_OK;
+}
+extern "C" int lab_polymul_batch_dev(lab_ctx *ctx, const uint32_t *a, const uint32_t *b, uint32_t *c, size_t n) {
+    if (!n) return LAB_OK;
+    LAUNCH(k_polymul_regs, grid_for(n, NTT_TPB, ctx->sms * 32), NTT_TPB, a, b, c, n);
+    return LAB_OK;
+}
+extern "C" int lab_ntt_fwd_batch(lab_ctx *ctx, const uint32_t *in, uint32_t *out, size_t n) {
+    CallScope cs(ctx);
+    if (!n) return LAB_OK;
+    uint32_t *di, *dout;
+    TRY(upload(ctx, in, n * 64, &di));
+    TRY(arena_alloc(ctx, n * 64, &dout));
+    TRY(lab_ntt_fwd_batch_dev(ctx, di, dout, n));
+    TRY(download(ctx, out, dout, n * 64));
+    return lab_sync(ctx);
+}
+extern "C" int lab_ntt_inv_batch(lab_ctx *ctx, const uint32_t *in, uint32_t *out, size_t n) {
+    CallScope cs(ctx);
+    if (!n) return LAB_OK;
+    uint32_t *di, *dout;
+    TRY(upload(ctx, in, n * 64, &di));
+    TRY(arena_alloc(ctx, n * 64, &dout));
+    TRY(lab_ntt_inv_batch_dev(ctx, di, dout, n));
+    TRY(download(ctx, out, dout, n * 64));
+    return lab_sync(ctx);
+}
+extern "C" int lab_polymul_batch(lab_ctx *ctx, const uint32_t *a, const uint32_t *b, uint32_t *c, size_t n) {
+    CallScope cs(ctx);
+    if (!n) return LAB_OK;
+    uint32_t *da, *db, *dc;
+    TRY(upload(ctx, a, n * 64, &da));
+    TRY(upload(ctx, b, n * 64, &db));
+    TRY(arena_alloc(ctx, n * 64, &dc));
+    TRY(lab_polymul_batch_dev(ctx, da, db, dc, n));
+    TRY(download(ctx, c, dc, n * 64));
+    return lab_sync(ctx);
+}
+extern "C" int lab_inner_product_batch(lab_ctx *ctx, const uint32_t *v1, const uint32_t *v2, size_t n_vecs, size_t len, uint32_t *out) {
+    CallScope cs(ctx);
+    if (!n_vecs) return LAB_OK;
+    if (!len) { std::memset(out, 0, n_vecs * 64 * sizeof(uint32_t)); return LAB_OK; }   // Rq::new(vec![]) (util.rs:503)
+    uint32_t *d1, *d2, *h1, *h2, *oh, *dout;
+    TRY(upload(ctx, v1, n_vecs * len * 64, &d1));
+    TRY(upload(ctx, v2, n_vecs * len * 64, &d2));
+    TRY(arena_alloc(ctx, n_vecs * len * 32, &h1));
+    TRY(arena_alloc(ctx, n_vecs * len * 32, &h2));
+    TRY(arena_alloc(ctx, n_vecs * 32, &oh));
+    TRY(arena_alloc(ctx, n_vecs * 64, &dout));
+    TRY(d_fwd_hat(ctx, d1, h1, n_vecs * len, 0, 0));
+    TRY(d_fwd_hat(ctx, d2, h2, n_vecs * len, 0, 0));
+    // vector b occupies hats [b*len, (b+1)*len): n stride 1, vector stride len, diagonal pairing
+    LAUNCH(k_ip_hat, (unsigned)n_vecs, 256, h1, (size_t)1, len, h2, (size_t)1, len, len, (size_t)0, 1u, 2, oh);
+    TRY(d_inv_hat(ctx, oh, dout, n_vecs));
+    TRY(download(ctx, out, dout, n_vecs * 64));
+    return lab_sync(ctx);
+}
+extern "C" int lab_decompose(lab_ctx *ctx, const uint32_t *in, size_t n_polys, int64_t base, int64_t exp, uint32_t *out) {
+    CallScope cs(ctx);
+    if (base < 2 || exp <= 0 || base > 0x7fffffff || exp > 64) FAIL(LAB_ERR_PARAMS, "decompose: base < 2 never terminates in the reference (util.rs:410-417)");
+    if (!n_polys) return LAB_OK;
+    uint32_t *di, *dout;
+    TRY(upload(ctx, in, n_polys * 64, &di));
+    TRY(arena_alloc(ctx, n_polys * 64 * (size_t)exp, &dout));
+    LAUNCH(k_decompose, grid_for(n_polys * 64, 256, ctx->sms * 16), 256, di, dout, n_polys * 64, (uint32_t)base, (int)exp);
+    TRY(download(ctx, out, dout, n_polys * 64 * (size_t)exp));
+    return lab_sync(ctx);
+}
+extern "C" int lab_norm_sq_dev(lab_ctx *ctx, const uint32_t *in, size_t n, uint64_t *out_host) {
+    unsigned long long *d;
+    TRY(arena_alloc(ctx, 1, &d));
+    CK(cudaMemsetAsync(d, 0, sizeof *d, ctx->stream));
+    if (n) LAUNCH(k_norm_sq, grid_for(n, 256 * 8, ctx->sms * 8), 256, in, n, d);
+    CK(cudaMemcpyAsync(out_host, d, sizeof *d, cudaMemcpyDeviceToHost, ctx->stream));
+    return lab_sync(ctx);
+}
+extern "C" int lab_norm_sq(lab_ctx *ctx, const uint32_t *in, size_t n, uint64_t *out) {
+    CallScope cs(ctx);
+    uint32_t *di = nullptr;
+    if (n) TRY(upload(ctx, in, n, &di));
+    return lab_norm_sq_dev(ctx, di, n, out);
+}
+extern "C" int lab_sigma_inv(lab_ctx *ctx, const uint32_t *in, size_t n_polys, uint32_t *out) {
+    CallScope cs(ctx);
+    if (!n_polys) return LAB_OK;
+    uint32_t *di, *dout;
+    TRY(upload(ctx, in, n_polys * 64, &di));
+    TRY(arena_alloc(ctx, n_polys * 64, &dout));
+    LAUNCH(k_sigma_inv, grid_for(n_polys * 64, 256, ctx->sms * 16), 256, di, dout, n_polys * 64);
+    TRY(download(ctx, out, dout, n_polys * 64));
+    return lab_sync(ctx);
+}
+
+// ---------------------------------------------------------------------------------------------
+// CRS
+// ---------------------------------------------------------------------------------------------
+extern "C" int lab_crs_expand_dev(lab_ctx *ctx, const uint8_t seed[32], uint64_t start_lo, uint64_t start_hi, size_t n_polys, uint32_t *out) {
+    if (!n_polys) return LAB_OK;
+    const size_t nc = n_polys * 64;
+    LAUNCH(k_crs_expand, grid_for(nc, 512, ctx->sms * 16), 256, make_seed(seed), start_lo, start_hi, nc, out);
+    return LAB_OK;
+}
+extern "C" int lab_crs_expand(lab_ctx *ctx, const uint8_t seed[32], uint64_t start_lo, uint64_t start_hi, size_t n_polys, uint32_t *out) {
+    CallScope cs(ctx);
+    if (!n_polys) return LAB_OK;
+    uint32_t *dout;
+    TRY(arena_alloc(ctx, n_polys * 64, &dout));
+    TRY(lab_crs_expand_dev(ctx, seed, start_lo, start_hi, n_polys, dout));
+    TRY(download(ctx, out, dout, n_polys * 64));
+    return lab_sync(ctx);
+}
+extern "C" int lab_crs_fetch(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], int which, uint64_t i, uint64_t j, uint64_t k,
+                             uint64_t row, uint32_t *out) {
+    TRY(check_consts(ctx, c, which != 'A'));
+    uint64_t lo, hi;
+    if (lab_crs_offset(c, which, i, j, k, row, &lo, &hi) != LAB_OK) FAIL(LAB_ERR_PARAMS, "bad CRS selector");
+    size_t n = which == 'A' ? c->N : (which == 'B' ? c->KAPPA : c->KAPPA_2);
+    return lab_crs_expand(ctx, seed, lo, hi, n, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// stages, host-pointer API
+// ---------------------------------------------------------------------------------------------
+static int load_witness(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, uint32_t **dS, uint32_t **What) {
+    const size_t n = c->R * c->N;
+    TRY(upload(ctx, S, n * 64, dS));
+    TRY(arena_alloc(ctx, n * 32, What));
+    return d_fwd_hat(ctx, *dS, *What, n, c->N, c->R);     // p = i*N + n  ->  n*R + i
+}
+extern "C" int lab_commit_inner(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], const uint32_t *S, uint64_t row0, uint64_t nrows, uint32_t *T) {
+    CallScope cs(ctx);
+    TRY(check_consts(ctx, c, false));
+    if (row0 + nrows > c->KAPPA) FAIL(LAB_ERR_SHAPE, "row range exceeds KAPPA");
+    if (!nrows) return LAB_OK;
+    uint32_t *dS, *What, *dT;
+    TRY(load_witness(ctx, c, S, &dS, &What));
+    TRY(arena_alloc(ctx, c->R * nrows * 64, &dT));
+    TRY(d_commit_inner(ctx, make_seed(seed), What, c->N, c->R, row0, nrows, dT));
+    TRY(download(ctx, T, dT, c->R * nrows * 64));
+    return lab_sync(ctx);
+}
+extern "C" int lab_gram(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, uint32_t *G) {
+    CallScope cs(ctx);
+    TRY(check_consts(ctx, c, false));
+    uint32_t *dS, *What, *Ghat, *dG;
+    TRY(load_witness(ctx, c, S, &dS, &What));
+    TRY(arena_alloc(ctx, c->R * c->R * 32, &Ghat));
+    TRY(arena_alloc(ctx, c->R * c->R * 64, &dG));
+    TRY(d_gram(ctx, What, c->N, c->R, Ghat, dG));
+    TRY(download(ctx, G, dG, c->R * c->R * 64));
+    return lab_sync(ctx);
+}
+extern "C" int lab_jl_project(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, const int8_t *pi, int64_t p[LAB_JL_ROWS], int *accepted) {
+    CallScope cs(ctx);
+    TRY(check_consts(ctx, c, false));
+    const uint64_t ND = c->N * LAB_D;
+    uint32_t *dS;
+    int8_t *dPi;
+    unsigned long long *dp;
+    TRY(upload(ctx, S, c->R * ND, &dS));
+    TRY(upload(ctx, pi, c->R * LAB_JL_ROWS * ND, &dPi));
+    TRY(arena_alloc(ctx, LAB_JL_ROWS, &dp));
+    TRY(d_jl(ctx, dPi, dS, ND, 0, c->R, dp));
+    CK(cudaMemcpyAsync(p, dp, LAB_JL_ROWS * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(lab_sync(ctx));
+    if (accepted) *accepted = valid_projection(c, p) ? 1 : 0;
+    return LAB_OK;
+}
+extern "C" int lab_commit_outer_u1(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], const uint32_t *T, const uint32_t *G, uint32_t *u1) {
+    CallScope cs(ctx);
+    TRY(check_consts(ctx, c, true));
+    uint32_t *dT, *dG, *du1;
+    TRY(upload(ctx, T, c->R * c->KAPPA * 64, &dT));
+    TRY(upload(ctx, G, c->R * c->R * 64, &dG));
+    TRY(arena_alloc(ctx, c->KAPPA_1 * 64, &du1));
+    TRY(d_outer_u1(ctx, c, make_seed(seed), dT, dG, du1));
+    TRY(download(ctx, u1, du1, c->KAPPA_1 * 64));
+    return lab_sync(ctx);
+}
+extern "C" int lab_commit_outer_u2(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], const uint32_t *H, uint32_t *u2) {
+    CallScope cs(ctx);
+    TRY(check_consts(ctx, c, true));
+    uint32_t *dH, *du2;
+    TRY(upload(ctx, H, c->R * c->R * 64, &dH));
+    TRY(arena_alloc(ctx, c->KAPPA_2 * 64, &du2));
+    TRY(d_outer_u2(ctx, c, make_seed(seed), dH, du2));
+    TRY(download(ctx, u2, du2, c->KAPPA_2 * 64));
+    return lab_sync(ctx);
+}
+static int d_aggregate_phi(lab_ctx *ctx, const lab_constants *c, const uint32_t *dphi, const int8_t *dPi, uint32_t psi, const uint32_t *domega, uint32_t *dpp) {
+    const uint64_t ND = c->N * LAB_D, total = c->R * ND;
+    uint32_t *v;
+    TRY(arena_alloc(ctx, total, &v));
+    LAUNCH(k_piT_omega, (unsigned)((total + 255) / 256), 256, dPi, domega, (size_t)total, (size_t)ND, v);
+    LAUNCH(k_phi_pp, (unsigned)((total + 255) / 256), 256, dphi, v, psi % LAB_Q, (size_t)total, dpp);
+    return LAB_OK;
+}
+extern "C" int lab_aggregate_phi(lab_ctx *ctx, const lab_constants *c, const uint32_t *phi, const int8_t *pi, uint32_t psi,
+                                 const uint32_t omega[LAB_JL_ROWS], uint32_t *phi_pp) {
+    CallScope cs(ctx);
+    TRY(check_consts(ctx, c, false));
+    const uint64_t ND = c->N * LAB_D;
+    uint32_t *dphi, *dom, *dpp;
+    int8_t *dPi;
+    TRY(upload(ctx, phi, c->R * ND, &dphi));
+    TRY(upload(ctx, pi, c->R * LAB_JL_ROWS * ND, &dPi));
+    TRY(upload(ctx, omega, (size_t)LAB_JL_ROWS, &dom));
+    TRY(arena_alloc(ctx, c->R * ND, &dpp));
+    TRY(d_aggregate_phi(ctx, c, dphi, dPi, psi, dom, dpp));
+    TRY(download(ctx, phi_pp, dpp, c->R * ND));
+    return lab_sync(ctx);
+}
+static int d_h_gram(lab_ctx *ctx, const uint32_t *PFhat, const uint32_t *What, uint64_t N, uint64_t R, uint32_t *Hhat, uint32_t *dH) {
+    // 2^-1 = 2^(Q-2) = 4096 (proofgen.rs:341-346)
+    LAUNCH(k_ip_hat, (unsigned)(R * R), 256, PFhat, (size_t)R, (size_t)1, What, (size_t)R, (size_t)1, (size_t)N, (size_t)R, 4096u, 1, Hhat);
+    return d_inv_hat(ctx, Hhat, dH, R * R);
+}
+extern "C" int lab_h_gram(lab_ctx *ctx, const lab_constants *c, const uint32_t *phi_final, const uint32_t *S, uint32_t *H) {
+    CallScope cs(ctx);
+    TRY(check_consts(ctx, c, false));
+    uint32_t *dS, *What, *dP, *PFhat, *Hhat, *dH;
+    TRY(load_witness(ctx, c, S, &dS, &What));
+    TRY(load_witness(ctx, c, phi_final, &dP, &PFhat));
+    TRY(arena_alloc(ctx, c->R * c->R * 32, &Hhat));
+    TRY(arena_alloc(ctx, c->R * c->R * 64, &dH));
+    TRY(d_h_gram(ctx, PFhat, What, c->N, c->R, Hhat, dH));
+    TRY(download(ctx, H, dH, c->R * c->R * 64));
+    return lab_sync(ctx);
+}
+static int d_amortize(lab_ctx *ctx, const uint32_t *Chat, const uint32_t *What, uint64_t N, uint64_t R, uint64_t i0, uint64_t ni, uint32_t *zhat, uint32_t *dz) {
+    LAUNCH(k_amortize, grid_for(N, 8, ctx->sms * 16), 256, Chat, What, (size_t)N, (size_t)R, (size_t)i0, (size_t)ni, zhat);
+    return d_inv_hat(ctx, zhat, dz, N);
+}
+extern "C" int lab_amortize_z(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, const uint32_t *ch, uint32_t *z) {
+    CallScope cs(ctx);
+    TRY(check_consts(ctx, c, false));
+    uint32_t *dS, *What, *dc, *Chat, *zhat, *dz;
+    TRY(load_witness(ctx, c, S, &dS, &What));
+    TRY(upload(ctx, ch, c->R * 64, &dc));
+    TRY(arena_alloc(ctx, c->R * 32, &Chat));
+    TRY(arena_alloc(ctx, c->N * 32, &zhat));
+    TRY(arena_alloc(ctx, c->N * 64, &dz));
+    TRY(d_fwd_hat(ctx, dc, Chat, c->R, 0, 0));
+    TRY(d_amortize(ctx, Chat, What, c->N, c->R, 0, c->R, zhat, dz));
+    TRY(download(ctx, z, dz, c->N * 64));
+    return lab_sync(ctx);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Prover::proof_gen (proofgen.rs:30-427)
+// ---------------------------------------------------------------------------------------------
+static int prove_one(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_bytes[32], const uint32_t *S, const lab_state *st,
+                     const lab_challenges *ch, lab_transcript *out) {
+    const uint64_t R = c->R, N = c->N, K = c->KAPPA, K1 = c->KAPPA_1, K2 = c->KAPPA_2, ND = N * LAB_D;
+    const uint64_t T1 = (uint64_t)c->T_1, T2 = (uint64_t)c->T_2;
+    if (!S || !st || !ch || !out || !st->phi || !st->a || !st->b || !ch->pi || !ch->omega || !ch->alpha || !ch->beta || !ch->c)
+        FAIL(LAB_ERR_PARAMS, "null argument");
+    if (ch->n_attempts < 1) FAIL(LAB_ERR_PARAMS, "need at least one JL attempt");
+    const LabSeed seed = make_seed(seed_bytes);
+    const uint32_t psi = ch->psi % LAB_Q;
+
+    // S1: inner commitments (proofgen.rs:35-49)
+    uint32_t *dS, *What, *dT;
+    TRY(load_witness(ctx, c, S, &dS, &What));
+    TRY(arena_alloc(ctx, R * K * 64, &dT));
+    TRY(d_commit_inner(ctx, seed, What, N, R, 0, K, dT));
+    // S2: g (proofgen.rs:59-70)
+    uint32_t *Ghat, *dG;
+    TRY(arena_alloc(ctx, R * R * 32, &Ghat));
+    TRY(arena_alloc(ctx, R * R * 64, &dG));
+    TRY(d_gram(ctx, What, N, R, Ghat, dG));
+    // S3: u_1 (proofgen.rs:101-153)
+    uint32_t *du1;
+    TRY(arena_alloc(ctx, K1 * 64, &du1));
+    TRY(d_outer_u1(ctx, c, seed, dT, dG, du1));
+    // S4: JL with retries (proofgen.rs:161-186)
+    int8_t *dPi;
+    unsigned long long *dp;
+    TRY(arena_alloc(ctx, R * LAB_JL_ROWS * ND, &dPi));
+    TRY(arena_alloc(ctx, (size_t)LAB_JL_ROWS, &dp));
+    int att = 0, rejections = 0;
+    for (;;) {
+        if (att >= ch->n_attempts) FAIL(LAB_ERR_JL_REJECTED, "JL projection rejected and no further attempt supplied");
+        CK(cudaMemcpyAsync(dPi, ch->pi + (size_t)att * R * LAB_JL_ROWS * ND, R * LAB_JL_ROWS * ND, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(d_jl(ctx, dPi, dS, ND, 0, R, dp));
+        CK(cudaMemcpyAsync(out->projection_int, dp, LAB_JL_ROWS * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        TRY(lab_sync(ctx));
+        if (valid_projection(c, out->projection_int)) break;
+        if (++rejections > 5) FAIL(LAB_ERR_JL_REJECTED, "failed JL... (proofgen.rs:175-176)");
+        att++;
+    }
+    out->jl_attempt = att;
+    for (int j = 0; j < LAB_JL_ROWS; j++) {
+        int64_t m = out->projection_int[j] % (int64_t)LAB_Q;
+        out->projection[j] = (uint32_t)(m < 0 ? m + (int64_t)LAB_Q : m);
+    }
+    // S5: aggregation (proofgen.rs:189-289), upper_bound = 1
+    uint32_t *dphi, *dom, *dpp, *Phihat, *PPhat;
+    TRY(upload(ctx, st->phi, R * ND, &dphi));
+    TRY(upload(ctx, ch->omega, (size_t)LAB_JL_ROWS, &dom));
+    TRY(arena_alloc(ctx, R * ND, &dpp));
+    TRY(d_aggregate_phi(ctx, c, dphi, dPi, psi, dom, dpp));
+    TRY(arena_alloc(ctx, R * N * 32, &Phihat));
+    TRY(arena_alloc(ctx, R * N * 32, &PPhat));
+    TRY(d_fwd_hat(ctx, dphi, Phihat, R * N, N, R));
+    TRY(d_fwd_hat(ctx, dpp, PPhat, R * N, N, R));
+    uint32_t *da, *Ahat, *AG, *diag, *sums, *dsums;
+    TRY(upload(ctx, st->a, R * R * 64, &da));
+    TRY(arena_alloc(ctx, R * R * 32, &Ahat));
+    TRY(arena_alloc(ctx, R * R * 32, &AG));
+    TRY(arena_alloc(ctx, R * 32, &diag));
+    TRY(arena_alloc(ctx, (size_t)2 * 32, &sums));
+    TRY(arena_alloc(ctx, (size_t)2 * 64, &dsums));
+    TRY(d_fwd_hat(ctx, da, Ahat, R * R, 0, 0));
+    LAUNCH(k_pointwise, grid_for(R * R * 32, 256, ctx->sms * 16), 256, Ahat, (size_t)1, (size_t)(R * R), Ghat, (const uint32_t *)nullptr, (size_t)1,
+           (size_t)0, (const uint32_t *)nullptr, AG, (size_t)(R * R));
+    LAUNCH(k_ip_hat, (unsigned)R, 256, PPhat, (size_t)R, (size_t)1, What, (size_t)R, (size_t)1, (size_t)N, (size_t)0, 1u, 2, diag);
+    LAUNCH(k_sum_hats, 1, 32, AG, (size_t)(R * R), (size_t)1, sums, (size_t)1);
+    LAUNCH(k_sum_hats, 1, 32, diag, (size_t)R, (size_t)1, sums + 32, (size_t)1);
+    TRY(d_inv_hat(ctx, sums, dsums, 2));
+    uint32_t hs[128];
+    TRY(download(ctx, hs, dsums, (size_t)128));
+    // S6: phi_final = alpha phi + beta phi'' (proofgen.rs:295-314)
+    uint32_t *dab, *ABhat, *PFhat;
+    uint32_t ab[128];
+    std::memcpy(ab, ch->alpha, 64 * sizeof(uint32_t));
+    std::memcpy(ab + 64, ch->beta, 64 * sizeof(uint32_t));
+    TRY(upload(ctx, ab, (size_t)128, &dab));
+    TRY(arena_alloc(ctx, (size_t)64, &ABhat));
+    TRY(arena_alloc(ctx, R * N * 32, &PFhat));
+    TRY(d_fwd_hat(ctx, dab, ABhat, 2, 0, 0));
+    LAUNCH(k_pointwise, grid_for(R * N * 32, 256, ctx->sms * 16), 256, ABhat, (size_t)1, (size_t)0, Phihat, ABhat + 32, (size_t)1, (size_t)0, PPhat,
+           PFhat, (size_t)(R * N));
+    // S7: h (proofgen.rs:320-358)
+    uint32_t *Hhat, *dH;
+    TRY(arena_alloc(ctx, R * R * 32, &Hhat));
+    TRY(arena_alloc(ctx, R * R * 64, &dH));
+    TRY(d_h_gram(ctx, PFhat, What, N, R, Hhat, dH));
+    // S8: u_2 (proofgen.rs:364-378)
+    uint32_t *du2;
+    TRY(arena_alloc(ctx, K2 * 64, &du2));
+    TRY(d_outer_u2(ctx, c, seed, dH, du2));
+    // S9: z (proofgen.rs:380-399)
+    uint32_t *dc, *Chat, *zhat, *dz;
+    TRY(upload(ctx, ch->c, R * 64, &dc));
+    TRY(arena_alloc(ctx, R * 32, &Chat));
+    TRY(arena_alloc(ctx, N * 32, &zhat));
+    TRY(arena_alloc(ctx, N * 64, &dz));
+    TRY(d_fwd_hat(ctx, dc, Chat, R, 0, 0));
+    TRY(d_amortize(ctx, Chat, What, N, R, 0, R, zhat, dz));
+    // exact integer of Check 14 (verification.rs:185-267): digits of z (B, 2), t (B_1, T_1), all g (B_2, T_2), all h (B_1, T_1)
+    unsigned long long *dnorm;
+    TRY(arena_alloc(ctx, (size_t)1, &dnorm));
+    CK(cudaMemsetAsync(dnorm, 0, sizeof *dnorm, ctx->stream));
+    LAUNCH(k_digit_norm_sq, grid_for(N * 64, 2048, ctx->sms * 8), 256, dz, (size_t)(N * 64), (uint32_t)c->B, 2, dnorm);
+    LAUNCH(k_digit_norm_sq, grid_for(R * K * 64, 2048, ctx->sms * 8), 256, dT, (size_t)(R * K * 64), (uint32_t)c->B_1, (int)T1, dnorm);
+    LAUNCH(k_digit_norm_sq, grid_for(R * R * 64, 2048, ctx->sms * 8), 256, dG, (size_t)(R * R * 64), (uint32_t)c->B_2, (int)T2, dnorm);
+    LAUNCH(k_digit_norm_sq, grid_for(R * R * 64, 2048, ctx->sms * 8), 256, dH, (size_t)(R * R * 64), (uint32_t)c->B_1, (int)T1, dnorm);
+    // outputs
+    if (out->phi_final) {
+        uint32_t *tmp;
+        TRY(arena_alloc(ctx, R * N * 64, &tmp));
+        TRY(d_inv_hat(ctx, PFhat, tmp, R * N));
+        // n-major polys (n*R + i) -> [R][N][64]: one strided 2D copy per i
+        for (uint64_t i = 0; i < R; i++)
+            CK(cudaMemcpy2DAsync(out->phi_final + i * N * 64, 64 * sizeof(uint32_t), tmp + i * 64, R * 64 * sizeof(uint32_t), 64 * sizeof(uint32_t), N,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    TRY(download(ctx, out->u_1, du1, K1 * 64));
+    TRY(download(ctx, out->u_2, du2, K2 * 64));
+    TRY(download(ctx, out->z, dz, N * 64));
+    TRY(download(ctx, out->t, dT, R * K * 64));
+    TRY(download(ctx, out->g, dG, R * R * 64));
+    TRY(download(ctx, out->h, dH, R * R * 64));
+    unsigned long long hnorm = 0;
+    CK(cudaMemcpyAsync(&hnorm, dnorm, sizeof hnorm, cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(lab_sync(ctx));
+    out->norm_sum = hnorm;
+    // b'' = psi * sum a_ij g_ij + sum <phi''_i, s_i> (proofgen.rs:258-278); check (verification.rs:532-551)
+    for (int d = 0; d < 64; d++) out->b_prime_prime[d] = (uint32_t)(((uint64_t)hs[d] * psi + hs[64 + d]) % LAB_Q);
+    uint64_t acc = 0;
+    for (int j = 0; j < LAB_JL_ROWS; j++) acc = (acc + (uint64_t)(ch->omega[j] % LAB_Q) * out->projection[j]) % LAB_Q;
+    const uint64_t check = (acc + (uint64_t)psi * (st->b[0] % LAB_Q)) % LAB_Q;
+    if (out->b_prime_prime[0] != check) FAIL(LAB_ERR_BPP_CHECK, "verify_b_prime_prime check failed (verification.rs:550)");
+    return LAB_OK;
+}
+
+extern "C" int lab_prove(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], const uint32_t *S, const lab_state *st,
+                         const lab_challenges *ch, lab_transcript *out) {
+    CallScope cs(ctx);
+    TRY(check_consts(ctx, c, true));
+    return prove_one(ctx, c, seed, S, st, ch, out);
+}
+extern "C" int lab_prove_batch(lab_ctx *ctx, const lab_constants *c, size_t n_statements, const uint8_t *seeds, int shared_crs, const uint32_t *S,
+                               const lab_state *st, const lab_challenges *ch, lab_transcript *out) {
+    TRY(check_consts(ctx, c, true));
+    const size_t wsz = c->R * c->N * 64;
+    (void)wsz;
+    for (size_t b = 0; b < n_statements; b++) {
+        CallScope cs(ctx);
+        const uint8_t *seed = shared_crs ? seeds : seeds + 32 * b;
+        TRY(prove_one(ctx, c, seed, S + b * wsz, &st[b], &ch[b], &out[b]));
+    }
+    return LAB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-resident stage API
+// ---------------------------------------------------------------------------------------------
+extern "C" int lab_witness_load_dev(lab_ctx *ctx, const lab_constants *c, const uint32_t *S_dev) {
+    cudaSetDevice(ctx->device);
+    TRY(check_consts(ctx, c, false));
+    const size_t bytes = c->R * c->N * 32 * sizeof(uint32_t);
+    if (bytes > ctx->What_bytes) {
+        if (ctx->What) cudaFree(ctx->What);
+        ctx->What = nullptr; ctx->What_bytes = 0;
+        CK(cudaMalloc(&ctx->What, bytes));
+        ctx->What_bytes = bytes;
+    }
+    ctx->wc = *c;
+    ctx->S_dev = S_dev;
+    return d_fwd_hat(ctx, S_dev, ctx->What, c->R * c->N, c->N, c->R);
+}
+#define NEED_WITNESS() do { if (!ctx->What || !ctx->S_dev) FAIL(LAB_ERR_PARAMS, "no witness loaded (lab_witness_load_dev)"); } while (0)
+extern "C" int lab_commit_inner_dev(lab_ctx *ctx, const uint8_t seed[32], uint64_t row0, uint64_t nrows, uint32_t *T_dev) {
+    NEED_WITNESS();
+    if (row0 + nrows > ctx->wc.KAPPA) FAIL(LAB_ERR_SHAPE, "row range exceeds KAPPA");
+    return d_commit_inner(ctx, make_seed(seed), ctx->What, ctx->wc.N, ctx->wc.R, row0, nrows, T_dev);
+}
+extern "C" int lab_gram_dev(lab_ctx *ctx, uint32_t *G_dev) {
+    NEED_WITNESS();
+    arena_reset(ctx);
+    uint32_t *Ghat;
+    TRY(arena_alloc(ctx, ctx->wc.R * ctx->wc.R * 32, &Ghat));
+    return d_gram(ctx, ctx->What, ctx->wc.N, ctx->wc.R, Ghat, G_dev);
+}
+extern "C" int lab_jl_project_dev(lab_ctx *ctx, const int8_t *pi_dev, uint64_t i0, uint64_t ni, int64_t *p_dev) {
+    NEED_WITNESS();
+    if (i0 + ni > ctx->wc.R) FAIL(LAB_ERR_SHAPE, "witness range exceeds R");
+    return d_jl(ctx, pi_dev, ctx->S_dev, ctx->wc.N * LAB_D, i0, ni, reinterpret_cast<unsigned long long *>(p_dev));
+}
+extern "C" int lab_amortize_z_dev(lab_ctx *ctx, const uint32_t *ch_dev, uint64_t i0, uint64_t ni, uint32_t *z_dev) {
+    NEED_WITNESS();
+    if (i0 + ni > ctx->wc.R) FAIL(LAB_ERR_SHAPE, "witness range exceeds R");
+    arena_reset(ctx);
+    uint32_t *Chat, *zhat;
+    TRY(arena_alloc(ctx, ctx->wc.R * 32, &Chat));
+    TRY(arena_alloc(ctx, ctx->wc.N * 32, &zhat));
+    TRY(d_fwd_hat(ctx, ch_dev, Chat, ctx->wc.R, 0, 0));
+    return d_amortize(ctx, Chat, ctx->What, ctx->wc.N, ctx->wc.R, i0, ni, zhat, z_dev);
+}

@@ -1,0 +1,611 @@
+// sm_100a kernels of the LaBRADOR prover hot path.  All arithmetic is exact integer arithmetic.
+//
+// Device layouts
+//   poly  : uint32_t[64] canonical coefficients                              (API boundary)
+//   hat   : uint32_t[32] packed slots re | im << 16, canonical              (transform domain)
+//   What  : witness in the transform domain, n-major: hat[(n * R + i)]       (K_A reads 128 B / (n,i))
+//
+// Kernels (roofline that bounds each is named; see DESIGN.md for the byte/op counts)
+//   k_ntt_fwd_regs / k_ntt_inv_regs / k_polymul_regs   lane-per-poly, swizzled smem staging   HBM
+//   k_crs_expand                                       thread per coefficient                  INT32 ALU
+//   k_commit_inner                                     CRS gen + warp NTT + reuse over R       INT32 ALU
+//   k_crs_matvec + k_finish_rows                       CRS gen + warp NTT + mat-vec            INT32 ALU
+//   k_fwd_hat / k_inv_hat / k_decomp_fwd / k_ip_hat / k_pointwise / k_jl / k_piT_omega / ...   HBM / L2
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "lab_chacha.cuh"
+#include "lab_ntt.cuh"
+
+namespace lab {
+
+// ------------------------------------------------------------------------------------------------
+// lane-per-poly batch transforms.  A CTA of 128 threads stages 128 polys (32 KB) through shared
+// memory with a 16-byte-chunk XOR swizzle so that both the coalesced global side (consecutive
+// lanes -> consecutive chunks) and the per-lane side (lane p reads chunk c of its own poly) are
+// bank-conflict free:  chunk (p, c) lives at p * 16 + (c ^ (p & 7))   [c in 0..15, low 3 bits swizzled]
+// ------------------------------------------------------------------------------------------------
+constexpr int NTT_TPB = 128;
+
+__device__ __forceinline__ int swz(int p, int c) { return p * 16 + (c ^ (p & 7)); }
+
+__device__ __forceinline__ void stage_in(uint4 *sm, const uint32_t *__restrict__ g, size_t base_poly, size_t n_polys, int tid) {
+    // 128 polys * 16 chunks = 2048 chunks, 16 per thread, coalesced
+    const uint4 *g4 = reinterpret_cast<const uint4 *>(g) + base_poly * 16;
+    const size_t avail = (n_polys - base_poly) * 16;
+#pragma unroll
+    for (int it = 0; it < 16; it++) {
+        int q = it * NTT_TPB + tid;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if ((size_t)q < avail) v = __ldg(g4 + q);
+        sm[swz(q >> 4, q & 15)] = v;
+    }
+}
+__device__ __forceinline__ void stage_out(const uint4 *sm, uint32_t *__restrict__ g, size_t base_poly, size_t n_polys, int tid) {
+    uint4 *g4 = reinterpret_cast<uint4 *>(g) + base_poly * 16;
+    const size_t avail = (n_polys - base_poly) * 16;
+#pragma unroll
+    for (int it = 0; it < 16; it++) {
+        int q = it * NTT_TPB + tid;
+        if ((size_t)q < avail) g4[q] = sm[swz(q >> 4, q & 15)];
+    }
+}
+// coefficient order -> registers: re[d] = f_d, im[d] = f_{d+32}
+__device__ __forceinline__ void load_coeffs(const uint4 *sm, int p, uint32_t (&re)[32], uint32_t (&im)[32]) {
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        uint4 a = sm[swz(p, c)], b = sm[swz(p, c + 8)];
+        re[4 * c] = a.x; re[4 * c + 1] = a.y; re[4 * c + 2] = a.z; re[4 * c + 3] = a.w;
+        im[4 * c] = b.x; im[4 * c + 1] = b.y; im[4 * c + 2] = b.z; im[4 * c + 3] = b.w;
+    }
+}
+__device__ __forceinline__ void store_coeffs(uint4 *sm, int p, const uint32_t (&re)[32], const uint32_t (&im)[32]) {
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        sm[swz(p, c)] = make_uint4(re[4 * c], re[4 * c + 1], re[4 * c + 2], re[4 * c + 3]);
+        sm[swz(p, c + 8)] = make_uint4(im[4 * c], im[4 * c + 1], im[4 * c + 2], im[4 * c + 3]);
+    }
+}
+// slot order, interleaved (re_j, im_j) -> registers
+__device__ __forceinline__ void load_slots(const uint4 *sm, int p, uint32_t (&re)[32], uint32_t (&im)[32]) {
+#pragma unroll
+    for (int c = 0; c < 16; c++) {
+        uint4 a = sm[swz(p, c)];
+        re[2 * c] = a.x; im[2 * c] = a.y; re[2 * c + 1] = a.z; im[2 * c + 1] = a.w;
+    }
+}
+__device__ __forceinline__ void store_slots(uint4 *sm, int p, const uint32_t (&re)[32], const uint32_t (&im)[32]) {
+#pragma unroll
+    for (int c = 0; c < 16; c++) sm[swz(p, c)] = make_uint4(re[2 * c], im[2 * c], re[2 * c + 1], im[2 * c + 1]);
+}
+__device__ __forceinline__ void canon_in(uint32_t (&re)[32], uint32_t (&im)[32]) {
+    // API inputs are documented canonical; a fold keeps any u32 input well-defined (value mod Q)
+#pragma unroll
+    for (int j = 0; j < 32; j++) { re[j] = lab_fold(lab_fold(re[j])); im[j] = lab_fold(lab_fold(im[j])); }
+}
+
+__global__ void __launch_bounds__(NTT_TPB) k_ntt_fwd_regs(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t n_polys) {
+    __shared__ uint4 sm[NTT_TPB * 16];
+    const int tid = threadIdx.x;
+    for (size_t base = (size_t)blockIdx.x * NTT_TPB; base < n_polys; base += (size_t)gridDim.x * NTT_TPB) {
+        stage_in(sm, in, base, n_polys, tid);
+        __syncthreads();
+        uint32_t re[32], im[32];
+        load_coeffs(sm, tid, re, im);
+        canon_in(re, im);
+        lab_ntt32_fwd_regs(re, im);
+        __syncthreads();
+        store_slots(sm, tid, re, im);
+        __syncthreads();
+        stage_out(sm, out, base, n_polys, tid);
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(NTT_TPB) k_ntt_inv_regs(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t n_polys) {
+    __shared__ uint4 sm[NTT_TPB * 16];
+    const int tid = threadIdx.x;
+    for (size_t base = (size_t)blockIdx.x * NTT_TPB; base < n_polys; base += (size_t)gridDim.x * NTT_TPB) {
+        stage_in(sm, in, base, n_polys, tid);
+        __syncthreads();
+        uint32_t re[32], im[32];
+        load_slots(sm, tid, re, im);
+        canon_in(re, im);
+        lab_ntt32_inv_regs(re, im);
+        __syncthreads();
+        store_coeffs(sm, tid, re, im);
+        __syncthreads();
+        stage_out(sm, out, base, n_polys, tid);
+        __syncthreads();
+    }
+}
+// c = a * b in R_q: two forward transforms, 32 slot products, one inverse -- &Rq * &Rq (algebraic.rs:517-523)
+__global__ void __launch_bounds__(NTT_TPB) k_polymul_regs(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
+                                                           uint32_t *__restrict__ c, size_t n_polys) {
+    __shared__ uint4 sm[NTT_TPB * 16];
+    const int tid = threadIdx.x;
+    for (size_t base = (size_t)blockIdx.x * NTT_TPB; base < n_polys; base += (size_t)gridDim.x * NTT_TPB) {
+        uint32_t re[32], im[32], pk[32];
+        stage_in(sm, a, base, n_polys, tid);
+        __syncthreads();
+        load_coeffs(sm, tid, re, im);
+        __syncthreads();
+        stage_in(sm, b, base, n_polys, tid);     // overlaps with the first transform
+        canon_in(re, im);
+        lab_ntt32_fwd_regs(re, im);
+#pragma unroll
+        for (int j = 0; j < 32; j++) pk[j] = lab_pack(re[j], im[j]);
+        __syncthreads();
+        load_coeffs(sm, tid, re, im);
+        canon_in(re, im);
+        lab_ntt32_fwd_regs(re, im);
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            uint32_t r, i;
+            lab_cmul(lab_re(pk[j]), lab_im(pk[j]), re[j], im[j], r, i);
+            re[j] = r; im[j] = i;                // < 2Q, fine for the generated inverse (bound Q+8 <= 8199)
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j++) { re[j] = lab_csub(re[j]); im[j] = lab_csub(im[j]); }
+        lab_ntt32_inv_regs(re, im);
+        __syncthreads();
+        store_coeffs(sm, tid, re, im);
+        __syncthreads();
+        stage_out(sm, c, base, n_polys, tid);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp-per-poly helpers (lane j <-> coefficient pair (j, j+32) / slot j)
+// ------------------------------------------------------------------------------------------------
+// poly (canonical u32[64]) -> hat (packed u32[32]); out index = perm(p) to allow the n-major transpose:
+// p = o * inner + i  ->  i * outer + o   (inner == 0: identity)
+__global__ void __launch_bounds__(256) k_fwd_hat(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t n_polys,
+                                                 size_t inner, size_t outer) {
+    const int lane = threadIdx.x & 31;
+    const LabWarpTw tw = lab_warp_tw(lane);
+    size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nw = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t p = warp; p < n_polys; p += nw) {
+        uint32_t re = lab_fold(lab_fold(in[p * 64 + lane])), im = lab_fold(lab_fold(in[p * 64 + 32 + lane]));
+        lab_ntt32_fwd_warp(re, im, tw, lane);
+        size_t q = inner ? (p % inner) * outer + (p / inner) : p;
+        out[q * 32 + lane] = lab_pack(re, im);
+    }
+}
+__global__ void __launch_bounds__(256) k_inv_hat(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t n_polys) {
+    const int lane = threadIdx.x & 31;
+    const LabWarpTw tw = lab_warp_tw(lane);
+    size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nw = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t p = warp; p < n_polys; p += nw) {
+        uint32_t v = in[p * 32 + lane];
+        uint32_t re = lab_re(v), im = lab_im(v);
+        lab_ntt32_inv_warp(re, im, tw, lane);
+        out[p * 64 + lane] = re;
+        out[p * 64 + 32 + lane] = im;
+    }
+}
+
+// digit_k(c) = f(floor(c / b^k) mod b), f(x) = x if x <= floor(b/2) else b - x  (util.rs:360-442)
+__device__ __forceinline__ uint32_t digit_of(uint32_t &v, uint32_t base) {
+    uint32_t q = v / base, x = v - q * base;
+    v = q;
+    return x <= (base >> 1) ? x : base - x;
+}
+// decompose + forward transform.  in: poly[n_polys]; out: hat[((p / inner) * exp + k) * inner + (p % inner)]
+__global__ void __launch_bounds__(256) k_decomp_fwd(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t n_polys,
+                                                    size_t inner, uint32_t base, int exp) {
+    const int lane = threadIdx.x & 31;
+    const LabWarpTw tw = lab_warp_tw(lane);
+    size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nw = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t p = warp; p < n_polys; p += nw) {
+        uint32_t a = in[p * 64 + lane], b = in[p * 64 + 32 + lane];
+        for (int k = 0; k < exp; k++) {
+            uint32_t re = digit_of(a, base), im = digit_of(b, base);
+            re = lab_canon(re); im = lab_canon(im);     // digits can exceed Q only for base > 2Q
+            lab_ntt32_fwd_warp(re, im, tw, lane);
+            size_t q = ((p / inner) * (size_t)exp + (size_t)k) * inner + (p % inner);
+            out[q * 32 + lane] = lab_pack(re, im);
+        }
+    }
+}
+// plain coefficient-domain decomposition (lab_decompose): out[k][p][d]
+__global__ void k_decompose(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t n_coeffs, uint32_t base, int exp) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; idx < n_coeffs; idx += stride) {
+        uint32_t v = in[idx];
+        for (int k = 0; k < exp; k++) out[(size_t)k * n_coeffs + idx] = lab_canon(digit_of(v, base));
+    }
+}
+__global__ void k_sigma_inv(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t n_coeffs) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; idx < n_coeffs; idx += stride) {
+        size_t p = idx >> 6;
+        int d = (int)(idx & 63);
+        uint32_t v = lab_canon(in[p * 64 + ((64 - d) & 63)]);
+        out[idx] = d == 0 ? v : (v ? LABQ - v : 0u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched inner products in the transform domain:
+//   out[b][slot] = scale * sum_{n < len} X[(n * x_sn + xi(b) * x_si)] (*) Y[(n * y_sn + yi(b) * y_si)]
+// with b = xi * nby + yi.  One CTA per b, 8 warps stride over n, smem tree at the end.
+// mode 0: plain; mode 2: diagonal (xi = yi = b); mode 1: symmetrised h: out[b] = (X[xi].Y[yi] + X[yi].Y[xi]) * scale  (proofgen.rs:334-347)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ip_hat(const uint32_t *__restrict__ X, size_t x_sn, size_t x_si,
+                                                const uint32_t *__restrict__ Y, size_t y_sn, size_t y_si,
+                                                size_t len, size_t nby, uint32_t scale, int mode, uint32_t *__restrict__ out) {
+    __shared__ uint32_t sre[8][32], sim[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const size_t b = blockIdx.x;
+    const size_t xi = mode == 2 ? b : b / nby, yi = mode == 2 ? b : b % nby;
+    uint32_t accr = 0, acci = 0;
+    int pending = 0;
+    for (size_t n = w; n < len; n += 8) {
+        uint32_t x = X[(n * x_sn + xi * x_si) * 32 + lane], y = Y[(n * y_sn + yi * y_si) * 32 + lane];
+        uint32_t xr = lab_re(x), xm = lab_im(x), yr = lab_re(y), ym = lab_im(y);
+        accr += xr * yr + (LABQ - xm) * ym;
+        acci += xr * ym + xm * yr;
+        if (mode == 1) {
+            uint32_t x2 = X[(n * x_sn + yi * x_si) * 32 + lane], y2 = Y[(n * y_sn + xi * y_si) * 32 + lane];
+            uint32_t ar = lab_re(x2), am = lab_im(x2), br = lab_re(y2), bm = lab_im(y2);
+            accr += ar * br + (LABQ - am) * bm;
+            acci += ar * bm + am * br;
+        }
+        if (++pending == 8) { accr = lab_fold(accr); acci = lab_fold(acci); pending = 0; }   // 8 * 4 * 2^26 < 2^32
+    }
+    sre[w][lane] = lab_canon(accr);
+    sim[w][lane] = lab_canon(acci);
+    __syncthreads();
+    if (w == 0) {
+        uint32_t r = 0, i = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { r += sre[k][lane]; i += sim[k][lane]; }
+        r = lab_canon(lab_canon(r) * scale);
+        i = lab_canon(lab_canon(i) * scale);
+        out[b * 32 + lane] = lab_pack(r, i);
+    }
+}
+
+// generic slot-wise fused multiply-add over hats:
+//   out[p] = A[ai(p)] (*) X[p]  (+ B[bi(p)] (*) Y[p] if Y)      ai(p) = (p / a_div) % a_mod  (a_mod == 0: index 0)
+__global__ void k_pointwise(const uint32_t *__restrict__ A, size_t a_div, size_t a_mod, const uint32_t *__restrict__ X,
+                            const uint32_t *__restrict__ B, size_t b_div, size_t b_mod, const uint32_t *__restrict__ Y,
+                            uint32_t *__restrict__ out, size_t n_polys) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; idx < n_polys * 32; idx += stride) {
+        size_t p = idx >> 5;
+        int s = (int)(idx & 31);
+        size_t ai = a_mod ? (p / a_div) % a_mod : 0;
+        uint32_t a = A[ai * 32 + s], x = X[idx];
+        uint32_t r, i;
+        lab_cmul(lab_re(a), lab_im(a), lab_re(x), lab_im(x), r, i);
+        if (Y) {
+            size_t bi = b_mod ? (p / b_div) % b_mod : 0;
+            uint32_t b = B[bi * 32 + s], y = Y[idx];
+            uint32_t r2, i2;
+            lab_cmul(lab_re(b), lab_im(b), lab_re(y), lab_im(y), r2, i2);
+            r += r2; i += i2;
+        }
+        out[idx] = lab_pack(lab_canon(r), lab_canon(i));
+    }
+}
+// out[n] = sum_{i in [i0,i0+ni)} C[i] (*) W[n * R + i]   (amortised opening z, proofgen.rs:387-399)
+__global__ void __launch_bounds__(256) k_amortize(const uint32_t *__restrict__ Chat, const uint32_t *__restrict__ What, size_t N, size_t R,
+                                                  size_t i0, size_t ni, uint32_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nw = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t n = warp; n < N; n += nw) {
+        uint32_t accr = 0, acci = 0;
+        int pending = 0;
+        for (size_t i = i0; i < i0 + ni; i++) {
+            uint32_t c = Chat[i * 32 + lane], s = What[(n * R + i) * 32 + lane];
+            uint32_t cr = lab_re(c), cm = lab_im(c), sr = lab_re(s), sm_ = lab_im(s);
+            accr += cr * sr + (LABQ - cm) * sm_;
+            acci += cr * sm_ + cm * sr;
+            if (++pending == 16) { accr = lab_fold(accr); acci = lab_fold(acci); pending = 0; }
+        }
+        out[n * 32 + lane] = lab_pack(lab_canon(accr), lab_canon(acci));
+    }
+}
+// sum over `cnt` hats spaced `stride` apart: out[p] = sum_t in[p + t * stride]   (b'' accumulation etc.)
+__global__ void k_sum_hats(const uint32_t *__restrict__ in, size_t cnt, size_t stride_polys, uint32_t *__restrict__ out, size_t n_polys) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_polys * 32) return;
+    uint32_t r = 0, i = 0;
+    for (size_t t = 0; t < cnt; t++) {
+        uint32_t v = in[idx + t * stride_polys * 32];
+        r += lab_re(v); i += lab_im(v);
+        if ((t & 1023) == 1023) { r = lab_fold(r); i = lab_fold(i); }
+    }
+    out[idx] = lab_pack(lab_canon(r), lab_canon(i));
+}
+
+// exact sum of squares of canonical representatives (util.rs:195-202)
+__global__ void __launch_bounds__(256) k_norm_sq(const uint32_t *__restrict__ in, size_t n, unsigned long long *out) {
+    unsigned long long acc = 0;
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; idx < n; idx += stride) {
+        unsigned long long v = in[idx];
+        acc += v * v;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+// sum of squared digits of every coefficient (verifier Check 14, verification.rs:185-267), exact
+__global__ void __launch_bounds__(256) k_digit_norm_sq(const uint32_t *__restrict__ in, size_t n, uint32_t base, int exp, unsigned long long *out) {
+    unsigned long long acc = 0;
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; idx < n; idx += stride) {
+        uint32_t v = in[idx];
+        for (int k = 0; k < exp; k++) {
+            unsigned long long dg = lab_canon(digit_of(v, base));
+            acc += dg * dg;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CRS expansion (structs.rs:35-45,147-171): thread per coefficient, coalesced stores.  INT32-ALU bound.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_crs_expand(LabSeed seed, uint64_t start_lo, uint64_t start_hi, size_t n_coeffs, uint32_t *__restrict__ out) {
+    size_t idx = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 2;
+    for (; idx < n_coeffs; idx += stride) {
+        uint64_t lo = start_lo + idx;
+        uint64_t hi = start_hi + (lo < start_lo);
+        const uint32_t off[2] = {0u, 1u};
+        uint32_t c[2];
+        lab_crs_coeffs<2>(seed, lo, hi, off, c);
+        if (idx + 1 < n_coeffs) *reinterpret_cast<uint2 *>(out + idx) = make_uint2(c[0], c[1]);
+        else out[idx] = c[0];
+    }
+}
+
+// one CRS polynomial per warp, in the transform domain: lane j produces coefficients j and j+32
+__device__ __forceinline__ void crs_poly_hat(const LabSeed &seed, uint64_t lo, uint64_t hi, const LabWarpTw &tw, int lane, uint32_t &re, uint32_t &im) {
+    const uint32_t off[2] = {(uint32_t)lane, (uint32_t)lane + 32u};
+    uint32_t c[2];
+    lab_crs_coeffs<2>(seed, lo, hi, off, c);
+    re = c[0]; im = c[1];
+    lab_ntt32_fwd_warp(re, im, tw, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_A: inner Ajtai commitments t_i[row] = sum_n A[row][n] * s_i[n]   (proofgen.rs:41-49)
+// CTA = 8 warps, RT = 4 rows.  Per step two columns n are processed: warp w generates and transforms
+// A[row0 + (w & 3)][n0 + (w >> 2)] (64 ChaCha blocks), parks it in shared memory, then every thread
+// (lane = slot, warp = group of IC witness vectors) does RT*IC complex multiply-accumulates per column
+// against the n-major transformed witness (128 B coalesced per (n, i), L2 resident).
+// ChaCha runs on the ALU pipe, the MACs on the FMA pipe.  A is generated exactly once.
+// ------------------------------------------------------------------------------------------------
+constexpr int KA_RT = 4;
+
+template <int IC>
+__global__ void __launch_bounds__(256, 2) k_commit_inner(LabSeed seed, const uint32_t *__restrict__ What, uint32_t N, uint32_t R,
+                                                          uint64_t row0, uint64_t nrows, uint32_t i_base, uint32_t *__restrict__ T) {
+    __shared__ uint32_t Abuf[2][8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const LabWarpTw tw = lab_warp_tw(lane);
+    const uint64_t rblk = (uint64_t)blockIdx.x * KA_RT;          // first row of this CTA, relative to row0
+    const int grow = w & 3, gcol = w >> 2;                       // generation role
+    const uint32_t i0 = i_base + (uint32_t)w * IC;                // MAC role: witness vectors i0..i0+IC
+    uint32_t accr[KA_RT][IC], acci[KA_RT][IC];
+#pragma unroll
+    for (int r = 0; r < KA_RT; r++)
+#pragma unroll
+        for (int ii = 0; ii < IC; ii++) { accr[r][ii] = 0; acci[r][ii] = 0; }
+
+    int pending = 0;
+    for (uint32_t n0 = 0, step = 0; n0 < N; n0 += 2, step++) {
+        const int buf = step & 1;
+        {   // generate
+            const uint64_t row = row0 + rblk + grow;
+            const uint32_t n = n0 + gcol;
+            uint32_t re = 0, im = 0;
+            if (rblk + grow < nrows && n < N) {
+                // counter of coefficient 0: (row * N + n) * 64  (structs.rs:55-72); < 2^64 for every supported shape
+                const uint64_t lo = (row * (uint64_t)N + n) * 64ull;
+                crs_poly_hat(seed, lo, 0ull, tw, lane, re, im);
+            }
+            Abuf[buf][w][lane] = lab_pack(re, im);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int nn = 0; nn < 2; nn++) {
+            const uint32_t n = n0 + nn;
+            if (n < N) {
+                uint32_t ar[KA_RT], am[KA_RT], nam[KA_RT];
+#pragma unroll
+                for (int r = 0; r < KA_RT; r++) {
+                    uint32_t a = Abuf[buf][nn * 4 + r][lane];
+                    ar[r] = lab_re(a); am[r] = lab_im(a); nam[r] = LABQ - am[r];
+                }
+#pragma unroll
+                for (int ii = 0; ii < IC; ii++) {
+                    if (i0 + ii < R) {
+                        uint32_t s = __ldg(What + ((size_t)n * R + i0 + ii) * 32 + lane);
+                        uint32_t sr = lab_re(s), sm_ = lab_im(s);
+#pragma unroll
+                        for (int r = 0; r < KA_RT; r++) {
+                            accr[r][ii] += ar[r] * sr + nam[r] * sm_;
+                            acci[r][ii] += ar[r] * sm_ + am[r] * sr;
+                        }
+                    }
+                }
+            }
+        }
+        if (++pending == 8) {                                    // 8 steps * 2 columns * 2 products < 2^5 * 2^26
+            pending = 0;
+#pragma unroll
+            for (int r = 0; r < KA_RT; r++)
+#pragma unroll
+                for (int ii = 0; ii < IC; ii++) { accr[r][ii] = lab_fold(accr[r][ii]); acci[r][ii] = lab_fold(acci[r][ii]); }
+        }
+    }
+    // inverse transform and store T[i][row][.]  (T is [R][nrows][64])
+#pragma unroll
+    for (int r = 0; r < KA_RT; r++)
+#pragma unroll
+        for (int ii = 0; ii < IC; ii++) {
+            uint32_t re = lab_canon(accr[r][ii]), im = lab_canon(acci[r][ii]);
+            lab_ntt32_inv_warp(re, im, tw, lane);
+            if (rblk + r < nrows && i0 + ii < R) {
+                uint32_t *dst = T + (((size_t)(i0 + ii)) * nrows + rblk + r) * 64;
+                dst[lane] = re;
+                dst[lane + 32] = im;
+            }
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_MV: generic CRS mat-vec in the transform domain (outer commitments u_1, u_2 and A*z):
+//   out[x] = sum_items sum_{y in item} hat(CRS(base + x*row_stride + (y / nk)*sp + (y % nk)*sk)) (*) V[vec_off + y]
+// One warp per (row x, item); partial sums go to `partial[(x * items_per_row + item)]`, k_finish_rows
+// adds them, inverts and writes canonical polynomials.  (proofgen.rs:101-153, 364-378; verification.rs:274-279)
+// ------------------------------------------------------------------------------------------------
+struct MvItem {
+    uint64_t base_lo, base_hi;   // counter of coefficient 0 of (x = 0, y = 0)
+    uint64_t row_stride;         // counter step per output row x
+    uint64_t sp, sk;             // counter steps of the two-level index y = p * nk + k
+    uint32_t nk;
+    uint32_t y0, cnt;            // this item covers y in [y0, y0 + cnt)
+    uint32_t vec_off;            // V index of y = 0
+};
+
+__global__ void __launch_bounds__(256) k_crs_matvec(LabSeed seed, const MvItem *__restrict__ items, uint32_t items_per_row, uint64_t n_rows,
+                                                    uint64_t x0, const uint32_t *__restrict__ V, uint32_t *__restrict__ partial) {
+    const int lane = threadIdx.x & 31;
+    const LabWarpTw tw = lab_warp_tw(lane);
+    uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t total = n_rows * items_per_row;
+    if (wid >= total) return;
+    const uint64_t xr = wid / items_per_row;
+    const MvItem it = items[wid % items_per_row];
+    const uint64_t x = x0 + xr;
+    // base + x * row_stride as 128 bit
+    uint64_t lo, hi;
+    {
+        unsigned __int128 b = ((unsigned __int128)it.base_hi << 64) | it.base_lo;
+        b += (unsigned __int128)x * it.row_stride;
+        lo = (uint64_t)b; hi = (uint64_t)(b >> 64);
+    }
+    uint32_t accr = 0, acci = 0;
+    int pending = 0;
+    for (uint32_t y = it.y0; y < it.y0 + it.cnt; y++) {
+        const uint64_t add = (uint64_t)(y / it.nk) * it.sp + (uint64_t)(y % it.nk) * it.sk;
+        const uint64_t plo = lo + add;
+        const uint64_t phi = hi + (plo < lo);
+        uint32_t re, im;
+        crs_poly_hat(seed, plo, phi, tw, lane, re, im);
+        const uint32_t v = __ldg(V + ((size_t)it.vec_off + y) * 32 + lane);
+        accr += re * lab_re(v) + (LABQ - im) * lab_im(v);
+        acci += re * lab_im(v) + im * lab_re(v);
+        if (++pending == 16) { accr = lab_fold(accr); acci = lab_fold(acci); pending = 0; }
+    }
+    partial[wid * 32 + lane] = lab_pack(lab_canon(accr), lab_canon(acci));
+}
+
+__global__ void __launch_bounds__(256) k_finish_rows(const uint32_t *__restrict__ partial, uint32_t items_per_row, uint64_t n_rows, uint32_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const LabWarpTw tw = lab_warp_tw(lane);
+    uint64_t x = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (x >= n_rows) return;
+    uint32_t r = 0, i = 0;
+    for (uint32_t t = 0; t < items_per_row; t++) {
+        uint32_t v = partial[(x * items_per_row + t) * 32 + lane];
+        r += lab_re(v); i += lab_im(v);
+        if ((t & 1023) == 1023) { r = lab_fold(r); i = lab_fold(i); }
+    }
+    r = lab_canon(r); i = lab_canon(i);
+    lab_ntt32_inv_warp(r, i, tw, lane);
+    out[x * 64 + lane] = r;
+    out[x * 64 + 32 + lane] = i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// JL projection p_j = sum_i sum_c Pi_i[j][c] * s_i[c], exact (proofgen.rs:429-457, util.rs:511-526).
+// CTA = one chunk of JL_CH coefficients of one witness vector x all 256 rows.  The witness chunk is
+// staged in shared memory once; warp w streams rows j = w, w+8, ... with 16-byte coalesced loads of
+// the int8 matrix (HBM bound on Pi), int32 partials per lane, shuffle reduction, int64 atomics.
+// ------------------------------------------------------------------------------------------------
+constexpr int JL_CH = 4096;
+
+__global__ void __launch_bounds__(256) k_jl(const int8_t *__restrict__ Pi, const uint32_t *__restrict__ S, size_t ND, size_t i0,
+                                            unsigned long long *__restrict__ p) {
+    __shared__ uint32_t ssm[JL_CH];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const size_t chunks_per_i = (ND + JL_CH - 1) / JL_CH;
+    const size_t i = i0 + blockIdx.x / chunks_per_i;            // absolute witness vector
+    const size_t li = blockIdx.x / chunks_per_i;                // index into Pi (which starts at i0)
+    const size_t c0 = (blockIdx.x % chunks_per_i) * JL_CH;
+    const size_t len = min((size_t)JL_CH, ND - c0);
+    for (size_t t = threadIdx.x; t < JL_CH; t += 256) ssm[t] = t < len ? S[i * ND + c0 + t] : 0u;
+    __syncthreads();
+    for (int j = w; j < 256; j += 8) {
+        const int8_t *row = Pi + (li * 256 + (size_t)j) * ND + c0;
+        int acc = 0;
+        for (size_t t = (size_t)lane * 16; t < len; t += 512) {
+            if (t + 16 <= len && ((reinterpret_cast<uintptr_t>(row + t) & 15) == 0)) {
+                int4 v = __ldg(reinterpret_cast<const int4 *>(row + t));
+                const int words[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        int tri = (int)(signed char)((words[q] >> (8 * e)) & 0xff);
+                        acc += tri * (int)ssm[t + q * 4 + e];
+                    }
+            } else {
+                for (size_t e = t; e < min(t + 16, len); e++) acc += (int)row[e] * (int)ssm[e];
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0 && acc) atomicAdd(p + j, (unsigned long long)(long long)acc);
+    }
+}
+
+// v[i][c] = sum_j omega_j * Pi_i[j][c] mod Q   (first half of phi'', proofgen.rs:244-253)
+__global__ void __launch_bounds__(256) k_piT_omega(const int8_t *__restrict__ Pi, const uint32_t *__restrict__ omega, size_t total /* R*ND */,
+                                                   size_t ND, uint32_t *__restrict__ v) {
+    __shared__ int som[256];
+    som[threadIdx.x] = (int)lab_canon(omega[threadIdx.x]);
+    __syncthreads();
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const size_t i = idx / ND, c = idx % ND;
+    const int8_t *col = Pi + i * 256 * ND + c;
+    int acc = 0;
+#pragma unroll 8
+    for (int j = 0; j < 256; j++) acc += (int)col[(size_t)j * ND] * som[j];
+    // |acc| <= 256 * 8190 < 2^21; bring into [0, Q)
+    int m = acc % (int)LABQ;
+    v[idx] = (uint32_t)(m < 0 ? m + (int)LABQ : m);
+}
+// phi''[i][n][d] = psi * phi[i][n][d] + sigma_inv(v_poly)[d]   (proofgen.rs:234-255)
+__global__ void k_phi_pp(const uint32_t *__restrict__ phi, const uint32_t *__restrict__ v, uint32_t psi, size_t n_coeffs, uint32_t *__restrict__ out) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_coeffs) return;
+    const size_t p = idx >> 6;
+    const int d = (int)(idx & 63);
+    uint32_t sv = v[p * 64 + ((64 - d) & 63)];
+    uint32_t conj = d == 0 ? sv : (sv ? LABQ - sv : 0u);
+    out[idx] = lab_canon(lab_canon(phi[idx]) * psi + conj);
+}
+// int64 projection -> mod Q lift (proofgen.rs:186) is done on the host (256 values)
+
+}  // namespace lab

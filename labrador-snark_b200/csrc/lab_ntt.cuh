@@ -1,0 +1,80 @@
+// 32-point transforms over F_{Q^2}: R_q = F_Q[X]/(X^64+1) ~ F_{Q^2}[X]/(X^32 - i) ~ F_{Q^2}^32.
+// Two mappings of the same network (tables and math in tools/gen_ntt.py):
+//   * lab_ntt32_{fwd,inv}_regs  -- one polynomial per LANE, 32 complex values in registers,
+//                                  straight-line generated code (batch NTT / polymul kernels)
+//   * lab_ntt32_{fwd,inv}_warp  -- one polynomial per WARP, lane j holds complex slot j,
+//                                  butterflies by __shfl_xor (CRS-fused commitment kernels)
+// This replaces concrete-ntt's Plan32::negacyclic_polymul (algebraic.rs:396): any exact
+// negacyclic product mod Q is bit-identical to it.
+#pragma once
+#include "lab_field.cuh"
+#include "lab_ntt_gen.cuh"
+
+#ifdef __CUDACC__
+static __constant__ uint32_t LAB_TW_FWD[32] = LAB_TW_FWD_INIT;
+static __constant__ uint32_t LAB_TW_INV[32] = LAB_TW_INV_INIT;
+
+// per-lane multipliers: stage s (len = 16 >> s) uses tree node (1 << s) + (lane >> (5 - s)).
+// Lower lanes of a butterfly multiply by 1 (forward) so that the code is branch-free.
+struct LabWarpTw {
+    uint32_t f[5];   // forward: upper lanes zeta^(e/2), lower lanes 1
+    uint32_t g[5];   // inverse: upper lanes zeta^-(e/2), lower lanes 1; last level also carries 2^8 = 32^-1
+};
+
+__device__ __forceinline__ LabWarpTw lab_warp_tw(int lane) {
+    LabWarpTw t;
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        const int len = 16 >> s;
+        const bool upper = (lane & len) != 0;
+        const int node = (1 << s) + (lane >> (5 - s));
+        t.f[s] = upper ? LAB_TW_FWD[node] : 1u;
+        uint32_t g = upper ? LAB_TW_INV[node] : 1u;
+        if (s == 0) {   // len == 16 is the LAST inverse level: fold in 32^-1 = 256
+            uint32_t gr = lab_canon(lab_re(g) * 256u), gi = lab_canon(lab_im(g) * 256u);
+            g = lab_pack(gr, gi);
+        }
+        t.g[s] = g;
+    }
+    return t;
+}
+
+// lane j holds g_j = f_j + i f_{j+32} (residues < 2Q); returns slot j = f(zeta^{e_j}), canonical.
+__device__ __forceinline__ void lab_ntt32_fwd_warp(uint32_t &re, uint32_t &im, const LabWarpTw &tw, int lane) {
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        const int len = 16 >> s;
+        const bool upper = (lane & len) != 0;
+        uint32_t pr, pi;
+        lab_cmul(re, im, lab_re(tw.f[s]), lab_im(tw.f[s]), pr, pi);          // < 2Q
+        const uint32_t recv = __shfl_xor_sync(0xffffffffu, lab_pack(pr, pi), len);
+        const uint32_t rr = lab_re(recv), ri = lab_im(recv);
+        // lower: lo + t ; upper: lo - t  (t is the upper lane's product)
+        re = upper ? rr + 2u * LABQ - pr : pr + rr;
+        im = upper ? ri + 2u * LABQ - pi : pi + ri;
+        re = lab_fold(re);                                                   // < Q + 4
+        im = lab_fold(im);
+    }
+    re = lab_csub(re);
+    im = lab_csub(im);
+}
+
+// lane j holds slot j (residues < 2Q); returns g_j = f_j + i f_{j+32}, canonical, scaled by 1/32.
+__device__ __forceinline__ void lab_ntt32_inv_warp(uint32_t &re, uint32_t &im, const LabWarpTw &tw, int lane) {
+#pragma unroll
+    for (int s = 4; s >= 0; s--) {
+        const int len = 16 >> s;
+        const bool upper = (lane & len) != 0;
+        const uint32_t recv = __shfl_xor_sync(0xffffffffu, lab_pack(re, im), len);
+        const uint32_t rr = lab_re(recv), ri = lab_im(recv);
+        // lower: u + v ; upper: (u - v) * zeta^-(e/2)
+        uint32_t xr = upper ? rr + 2u * LABQ - re : re + rr;
+        uint32_t xi = upper ? ri + 2u * LABQ - im : im + ri;
+        xr = lab_fold(xr);
+        xi = lab_fold(xi);
+        lab_cmul(xr, xi, lab_re(tw.g[s]), lab_im(tw.g[s]), re, im);          // < 2Q
+    }
+    re = lab_csub(re);
+    im = lab_csub(im);
+}
+#endif

@@ -1,0 +1,430 @@
+"""Host-side mirror of the reference's public API for the prover path, over the C ABI.
+
+Names follow the reference (constants.rs / structs.rs / proofgen.rs): RuntimeConstants, CRS, State,
+Verifier (as the source of challenges), Prover.proof_gen, Transcript.  The reference's toolchain (Rust)
+is not present in this image, so this ctypes harness is the caller that can run here; the Rust wrapper a
+maintainer would use is in INTEGRATION.md / rust/.  All arithmetic happens in liblabrador_b200.so on the
+GPU; numpy is only used to hold buffers.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, synth
+from ._lib import Constants, D, JL_ROWS, LabError, Q
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _seed_buf(seed):
+    s = np.frombuffer(bytes(seed), dtype=np.uint8).copy()
+    if s.size != 32:
+        raise ValueError("CRS seed must be 32 bytes")
+    return s
+
+
+class RuntimeConstants:
+    """RuntimeConstants::new(N, R) (constants.rs:234-264)."""
+
+    @staticmethod
+    def new(N, R, allow_degenerate=False):
+        c = Constants()
+        rc = _lib.lib().lab_runtime_constants(C.c_uint64(N), C.c_uint64(R), C.byref(c))
+        if rc != 0 and not allow_degenerate:
+            raise LabError(rc, f"RuntimeConstants::new({N},{R}) is degenerate (B={c.B}, T_1={c.T_1}, T_2={c.T_2})")
+        return c
+
+
+class Context:
+    """One CUDA device + stream + scratch arena (lab_ctx)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        L = _lib.lib()
+        rc = L.lab_ctx_create(C.c_int(device), C.byref(self._h))
+        if rc != 0:
+            raise LabError(rc, L.lab_last_error(None).decode())
+        self.L = L
+        self.device = device
+
+    def close(self):
+        if self._h:
+            self.L.lab_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise LabError(rc, self.L.lab_last_error(self._h).decode())
+
+    @property
+    def kernel_launches(self):
+        return int(self.L.lab_kernel_launches(self._h))
+
+    @property
+    def stream(self):
+        return self.L.lab_stream(self._h)
+
+    def sync(self):
+        self._ck(self.L.lab_sync(self._h))
+
+    def timer_start(self):
+        self._ck(self.L.lab_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_double(0)
+        self._ck(self.L.lab_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    # ---- device-pointer entry points (inputs resident in HBM) ----
+    def ntt_fwd_batch_dev(self, din, dout, n):
+        self._ck(self.L.lab_ntt_fwd_batch_dev(self._h, C.c_void_p(din), C.c_void_p(dout), C.c_size_t(n)))
+
+    def ntt_inv_batch_dev(self, din, dout, n):
+        self._ck(self.L.lab_ntt_inv_batch_dev(self._h, C.c_void_p(din), C.c_void_p(dout), C.c_size_t(n)))
+
+    def polymul_batch_dev(self, da, db, dc, n):
+        self._ck(self.L.lab_polymul_batch_dev(self._h, C.c_void_p(da), C.c_void_p(db), C.c_void_p(dc), C.c_size_t(n)))
+
+    def crs_expand_dev(self, seed, start, n_polys, dout):
+        self._ck(self.L.lab_crs_expand_dev(self._h, _p(_seed_buf(seed)), C.c_uint64(start & (2**64 - 1)), C.c_uint64(start >> 64),
+                                           C.c_size_t(n_polys), C.c_void_p(dout)))
+
+    def witness_load_dev(self, c, dS):
+        self._ck(self.L.lab_witness_load_dev(self._h, C.byref(c), C.c_void_p(dS)))
+
+    def commit_inner_dev(self, seed, row0, nrows, dT):
+        self._ck(self.L.lab_commit_inner_dev(self._h, _p(_seed_buf(seed)), C.c_uint64(row0), C.c_uint64(nrows), C.c_void_p(dT)))
+
+    def gram_dev(self, dG):
+        self._ck(self.L.lab_gram_dev(self._h, C.c_void_p(dG)))
+
+    def jl_project_dev(self, dpi, i0, ni, dp):
+        self._ck(self.L.lab_jl_project_dev(self._h, C.c_void_p(dpi), C.c_uint64(i0), C.c_uint64(ni), C.c_void_p(dp)))
+
+    def amortize_z_dev(self, dch, i0, ni, dz):
+        self._ck(self.L.lab_amortize_z_dev(self._h, C.c_void_p(dch), C.c_uint64(i0), C.c_uint64(ni), C.c_void_p(dz)))
+
+    def norm_sq_dev(self, din, n):
+        out = C.c_uint64(0)
+        self._ck(self.L.lab_norm_sq_dev(self._h, C.c_void_p(din), C.c_size_t(n), C.byref(out)))
+        return out.value
+
+    # ---- raw device memory (device-resident API) ----
+    def malloc(self, nbytes):
+        p = C.c_void_p()
+        self._ck(self.L.lab_malloc(self._h, C.c_size_t(nbytes), C.byref(p)))
+        return p.value
+
+    def free(self, dptr):
+        self._ck(self.L.lab_free(self._h, C.c_void_p(dptr)))
+
+    def h2d(self, dptr, arr):
+        arr = np.ascontiguousarray(arr)
+        self._ck(self.L.lab_memcpy_h2d(self._h, C.c_void_p(dptr), _p(arr), C.c_size_t(arr.nbytes)))
+        return arr
+
+    def d2h(self, arr, dptr):
+        self._ck(self.L.lab_memcpy_d2h(self._h, _p(arr), C.c_void_p(dptr), C.c_size_t(arr.nbytes)))
+
+    # ---- ring primitives ----
+    def ntt_fwd_batch(self, polys):
+        a = _u32(polys).reshape(-1, D)
+        out = np.empty_like(a)
+        self._ck(self.L.lab_ntt_fwd_batch(self._h, _p(a), _p(out), C.c_size_t(a.shape[0])))
+        return out
+
+    def ntt_inv_batch(self, slots):
+        a = _u32(slots).reshape(-1, D)
+        out = np.empty_like(a)
+        self._ck(self.L.lab_ntt_inv_batch(self._h, _p(a), _p(out), C.c_size_t(a.shape[0])))
+        return out
+
+    def polymul_batch(self, a, b):
+        a, b = _u32(a).reshape(-1, D), _u32(b).reshape(-1, D)
+        if a.shape != b.shape:
+            raise LabError(3, "polymul_batch: shape mismatch")
+        out = np.empty_like(a)
+        self._ck(self.L.lab_polymul_batch(self._h, _p(a), _p(b), _p(out), C.c_size_t(a.shape[0])))
+        return out
+
+    def inner_product_batch(self, v1, v2):
+        """polynomial_vec_inner_product (util.rs:496-509) for a batch: v1, v2 [B][len][64] -> [B][64]."""
+        v1, v2 = _u32(v1), _u32(v2)
+        if v1.shape != v2.shape:   # util.rs:497-502 assert
+            raise LabError(3, f"inner product not defined on vectors of unequal length. v1 length: {v1.shape}, v2 length: {v2.shape}")
+        B, ln = v1.shape[0], v1.shape[1]
+        out = np.empty((B, D), np.uint32)
+        self._ck(self.L.lab_inner_product_batch(self._h, _p(v1), _p(v2), C.c_size_t(B), C.c_size_t(ln), _p(out)))
+        return out
+
+    def decompose(self, polys, base, exp):
+        a = _u32(polys).reshape(-1, D)
+        out = np.empty((exp, a.shape[0], D), np.uint32)
+        self._ck(self.L.lab_decompose(self._h, _p(a), C.c_size_t(a.shape[0]), C.c_int64(base), C.c_int64(exp), _p(out)))
+        return out
+
+    def norm_sq(self, x):
+        a = _u32(x).reshape(-1)
+        out = C.c_uint64(0)
+        self._ck(self.L.lab_norm_sq(self._h, _p(a), C.c_size_t(a.size), C.byref(out)))
+        return out.value
+
+    def sigma_inv(self, polys):
+        a = _u32(polys).reshape(-1, D)
+        out = np.empty_like(a)
+        self._ck(self.L.lab_sigma_inv(self._h, _p(a), C.c_size_t(a.shape[0]), _p(out)))
+        return out
+
+    # ---- CRS ----
+    def crs_expand(self, seed, start, n_polys):
+        s = _seed_buf(seed)
+        out = np.empty((n_polys, D), np.uint32)
+        self._ck(self.L.lab_crs_expand(self._h, _p(s), C.c_uint64(start & (2**64 - 1)), C.c_uint64(start >> 64), C.c_size_t(n_polys), _p(out)))
+        return out
+
+    # ---- stages ----
+    def commit_inner(self, c, seed, S, row0=0, nrows=None):
+        S = _u32(S)
+        nrows = c.KAPPA - row0 if nrows is None else nrows
+        T = np.empty((c.R, nrows, D), np.uint32)
+        self._ck(self.L.lab_commit_inner(self._h, C.byref(c), _p(_seed_buf(seed)), _p(S), C.c_uint64(row0), C.c_uint64(nrows), _p(T)))
+        return T
+
+    def gram(self, c, S):
+        S = _u32(S)
+        G = np.empty((c.R, c.R, D), np.uint32)
+        self._ck(self.L.lab_gram(self._h, C.byref(c), _p(S), _p(G)))
+        return G
+
+    def jl_project(self, c, S, pi):
+        S = _u32(S)
+        pi = np.ascontiguousarray(pi, dtype=np.int8)
+        p = np.empty(JL_ROWS, np.int64)
+        acc = C.c_int(0)
+        self._ck(self.L.lab_jl_project(self._h, C.byref(c), _p(S), _p(pi), _p(p), C.byref(acc)))
+        return p, bool(acc.value)
+
+    def commit_outer_u1(self, c, seed, T, G):
+        T, G = _u32(T), _u32(G)
+        u1 = np.empty((c.KAPPA_1, D), np.uint32)
+        self._ck(self.L.lab_commit_outer_u1(self._h, C.byref(c), _p(_seed_buf(seed)), _p(T), _p(G), _p(u1)))
+        return u1
+
+    def commit_outer_u2(self, c, seed, H):
+        H = _u32(H)
+        u2 = np.empty((c.KAPPA_2, D), np.uint32)
+        self._ck(self.L.lab_commit_outer_u2(self._h, C.byref(c), _p(_seed_buf(seed)), _p(H), _p(u2)))
+        return u2
+
+    def aggregate_phi(self, c, phi, pi, psi, omega):
+        phi, omega = _u32(phi), _u32(omega)
+        pi = np.ascontiguousarray(pi, dtype=np.int8)
+        out = np.empty((c.R, c.N, D), np.uint32)
+        self._ck(self.L.lab_aggregate_phi(self._h, C.byref(c), _p(phi), _p(pi), C.c_uint32(psi), _p(omega), _p(out)))
+        return out
+
+    def h_gram(self, c, phi_final, S):
+        phi_final, S = _u32(phi_final), _u32(S)
+        H = np.empty((c.R, c.R, D), np.uint32)
+        self._ck(self.L.lab_h_gram(self._h, C.byref(c), _p(phi_final), _p(S), _p(H)))
+        return H
+
+    def amortize_z(self, c, S, ch):
+        S, ch = _u32(S), _u32(ch)
+        z = np.empty((c.N, D), np.uint32)
+        self._ck(self.L.lab_amortize_z(self._h, C.byref(c), _p(S), _p(ch), _p(z)))
+        return z
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+class CRS:
+    """CRS (structs.rs:27-190).  `from_seed` is the addition parity needs (the reference's CRS::new draws
+    the seed from thread_rng and keeps it private, structs.rs:173-189)."""
+
+    def __init__(self, constants, base_seed, ctx=None):
+        self.constants = constants
+        self.base_seed = bytes(base_seed)
+        self.ctx = ctx or default_context()
+
+    @classmethod
+    def new(cls, constants, ctx=None):
+        import os
+        return cls(constants, os.urandom(32), ctx)
+
+    @classmethod
+    def from_seed(cls, constants, seed, ctx=None):
+        return cls(constants, seed, ctx)
+
+    def _fetch(self, which, i=0, j=0, k=0, row=0):
+        c = self.constants
+        n = c.N if which == "A" else (c.KAPPA if which == "B" else c.KAPPA_2)
+        out = np.empty((n, D), np.uint32)
+        self.ctx._ck(self.ctx.L.lab_crs_fetch(self.ctx._h, C.byref(c), _p(_seed_buf(self.base_seed)), C.c_int(ord(which)),
+                                              C.c_uint64(i), C.c_uint64(j), C.c_uint64(k), C.c_uint64(row), _p(out)))
+        return out
+
+    def fetch_A_row(self, row):
+        return self._fetch("A", row=row)
+
+    def fetch_B_ik_row(self, i, k, row):
+        return self._fetch("B", i=i, k=k, row=row)
+
+    def fetch_C_ijk(self, i, j, k):
+        return self._fetch("C", i=i, j=j, k=k)
+
+    def fetch_D_ijk(self, i, j, k):
+        return self._fetch("D", i=i, j=j, k=k)
+
+
+class State:
+    """State (structs.rs:269-388) with K = L = 1: phi [R][N][64], a [R][R][64] symmetric, b [64]."""
+
+    def __init__(self, phi, a, b):
+        self.phi_k = [_u32(phi)]
+        self.a_k = [_u32(a)]
+        self.b_k = [_u32(b)]
+        self.phi_prime_k, self.a_prime_k = self.phi_k, self.a_k          # structs.rs:367-372
+        self.b_prime_k = [int(self.b_k[0][0])]                           # b.eval(0), structs.rs:373
+
+    @classmethod
+    def new(cls, witness, constants, seed=synth.SEED, ctx=None):
+        """gen_f (structs.rs:289-350): random symmetric a, random phi, b = sum a_ij <s_i,s_j> + sum <phi_i,s_i>."""
+        ctx = ctx or default_context()
+        c = constants
+        S = _u32(witness)
+        phi, a = synth.generate_statement_inputs(c.N, c.R, seed)
+        G = ctx.gram(c, S)
+        ag = ctx.polymul_batch(a.reshape(-1, D), G.reshape(-1, D)).astype(np.uint64).sum(axis=0)
+        ps = ctx.inner_product_batch(phi, S).astype(np.uint64).sum(axis=0)
+        b = ((ag + ps) % Q).astype(np.uint32)
+        return cls(phi, a, b)
+
+
+class Verifier:
+    """The part of Verifier the prover talks to (verification.rs:441-513,553-579): a replayable challenge
+    source.  Challenges may be given explicitly (dict as synth.sample_challenges returns) or drawn from the
+    seeded PRG."""
+
+    def __init__(self, b_prime_k, constants, challenges=None, seed=synth.SEED, n_attempts=6):
+        self.b_prime = list(b_prime_k)
+        self.constants = constants
+        c = constants
+        self.challenges = challenges if challenges is not None else synth.sample_challenges(c.N, c.R, seed, n_attempts)
+
+    @classmethod
+    def new(cls, b_prime_k, constants, **kw):
+        return cls(b_prime_k, constants, **kw)
+
+    def sample_jl_projection(self, attempt=0):
+        return self.challenges["pi"][attempt]
+
+    def generate_psi(self):
+        return [self.challenges["psi"]]
+
+    def generate_omega(self):
+        return self.challenges["omega"]
+
+    def fetch_alpha(self):
+        return [self.challenges["alpha"]]
+
+    def fetch_beta(self):
+        return [self.challenges["beta"]]
+
+    def fetch_challenge(self, i):
+        return self.challenges["c"][i]
+
+
+class Transcript:
+    """Transcript (structs.rs:192-209), dense arrays.  pi_i_all is the accepted JL attempt lifted to Z_q."""
+
+    FIELDS = ("u_1", "projection", "psi", "omega", "b_prime_prime", "alpha", "beta", "u_2", "c", "z", "t_i_all", "g_mat", "h_mat")
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    @property
+    def pi_i_all(self):
+        pi = self.pi_accepted.astype(np.int32)
+        return np.where(pi < 0, pi + Q, pi).astype(np.uint32)
+
+    def as_oracle_dict(self):
+        return {"u_1": self.u_1, "projection_int": self.projection_int, "projection": self.projection,
+                "b_prime_prime": self.b_prime_prime[0], "u_2": self.u_2, "z": self.z, "t": self.t_i_all,
+                "g": self.g_mat, "h": self.h_mat, "phi_final": self.phi_final, "jl_attempt": self.jl_attempt}
+
+
+class Prover:
+    """Prover (proofgen.rs:14-28)."""
+
+    def __init__(self, witness, verifier, constants, ctx=None):
+        self.witness = _u32(witness)
+        self.verifier = verifier
+        self.constants = constants
+        self.ctx = ctx or default_context()
+
+    @classmethod
+    def new(cls, witness, verifier, constants, ctx=None):
+        return cls(witness, verifier, constants, ctx)
+
+    def jl_project(self, attempt=0):
+        """Prover::jl_project (proofgen.rs:429-457): (projection ints, Pi lifted)."""
+        pi = self.verifier.sample_jl_projection(attempt)
+        p, _ = self.ctx.jl_project(self.constants, self.witness, pi)
+        lifted = np.where(pi < 0, pi.astype(np.int32) + Q, pi).astype(np.uint32)
+        return p, lifted
+
+    def proof_gen(self, st, crs):
+        """Prover::proof_gen (proofgen.rs:30-427) -> Transcript."""
+        c, ctx, ch = self.constants, self.ctx, self.verifier.challenges
+        pi = np.ascontiguousarray(ch["pi"], dtype=np.int8)
+        if pi.ndim == 3:
+            pi = pi[None]
+        omega, alpha, beta, cc = _u32(ch["omega"]), _u32(ch["alpha"]), _u32(ch["beta"]), _u32(ch["c"])
+        phi, a, b = st.phi_k[0], st.a_k[0], st.b_k[0]
+        cst = _lib.CState(_p(phi), _p(a), _p(b))
+        cch = _lib.CChallenges(_p(pi), pi.shape[0], int(ch["psi"]), _p(omega), _p(alpha), _p(beta), _p(cc))
+        out = {
+            "u_1": np.zeros((c.KAPPA_1, D), np.uint32), "projection_int": np.zeros(JL_ROWS, np.int64),
+            "projection": np.zeros(JL_ROWS, np.uint32), "b_prime_prime": np.zeros(D, np.uint32),
+            "u_2": np.zeros((c.KAPPA_2, D), np.uint32), "z": np.zeros((c.N, D), np.uint32),
+            "t": np.zeros((c.R, c.KAPPA, D), np.uint32), "g": np.zeros((c.R, c.R, D), np.uint32),
+            "h": np.zeros((c.R, c.R, D), np.uint32), "phi_final": np.zeros((c.R, c.N, D), np.uint32),
+        }
+        tr = _lib.CTranscript(_p(out["u_1"]), 0, _p(out["projection_int"]), _p(out["projection"]), _p(out["b_prime_prime"]),
+                              _p(out["u_2"]), _p(out["z"]), _p(out["t"]), _p(out["g"]), _p(out["h"]), _p(out["phi_final"]), 0)
+        S = self.witness
+        rc = ctx.L.lab_prove(ctx._h, C.byref(c), _p(_seed_buf(crs.base_seed)), _p(S), C.byref(cst), C.byref(cch), C.byref(tr))
+        if rc == 1:
+            raise LabError(rc, "failed JL...")                                     # proofgen.rs:176
+        ctx._ck(rc)
+        return Transcript(u_1=out["u_1"], pi_accepted=pi[tr.jl_attempt], jl_attempt=tr.jl_attempt,
+                          projection_int=out["projection_int"], projection=out["projection"],
+                          psi=[[int(ch["psi"])]], omega=[omega], b_prime_prime=[out["b_prime_prime"]],
+                          alpha=[alpha], beta=[beta], u_2=out["u_2"], c=cc, z=out["z"], t_i_all=out["t"],
+                          g_mat=out["g"], h_mat=out["h"], phi_final=out["phi_final"], norm_sum=int(tr.norm_sum))
+
+
+def generate_witness(constants, seed=synth.SEED):
+    """generate_witness (proofgen.rs:460-518), seeded."""
+    return synth.generate_witness(constants.N, constants.R, constants.BETA_BOUND, seed)

@@ -1,0 +1,77 @@
+#!/usr/bin/env python3
+"""Kernel microbenchmarks on one B200 (CUDA-event timing on the ctx stream, inputs resident in HBM).
+Prints one JSON object per measurement.  Used to pick kernel variants and to measure the INT32-ALU
+ceiling the CRS kernels are judged against."""
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import labrador_b200 as lb  # noqa: E402
+from labrador_b200 import synth  # noqa: E402
+
+SEED32 = bytes(range(32))
+
+
+def timeit(ctx, fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    ctx.sync()
+    ts = []
+    for _ in range(reps):
+        ctx.timer_start()
+        fn()
+        ts.append(ctx.timer_stop())
+    return min(ts), sorted(ts)[len(ts) // 2]
+
+
+def main():
+    ctx = lb.Context(0)
+    which = sys.argv[1:] or ["ntt", "crs", "commit"]
+    if "ntt" in which:
+        for logn in (16, 20, 22, 24):
+            n = 1 << logn
+            nbytes = n * 256
+            da, db, dc = ctx.malloc(nbytes), ctx.malloc(nbytes), ctx.malloc(nbytes)
+            a = synth.prg_zq(1, 1, min(n, 1 << 20) * 64).reshape(-1, 64)
+            reps = n // a.shape[0]
+            for r in range(reps):
+                ctx.h2d(da + r * a.nbytes, a)
+                ctx.h2d(db + r * a.nbytes, a)
+            ctx.sync()
+            for name, fn, bpp in (("ntt_fwd", lambda: ctx.ntt_fwd_batch_dev(da, dc, n), 512),
+                                  ("ntt_inv", lambda: ctx.ntt_inv_batch_dev(da, dc, n), 512),
+                                  ("polymul", lambda: ctx.polymul_batch_dev(da, db, dc, n), 768)):
+                best, med = timeit(ctx, fn)
+                print(json.dumps({"kernel": name, "log2_polys": logn, "ms_best": best, "ms_median": med,
+                                  "polys_per_s": n / (med * 1e-3), "GBps_algorithmic": n * bpp / (med * 1e-3) / 1e9}), flush=True)
+            for d in (da, db, dc):
+                ctx.free(d)
+    if "crs" in which:
+        for logn in (16, 20):
+            n = 1 << logn
+            dout = ctx.malloc(n * 256)
+            best, med = timeit(ctx, lambda: ctx.crs_expand_dev(SEED32, 12345, n, dout), reps=3, warm=1)
+            print(json.dumps({"kernel": "crs_expand", "log2_polys": logn, "ms_median": med, "coeffs_per_s": n * 64 / (med * 1e-3),
+                              "chacha_blocks_per_s": n * 64 / (med * 1e-3)}), flush=True)
+            ctx.free(dout)
+    if "commit" in which:
+        for (N, R, rows) in ((256, 2, 4096), (256, 8, 4096), (256, 32, 4096), (256, 64, 4096), (4096, 64, 1024)):
+            c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
+            S = synth.uniform_witness(N, R)
+            dS = ctx.malloc(S.nbytes)
+            ctx.h2d(dS, S)
+            ctx.witness_load_dev(c, dS)
+            dT = ctx.malloc(R * rows * 256)
+            best, med = timeit(ctx, lambda: ctx.commit_inner_dev(SEED32, 0, rows, dT), reps=3, warm=1)
+            blocks = rows * N * 64
+            print(json.dumps({"kernel": "commit_inner", "N": N, "R": R, "rows": rows, "ms_median": med,
+                              "chacha_blocks_per_s": blocks / (med * 1e-3), "cmacs_per_s": rows * N * R * 32 / (med * 1e-3)}), flush=True)
+            ctx.free(dS); ctx.free(dT)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
