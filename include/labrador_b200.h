@@ -185,12 +185,25 @@ int lab_prove_batch(lab_ctx *ctx, const lab_constants *c, size_t n_statements, c
 int lab_witness_load_dev(lab_ctx *ctx, const lab_constants *c, const uint32_t *S_dev);
 /* rows [row0,row0+nrows) of T for the loaded witness; T_dev: [R][nrows][64] */
 int lab_commit_inner_dev(lab_ctx *ctx, const uint8_t seed[32], uint64_t row0, uint64_t nrows, uint32_t *T_dev);
-int lab_gram_dev(lab_ctx *ctx, uint32_t *G_dev);
+/* rows i in [i0,i0+ni) of g for the loaded witness; G_dev: [ni][R][64] (the (i,j) tile sharding of S2) */
+int lab_gram_dev(lab_ctx *ctx, uint64_t i0, uint64_t ni, uint32_t *G_dev);
 /* i in [i0,i0+ni): partial projection of those witness vectors; p_dev: int64[256] (overwritten) */
 int lab_jl_project_dev(lab_ctx *ctx, const int8_t *pi_dev, uint64_t i0, uint64_t ni, int64_t *p_dev);
 /* z restricted to witness vectors [i0,i0+ni) as exact int64 partial sums are not needed: z is mod q;
  * z_dev: [N][64] canonical partial (sum over the given i range) */
 int lab_amortize_z_dev(lab_ctx *ctx, const uint32_t *ch_dev, uint64_t i0, uint64_t ni, uint32_t *z_dev);
+
+
+/* ---- seeded synthetic inputs / device-side challenge source ----
+ * SplitMix64 counter PRG, value(idx) = mix(seed + stream * 0xD1342543DE82EF95 + (idx + 1) * 0x9E3779B97F4A7C15).
+ * lab_synth_zq_dev: uniform residues floor(u64 * q / 2^64) for idx in [start, start + n).
+ * lab_synth_pi_dev: JL matrix entries {-1,0,1} with P = (1/4,1/2,1/4) (verification.rs:553-566), two bits per
+ * entry from stream 5 + (attempt << 8), row-major fill order. */
+int lab_synth_zq_dev(lab_ctx *ctx, uint64_t seed, uint64_t stream, uint64_t start, size_t n, uint32_t *out_dev);
+int lab_synth_pi_dev(lab_ctx *ctx, uint64_t seed, uint64_t attempt, uint64_t first_entry /* multiple of 32 */, size_t total, int8_t *out_dev);
+/* measured ALU-pipe (LOP3 + SHF) ceiling in lane-operations per second: the roofline denominator of the
+ * ChaCha20-bound kernels (BASELINE.md section 2 asks for a measured INT32 figure) */
+int lab_bench_alu_peak(lab_ctx *ctx, double *lane_ops_per_s);
 
 #ifdef __cplusplus
 }

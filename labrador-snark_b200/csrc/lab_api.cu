@@ -366,9 +366,11 @@ static int d_outer_u2(lab_ctx *ctx, const lab_constants *c, const LabSeed &seed,
     segs.push_back(MvSeg{off_D(c, 0, 0, 0), LAB_D, T1 * K2 * LAB_D, K2 * LAB_D, (uint32_t)T1, (uint32_t)(npairs * T1), 0u});
     return d_crs_matvec(ctx, seed, segs, 0, K2, V, du2);
 }
-static int d_gram(lab_ctx *ctx, const uint32_t *What, uint64_t N, uint64_t R, uint32_t *Ghat /* scratch R*R*32 */, uint32_t *dG) {
-    LAUNCH(k_ip_hat, (unsigned)(R * R), 256, What, (size_t)R, (size_t)1, What, (size_t)R, (size_t)1, (size_t)N, (size_t)R, 1u, 0, Ghat);
-    return d_inv_hat(ctx, Ghat, dG, R * R);
+// rows i in [i0, i0+ni) of g: dG is [ni][R][64]
+static int d_gram(lab_ctx *ctx, const uint32_t *What, uint64_t N, uint64_t R, uint64_t i0, uint64_t ni, uint32_t *Ghat /* scratch ni*R*32 */, uint32_t *dG) {
+    if (!ni) return LAB_OK;
+    LAUNCH(k_ip_hat, (unsigned)(ni * R), 256, What + i0 * 32, (size_t)R, (size_t)1, What, (size_t)R, (size_t)1, (size_t)N, (size_t)R, 1u, 0, Ghat);
+    return d_inv_hat(ctx, Ghat, dG, ni * R);
 }
 static int d_jl(lab_ctx *ctx, const int8_t *dPi, const uint32_t *dS, uint64_t ND, uint64_t i0, uint64_t ni, unsigned long long *dp) {
     CK(cudaMemsetAsync(dp, 0, LAB_JL_ROWS * sizeof(unsigned long long), ctx->stream));
@@ -564,7 +566,7 @@ extern "C" int lab_gram(lab_ctx *ctx, const lab_constants *c, const uint32_t *S,
     TRY(load_witness(ctx, c, S, &dS, &What));
     TRY(arena_alloc(ctx, c->R * c->R * 32, &Ghat));
     TRY(arena_alloc(ctx, c->R * c->R * 64, &dG));
-    TRY(d_gram(ctx, What, c->N, c->R, Ghat, dG));
+    TRY(d_gram(ctx, What, c->N, c->R, 0, c->R, Ghat, dG));
     TRY(download(ctx, G, dG, c->R * c->R * 64));
     return lab_sync(ctx);
 }
@@ -686,7 +688,7 @@ static int prove_one(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_by
     uint32_t *Ghat, *dG;
     TRY(arena_alloc(ctx, R * R * 32, &Ghat));
     TRY(arena_alloc(ctx, R * R * 64, &dG));
-    TRY(d_gram(ctx, What, N, R, Ghat, dG));
+    TRY(d_gram(ctx, What, N, R, 0, R, Ghat, dG));
     // S3: u_1 (proofgen.rs:101-153)
     uint32_t *du1;
     TRY(arena_alloc(ctx, K1 * 64, &du1));
@@ -845,12 +847,46 @@ extern "C" int lab_commit_inner_dev(lab_ctx *ctx, const uint8_t seed[32], uint64
     if (row0 + nrows > ctx->wc.KAPPA) FAIL(LAB_ERR_SHAPE, "row range exceeds KAPPA");
     return d_commit_inner(ctx, make_seed(seed), ctx->What, ctx->wc.N, ctx->wc.R, row0, nrows, T_dev);
 }
-extern "C" int lab_gram_dev(lab_ctx *ctx, uint32_t *G_dev) {
+extern "C" int lab_gram_dev(lab_ctx *ctx, uint64_t i0, uint64_t ni, uint32_t *G_dev) {
     NEED_WITNESS();
+    if (i0 + ni > ctx->wc.R) FAIL(LAB_ERR_SHAPE, "witness range exceeds R");
     arena_reset(ctx);
     uint32_t *Ghat;
-    TRY(arena_alloc(ctx, ctx->wc.R * ctx->wc.R * 32, &Ghat));
-    return d_gram(ctx, ctx->What, ctx->wc.N, ctx->wc.R, Ghat, G_dev);
+    TRY(arena_alloc(ctx, ni * ctx->wc.R * 32, &Ghat));
+    return d_gram(ctx, ctx->What, ctx->wc.N, ctx->wc.R, i0, ni, Ghat, G_dev);
+}
+// ---- seeded synthetic inputs / device-side challenge source ----
+static uint64_t prg_base(uint64_t seed, uint64_t stream) { return seed + stream * 0xD1342543DE82EF95ull; }
+extern "C" int lab_synth_zq_dev(lab_ctx *ctx, uint64_t seed, uint64_t stream, uint64_t start, size_t n, uint32_t *out_dev) {
+    if (!n) return LAB_OK;
+    LAUNCH(k_synth_zq, grid_for(n, 1024, ctx->sms * 16), 256, prg_base(seed, stream), start, n, out_dev);
+    return LAB_OK;
+}
+extern "C" int lab_synth_pi_dev(lab_ctx *ctx, uint64_t seed, uint64_t attempt, uint64_t first_entry, size_t total, int8_t *out_dev) {
+    if (!total) return LAB_OK;
+    if (first_entry % 32) FAIL(LAB_ERR_PARAMS, "first_entry must be a multiple of 32");
+    // entry e comes from PRG word e / 32: shifting the word index by first_entry / 32 is a shift of the PRG base
+    const uint64_t base = prg_base(seed, 5 + (attempt << 8)) + (first_entry / 32) * 0x9E3779B97F4A7C15ull;
+    LAUNCH(k_synth_pi, grid_for((total + 31) / 32, 256, ctx->sms * 16), 256, base, total, out_dev);
+    return LAB_OK;
+}
+// measured ALU-pipe ceiling in lane-ops/s (roofline denominator of the ChaCha-bound kernels)
+extern "C" int lab_bench_alu_peak(lab_ctx *ctx, double *lane_ops_per_s) {
+    CallScope cs(ctx);
+    const int iters = 4096, blocks = ctx->sms * 16;
+    uint32_t *d;
+    TRY(arena_alloc(ctx, (size_t)blocks * 256, &d));
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        TRY(lab_timer_start(ctx));
+        LAUNCH(k_alu_peak, blocks, 256, d, iters);
+        double ms = 0;
+        TRY(lab_timer_stop(ctx, &ms));
+        double rate = (double)blocks * 256.0 * iters * 4 * 8 * 2 / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    *lane_ops_per_s = best;
+    return LAB_OK;
 }
 extern "C" int lab_jl_project_dev(lab_ctx *ctx, const int8_t *pi_dev, uint64_t i0, uint64_t ni, int64_t *p_dev) {
     NEED_WITNESS();

@@ -394,15 +394,24 @@ __device__ __forceinline__ void crs_poly_hat(const LabSeed &seed, uint64_t lo, u
 // ------------------------------------------------------------------------------------------------
 constexpr int KA_RT = 4;
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 template <int IC>
 __global__ void __launch_bounds__(256, 2) k_commit_inner(LabSeed seed, const uint32_t *__restrict__ What, uint32_t N, uint32_t R,
                                                           uint64_t row0, uint64_t nrows, uint32_t i_base, uint32_t *__restrict__ T) {
+    constexpr int IT = 8 * IC;                                   // witness vectors per CTA pass
     __shared__ uint32_t Abuf[2][8][32];
+    __shared__ __align__(16) uint32_t Sbuf[2][2][IT][32];        // [buffer][column][i][slot], filled by cp.async
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const LabWarpTw tw = lab_warp_tw(lane);
     const uint64_t rblk = (uint64_t)blockIdx.x * KA_RT;          // first row of this CTA, relative to row0
     const int grow = w & 3, gcol = w >> 2;                       // generation role
-    const uint32_t i0 = i_base + (uint32_t)w * IC;                // MAC role: witness vectors i0..i0+IC
+    const int il0 = w * IC;                                      // MAC role: local witness vectors il0..il0+IC
     uint32_t accr[KA_RT][IC], acci[KA_RT][IC];
 #pragma unroll
     for (int r = 0; r < KA_RT; r++)
@@ -412,7 +421,15 @@ __global__ void __launch_bounds__(256, 2) k_commit_inner(LabSeed seed, const uin
     int pending = 0;
     for (uint32_t n0 = 0, step = 0; n0 < N; n0 += 2, step++) {
         const int buf = step & 1;
-        {   // generate
+        // 1. start fetching this step's slice of the transformed witness (L2 -> smem); it lands while
+        //    the ChaCha blocks below are computed
+        for (int q = threadIdx.x; q < 2 * IT * 8; q += 256) {
+            const int nn = q / (IT * 8), rem = q % (IT * 8), il = rem >> 3, chk = rem & 7;
+            if (n0 + nn < N && i_base + il < R)
+                cp_async16(&Sbuf[buf][nn][il][chk * 4], What + ((size_t)(n0 + nn) * R + i_base + il) * 32 + chk * 4);
+        }
+        cp_async_commit();
+        {   // 2. generate one CRS polynomial per warp, transformed
             const uint64_t row = row0 + rblk + grow;
             const uint32_t n = n0 + gcol;
             uint32_t re = 0, im = 0;
@@ -423,11 +440,12 @@ __global__ void __launch_bounds__(256, 2) k_commit_inner(LabSeed seed, const uin
             }
             Abuf[buf][w][lane] = lab_pack(re, im);
         }
+        cp_async_wait_all();
         __syncthreads();
+        // 3. multiply-accumulate: RT rows x IC witness vectors per thread, lane = slot
 #pragma unroll
         for (int nn = 0; nn < 2; nn++) {
-            const uint32_t n = n0 + nn;
-            if (n < N) {
+            if (n0 + nn < N) {
                 uint32_t ar[KA_RT], am[KA_RT], nam[KA_RT];
 #pragma unroll
                 for (int r = 0; r < KA_RT; r++) {
@@ -436,8 +454,8 @@ __global__ void __launch_bounds__(256, 2) k_commit_inner(LabSeed seed, const uin
                 }
 #pragma unroll
                 for (int ii = 0; ii < IC; ii++) {
-                    if (i0 + ii < R) {
-                        uint32_t s = __ldg(What + ((size_t)n * R + i0 + ii) * 32 + lane);
+                    if (i_base + il0 + ii < R) {
+                        uint32_t s = Sbuf[buf][nn][il0 + ii][lane];
                         uint32_t sr = lab_re(s), sm_ = lab_im(s);
 #pragma unroll
                         for (int r = 0; r < KA_RT; r++) {
@@ -463,8 +481,9 @@ __global__ void __launch_bounds__(256, 2) k_commit_inner(LabSeed seed, const uin
         for (int ii = 0; ii < IC; ii++) {
             uint32_t re = lab_canon(accr[r][ii]), im = lab_canon(acci[r][ii]);
             lab_ntt32_inv_warp(re, im, tw, lane);
-            if (rblk + r < nrows && i0 + ii < R) {
-                uint32_t *dst = T + (((size_t)(i0 + ii)) * nrows + rblk + r) * 64;
+            const uint32_t i = i_base + il0 + ii;
+            if (rblk + r < nrows && i < R) {
+                uint32_t *dst = T + ((size_t)i * nrows + rblk + r) * 64;
                 dst[lane] = re;
                 dst[lane + 32] = im;
             }
@@ -607,5 +626,55 @@ __global__ void k_phi_pp(const uint32_t *__restrict__ phi, const uint32_t *__res
     out[idx] = lab_canon(lab_canon(phi[idx]) * psi + conj);
 }
 // int64 projection -> mod Q lift (proofgen.rs:186) is done on the host (256 values)
+
+
+// ------------------------------------------------------------------------------------------------
+// seeded synthetic inputs on the device (same SplitMix64 counter PRG as labrador_b200/synth.py and the
+// oracle's generators): uniform Z_q values and JL matrices {-1,0,1} with P = (1/4,1/2,1/4)
+// (verification.rs:553-566).  Used by bench.py and as the device-side challenge source.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t prg_u64(uint64_t base, uint64_t idx) {
+    uint64_t z = base + (idx + 1ull) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void k_synth_zq(uint64_t base, uint64_t start, size_t n, uint32_t *__restrict__ out) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; idx < n; idx += stride) out[idx] = (uint32_t)__umul64hi(prg_u64(base, start + idx), (uint64_t)LABQ);
+}
+__global__ void k_synth_pi(uint64_t base, size_t total, int8_t *__restrict__ out) {
+    size_t wd = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t nwords = (total + 31) / 32;
+    for (; wd < nwords; wd += stride) {
+        const uint64_t bits = prg_u64(base, wd);
+        for (int t = 0; t < 32 && wd * 32 + t < total; t++) {
+            const unsigned two = (unsigned)(bits >> (2 * t)) & 3u;
+            out[wd * 32 + t] = (int8_t)(two == 0 ? -1 : (two == 3 ? 1 : 0));
+        }
+    }
+}
+// ALU-pipe ceiling: 8 independent xor+rotate chains per thread (LOP3 + SHF, the ChaCha20 quarter-round
+// mix minus the adds, which can issue on the FMA pipe).  2 * 8 * iters ALU-pipe ops per thread.
+__global__ void __launch_bounds__(256) k_alu_peak(uint32_t *out, int iters) {
+    uint32_t x[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) x[j] = threadIdx.x * 2654435761u + j * 40503u + blockIdx.x;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                uint32_t t = x[j] ^ x[(j + 3) & 7];
+                x[j] = __funnelshift_l(t, t, 7 + u);
+            }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc ^= x[j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
 
 }  // namespace lab

@@ -60,6 +60,7 @@ SYMBOLS = [
     "lab_commit_inner", "lab_gram", "lab_jl_project", "lab_commit_outer_u1", "lab_commit_outer_u2",
     "lab_aggregate_phi", "lab_h_gram", "lab_amortize_z", "lab_prove", "lab_prove_batch",
     "lab_witness_load_dev", "lab_commit_inner_dev", "lab_gram_dev", "lab_jl_project_dev", "lab_amortize_z_dev",
+    "lab_synth_zq_dev", "lab_synth_pi_dev", "lab_bench_alu_peak",
 ]
 
 _lib = None

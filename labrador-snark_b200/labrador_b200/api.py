@@ -107,8 +107,19 @@ class Context:
     def commit_inner_dev(self, seed, row0, nrows, dT):
         self._ck(self.L.lab_commit_inner_dev(self._h, _p(_seed_buf(seed)), C.c_uint64(row0), C.c_uint64(nrows), C.c_void_p(dT)))
 
-    def gram_dev(self, dG):
-        self._ck(self.L.lab_gram_dev(self._h, C.c_void_p(dG)))
+    def gram_dev(self, i0, ni, dG):
+        self._ck(self.L.lab_gram_dev(self._h, C.c_uint64(i0), C.c_uint64(ni), C.c_void_p(dG)))
+
+    def synth_zq_dev(self, seed, stream, start, n, dout):
+        self._ck(self.L.lab_synth_zq_dev(self._h, C.c_uint64(seed), C.c_uint64(stream), C.c_uint64(start), C.c_size_t(n), C.c_void_p(dout)))
+
+    def synth_pi_dev(self, seed, attempt, first_entry, total, dout):
+        self._ck(self.L.lab_synth_pi_dev(self._h, C.c_uint64(seed), C.c_uint64(attempt), C.c_uint64(first_entry), C.c_size_t(total), C.c_void_p(dout)))
+
+    def alu_peak(self):
+        v = C.c_double(0)
+        self._ck(self.L.lab_bench_alu_peak(self._h, C.byref(v)))
+        return v.value
 
     def jl_project_dev(self, dpi, i0, ni, dp):
         self._ck(self.L.lab_jl_project_dev(self._h, C.c_void_p(dpi), C.c_uint64(i0), C.c_uint64(ni), C.c_void_p(dp)))

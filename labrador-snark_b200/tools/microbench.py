@@ -57,6 +57,17 @@ def main():
             print(json.dumps({"kernel": "crs_expand", "log2_polys": logn, "ms_median": med, "coeffs_per_s": n * 64 / (med * 1e-3),
                               "chacha_blocks_per_s": n * 64 / (med * 1e-3)}), flush=True)
             ctx.free(dout)
+    if "commit1" in which:      # one mid-size launch pair, for ncu --set full captures
+        N, R, rows = 1024, 64, 2048
+        c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
+        dS = ctx.malloc(R * N * 256)
+        ctx.synth_zq_dev(synth.SEED, 1, 0, R * N * 64, dS)
+        ctx.witness_load_dev(c, dS)
+        dT = ctx.malloc(R * rows * 256)
+        best, med = timeit(ctx, lambda: ctx.commit_inner_dev(SEED32, 0, rows, dT), reps=2, warm=1)
+        print(json.dumps({"kernel": "commit_inner", "N": N, "R": R, "rows": rows, "ms_median": med,
+                          "chacha_blocks_per_s": rows * N * 64 / (med * 1e-3)}), flush=True)
+        ctx.free(dS); ctx.free(dT)
     if "commit" in which:
         for (N, R, rows) in ((256, 2, 4096), (256, 8, 4096), (256, 32, 4096), (256, 64, 4096), (4096, 64, 1024)):
             c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
