@@ -174,12 +174,8 @@ def main():
     kappa, ND = c.KAPPA, N * D
 
     # ---- shards (strong scaling): rows of A / T, rows of g, witness vectors for JL and z ----
-    def split(total, parts, idx):
-        base, rem = divmod(total, parts)
-        lo = idx * base + min(idx, rem)
-        return lo, base + (1 if idx < rem else 0)
-    row0, nrows = split(kappa, world, rank)
-    i0, ni = split(R, world, rank)
+    pl = lb.shard.plan(kappa, R, world, rank)
+    row0, nrows, i0, ni = pl["row0"], pl["nrows"], pl["i0"], pl["ni"]
 
     # ---- device-resident inputs (torch owns the memory; the library gets raw pointers) ----
     S = torch.empty((R, N, D), dtype=torch.int32, device=dev)

@@ -14,8 +14,10 @@
 constexpr uint32_t LABQ = 8191u;
 constexpr int LABD = 64;
 
-// x == fold(x) (mod Q); fold(x) <= Q + (x >> 13)
-LAB_HD uint32_t lab_fold(uint32_t x) { return (x & LABQ) + (x >> 13); }
+// x == fold(x) (mod Q); fold(x) = (x & Q) + (x >> 13) <= Q + (x >> 13).  Written as x - (x >> 13) * Q so that it
+// compiles to one shift (ALU pipe) + one multiply-add (FMA pipe): the ChaCha-bound kernels are limited by the ALU
+// pipe and the transform kernels get an even ALU/FMA split.
+LAB_HD uint32_t lab_fold(uint32_t x) { return x - (x >> 13) * LABQ; }
 // x in [0, 2Q) -> [0, Q)
 LAB_HD uint32_t lab_csub(uint32_t x) {
     uint32_t y = x - LABQ;

@@ -405,13 +405,30 @@ template <int IC>
 __global__ void __launch_bounds__(256, 2) k_commit_inner(LabSeed seed, const uint32_t *__restrict__ What, uint32_t N, uint32_t R,
                                                           uint64_t row0, uint64_t nrows, uint32_t i_base, uint32_t *__restrict__ T) {
     constexpr int IT = 8 * IC;                                   // witness vectors per CTA pass
-    __shared__ uint32_t Abuf[2][8][32];
-    __shared__ __align__(16) uint32_t Sbuf[2][2][IT][32];        // [buffer][column][i][slot], filled by cp.async
+    constexpr int NCP = (2 * IT * 8 + 255) / 256;                // 16-byte cp.async chunks per thread per step
+    __shared__ uint32_t Are[2][8][32], Aim[2][8][32], Anim[2][8][32];   // generated polys: re, im, Q - im
+    __shared__ __align__(16) uint32_t Sbuf[2][2][IT][32];        // [buffer][column][i][slot] packed, filled by cp.async
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const LabWarpTw tw = lab_warp_tw(lane);
     const uint64_t rblk = (uint64_t)blockIdx.x * KA_RT;          // first row of this CTA, relative to row0
     const int grow = w & 3, gcol = w >> 2;                       // generation role
     const int il0 = w * IC;                                      // MAC role: local witness vectors il0..il0+IC
+    const bool gen_row_ok = rblk + grow < nrows;
+    // counter of coefficient 0 of A[row][n]: (row * N + n) * 64 (structs.rs:55-72); < 2^64 for every supported shape
+    uint64_t ctr = ((row0 + rblk + grow) * (uint64_t)N + gcol) * 64ull;
+    // per-thread cp.async sources / destinations (advance by two witness columns per step)
+    const uint32_t *src[NCP];
+    uint32_t dsto[NCP], cp_nn[NCP];
+    bool cp_ok[NCP];
+#pragma unroll
+    for (int t = 0; t < NCP; t++) {
+        const int q = threadIdx.x + 256 * t;
+        const int nn = q / (IT * 8), rem = q % (IT * 8), il = rem >> 3, chk = rem & 7;
+        cp_ok[t] = q < 2 * IT * 8 && i_base + il < R;
+        cp_nn[t] = nn;
+        src[t] = What + ((size_t)nn * R + i_base + il) * 32 + chk * 4;
+        dsto[t] = ((nn * IT + il) * 32 + chk * 4);
+    }
     uint32_t accr[KA_RT][IC], acci[KA_RT][IC];
 #pragma unroll
     for (int r = 0; r < KA_RT; r++)
@@ -423,40 +440,39 @@ __global__ void __launch_bounds__(256, 2) k_commit_inner(LabSeed seed, const uin
         const int buf = step & 1;
         // 1. start fetching this step's slice of the transformed witness (L2 -> smem); it lands while
         //    the ChaCha blocks below are computed
-        for (int q = threadIdx.x; q < 2 * IT * 8; q += 256) {
-            const int nn = q / (IT * 8), rem = q % (IT * 8), il = rem >> 3, chk = rem & 7;
-            if (n0 + nn < N && i_base + il < R)
-                cp_async16(&Sbuf[buf][nn][il][chk * 4], What + ((size_t)(n0 + nn) * R + i_base + il) * 32 + chk * 4);
+#pragma unroll
+        for (int t = 0; t < NCP; t++) {
+            if (cp_ok[t] && n0 + cp_nn[t] < N) cp_async16(&Sbuf[buf][0][0][0] + dsto[t], src[t]);
+            src[t] += (size_t)2 * R * 32;
         }
         cp_async_commit();
         {   // 2. generate one CRS polynomial per warp, transformed
-            const uint64_t row = row0 + rblk + grow;
-            const uint32_t n = n0 + gcol;
             uint32_t re = 0, im = 0;
-            if (rblk + grow < nrows && n < N) {
-                // counter of coefficient 0: (row * N + n) * 64  (structs.rs:55-72); < 2^64 for every supported shape
-                const uint64_t lo = (row * (uint64_t)N + n) * 64ull;
-                crs_poly_hat(seed, lo, 0ull, tw, lane, re, im);
-            }
-            Abuf[buf][w][lane] = lab_pack(re, im);
+            if (gen_row_ok && n0 + gcol < N) crs_poly_hat(seed, ctr, 0ull, tw, lane, re, im);
+            ctr += 128ull;
+            Are[buf][w][lane] = re;
+            Aim[buf][w][lane] = im;
+            Anim[buf][w][lane] = LABQ - im;
         }
         cp_async_wait_all();
         __syncthreads();
-        // 3. multiply-accumulate: RT rows x IC witness vectors per thread, lane = slot
+        // 3. multiply-accumulate: RT rows x IC witness vectors per thread, lane = slot.  Operands come out of
+        //    shared memory already split (LDS.U16 for the packed witness) so that no ALU-pipe unpacking is needed.
 #pragma unroll
         for (int nn = 0; nn < 2; nn++) {
             if (n0 + nn < N) {
                 uint32_t ar[KA_RT], am[KA_RT], nam[KA_RT];
 #pragma unroll
                 for (int r = 0; r < KA_RT; r++) {
-                    uint32_t a = Abuf[buf][nn * 4 + r][lane];
-                    ar[r] = lab_re(a); am[r] = lab_im(a); nam[r] = LABQ - am[r];
+                    ar[r] = Are[buf][nn * 4 + r][lane];
+                    am[r] = Aim[buf][nn * 4 + r][lane];
+                    nam[r] = Anim[buf][nn * 4 + r][lane];
                 }
 #pragma unroll
                 for (int ii = 0; ii < IC; ii++) {
                     if (i_base + il0 + ii < R) {
-                        uint32_t s = Sbuf[buf][nn][il0 + ii][lane];
-                        uint32_t sr = lab_re(s), sm_ = lab_im(s);
+                        const uint16_t *sp = reinterpret_cast<const uint16_t *>(&Sbuf[buf][nn][il0 + ii][lane]);
+                        const uint32_t sr = sp[0], sm_ = sp[1];
 #pragma unroll
                         for (int r = 0; r < KA_RT; r++) {
                             accr[r][ii] += ar[r] * sr + nam[r] * sm_;

@@ -1,0 +1,162 @@
+"""Host-side logic and the C-ABI surface, no GPU needed: the shared library loads and exports every symbol the
+header declares, the host restatement of RuntimeConstants / CRS offsets / synthetic inputs equals the oracle's,
+the generated transform code is current and correct, and the product fails loudly without a CUDA device."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+import labrador_b200 as lb
+from labrador_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+Q = 8191
+PKG = os.path.join(ROOT, "labrador-snark_b200")
+
+
+def have_gpu():
+    try:
+        lb.Context(0).close()
+        return True
+    except lb.LabError:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "labrador_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(lab_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared, "no declarations found"
+    lib = ctypes.CDLL(lb.SO_PATH)
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, f"declared but not exported: {missing}"
+    assert sorted(lb.SYMBOLS) == declared
+    lib.lab_version.restype = ctypes.c_int
+    assert lib.lab_version() >= 100
+
+
+def test_product_does_not_link_the_oracle():
+    out = subprocess.run(["ldd", lb.SO_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+    for root, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert "liblabrador_oracle" not in src, f
+                assert not re.search(r"^\s*(import|from)\s+(oracle|pyref)\b", src, re.M), f
+
+
+def test_no_cpu_fallback():
+    if have_gpu():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(lb.LabError) as e:
+        lb.Context(0)
+    assert e.value.status == 5 and "no CPU fallback" in str(e.value)
+
+
+def test_runtime_constants_match_oracle(orc):
+    for N, R in [(1, 1), (1, 2), (2, 2), (2, 4), (3, 5), (4, 4), (8, 8), (16, 32), (32, 32), (64, 64), (4096, 64), (65536, 256)]:
+        c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
+        co, rc = orc.constants(N, R)
+        for name, _ in c._fields_:
+            a, b = getattr(c, name), getattr(co, name)
+            assert a == b or (a != a and b != b), (N, R, name, a, b)
+    with pytest.raises(lb.LabError):
+        lb.RuntimeConstants.new(4096, 64)
+
+
+def test_crs_offsets_match_oracle(orc):
+    L = lb._lib.lib()
+    for N, R in [(2, 2), (2, 3), (5, 4)]:
+        c = lb.RuntimeConstants.new(N, R)
+        co, _ = orc.constants(N, R)
+        for which, args in (("A", dict(row=7)), ("B", dict(i=R - 1, k=c.T_1 - 1, row=c.KAPPA_1 - 1)), ("C", dict(i=1, j=R - 1, k=c.T_2 - 1)),
+                            ("D", dict(i=0, j=R - 1, k=c.T_1 - 1)), ("D", dict(i=R - 1, j=R - 1, k=0))):
+            lo, hi = ctypes.c_uint64(), ctypes.c_uint64()
+            rc = L.lab_crs_offset(ctypes.byref(c), ord(which), ctypes.c_uint64(args.get("i", 0)), ctypes.c_uint64(args.get("j", 0)),
+                                  ctypes.c_uint64(args.get("k", 0)), ctypes.c_uint64(args.get("row", 0)), ctypes.byref(lo), ctypes.byref(hi))
+            assert rc == 0
+            assert (lo.value | (hi.value << 64)) == orc.offset(which, co, **args)
+    # the reference's overlapping regions are reproduced literally
+    co, _ = orc.constants(2, 2)
+    assert orc.offset("B", co, i=0, k=1, row=0) - orc.offset("B", co, i=0, k=0, row=0) == co.KAPPA_1 * co.KAPPA     # no *D
+    assert orc.offset("D", co, i=0, j=0, k=0) - orc.offset("C", co, i=0, j=0, k=0) == (co.R * (co.R + 1) // 2) * co.KAPPA_2 * 64
+
+
+def test_synthetic_inputs_match_oracle(orc):
+    for N, R, s in [(1, 2, 3), (2, 2, synth.SEED), (3, 2, 99)]:
+        c, _ = orc.constants(N, R)
+        assert np.array_equal(synth.generate_witness(N, R, c.BETA_BOUND, s), orc.generate_witness(c, s))
+        S = orc.generate_witness(c, s)
+        phi, a, _ = orc.generate_state(c, S, s)
+        phi2, a2 = synth.generate_statement_inputs(N, R, s)
+        assert np.array_equal(phi, phi2) and np.array_equal(a, a2)
+        ch, ch2 = orc.sample_challenges(c, s, 2), synth.sample_challenges(N, R, s, 2)
+        for k in ch:
+            assert np.array_equal(ch[k], ch2[k]), k
+    pi = synth.sample_pi(2, 2, 1, 0)
+    frac = [(pi == v).mean() for v in (-1, 0, 1)]
+    assert abs(frac[0] - 0.25) < 0.01 and abs(frac[1] - 0.5) < 0.01 and abs(frac[2] - 0.25) < 0.01   # verification.rs:555-557
+    ch = synth.sample_challenge_poly(5, 0)                    # verification.rs:460-489 multiset 23/31/10
+    cen = np.where(ch > Q // 2, Q - ch.astype(np.int64), ch)
+    assert sorted(np.bincount(cen, minlength=3).tolist()) == [10, 23, 31]
+
+
+def test_generated_transform_header_is_current():
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "gen.cuh")
+        subprocess.check_call([sys.executable, os.path.join(PKG, "tools", "gen_ntt.py"), out], stdout=subprocess.DEVNULL)
+        assert open(out).read() == open(os.path.join(PKG, "csrc", "lab_ntt_gen.cuh")).read()
+
+
+def test_generated_transform_code_on_host(orc):
+    """The straight-line register transforms are plain C++ once LAB_HD is empty: compile them for the host and
+    compare with the oracle (bit exact), including the largest inputs the bound tracker allows."""
+    src = r'''
+#include <cstdio>
+#include <cstdint>
+#define __device__
+#define __forceinline__ inline
+#include "lab_field.cuh"
+#include "lab_ntt_gen.cuh"
+int main() {
+    uint32_t re[32], im[32];
+    for (int t = 0; t < 3; t++) {
+        for (int j = 0; j < 32; j++) { if (scanf("%u %u", &re[j], &im[j]) != 2) return 1; }
+        if (t < 2) lab_ntt32_fwd_regs(re, im); else lab_ntt32_inv_regs(re, im);
+        for (int j = 0; j < 32; j++) printf("%u %u\n", re[j], im[j]);
+    }
+    return 0;
+}'''
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "t.cpp"), "w").write(src)
+        exe = os.path.join(td, "t")
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", os.path.join(PKG, "csrc"), "-o", exe, os.path.join(td, "t.cpp")])
+        rng = np.random.default_rng(1)
+        a = rng.integers(0, 8191, 64, dtype=np.uint32)
+        mx = np.full(64, 8191, np.uint32)                     # non-canonical maximum the code must tolerate
+        fa = orc.ntt_fwd(a)
+        inp = []
+        for p in (a, mx):
+            inp += [f"{p[j]} {p[j + 32]}" for j in range(32)]
+        inp += [f"{fa[2 * j]} {fa[2 * j + 1]}" for j in range(32)]
+        out = subprocess.run([exe], input="\n".join(inp), capture_output=True, text=True, check=True).stdout.split()
+        vals = np.array(out, dtype=np.uint32).reshape(3, 32, 2)
+        assert np.array_equal(vals[0].reshape(-1), fa)
+        assert np.array_equal(vals[1].reshape(-1), orc.ntt_fwd(np.zeros(64, np.uint32)))      # 8191 == 0 mod Q
+        back = np.concatenate([vals[2][:, 0], vals[2][:, 1]])
+        assert np.array_equal(back, a)
+
+
+def test_shard_plan_covers_everything():
+    from labrador_b200 import shard
+    for total in (1, 7, 64, 262144):
+        for world in (1, 2, 3, 8):
+            parts = [shard.split(total, world, r) for r in range(world)]
+            assert parts[0][0] == 0 and sum(n for _, n in parts) == total
+            for (s0, n0), (s1, _) in zip(parts, parts[1:]):
+                assert s0 + n0 == s1
