@@ -109,6 +109,8 @@ static LabSeed make_seed(const uint8_t seed[32]) {
         for (int b = 0; b < 8; b++) v = (v << 8) | seed[(3 - l) * 8 + b];
         s.limb[l] = v;
     }
+    s.one = 1u;
+    s.pad = 0u;
     return s;
 }
 static unsigned grid_for(size_t work_items, unsigned per_block, unsigned cap) {
@@ -276,13 +278,15 @@ static int d_commit_inner(lab_ctx *ctx, const LabSeed &seed, const uint32_t *Wha
         if (last >> 64) FAIL(LAB_ERR_PARAMS, "A counter exceeds 64 bits");
     }
     const unsigned grid = (unsigned)((nrows + KA_RT - 1) / KA_RT);
-    const int IC = R > 32 ? 8 : (R > 16 ? 4 : (R > 8 ? 2 : 1));
-    for (uint64_t ib = 0; ib < R; ib += 8ull * IC) {
+    // four consumer warps x IC witness vectors per pass
+    const int IC = R > 32 ? 16 : (R > 16 ? 8 : (R > 8 ? 4 : (R > 4 ? 2 : 1)));
+    for (uint64_t ib = 0; ib < R; ib += (uint64_t)KA_CONS * IC) {
         switch (IC) {
-            case 8: LAUNCH(k_commit_inner<8>, grid, 256, seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
-            case 4: LAUNCH(k_commit_inner<4>, grid, 256, seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
-            case 2: LAUNCH(k_commit_inner<2>, grid, 256, seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
-            default: LAUNCH(k_commit_inner<1>, grid, 256, seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
+            case 16: LAUNCH(k_commit_inner<16>, grid, KA_THREADS, seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
+            case 8: LAUNCH(k_commit_inner<8>, grid, KA_THREADS, seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
+            case 4: LAUNCH(k_commit_inner<4>, grid, KA_THREADS, seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
+            case 2: LAUNCH(k_commit_inner<2>, grid, KA_THREADS, seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
+            default: LAUNCH(k_commit_inner<1>, grid, KA_THREADS, seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
         }
     }
     return LAB_OK;
@@ -541,10 +545,12 @@ extern "C" int lab_crs_fetch(lab_ctx *ctx, const lab_constants *c, const uint8_t
 // ---------------------------------------------------------------------------------------------
 // stages, host-pointer API
 // ---------------------------------------------------------------------------------------------
+// transformed-witness buffer size in hats, including the read-only padding K_A's consumers rely on
+static size_t what_hats(uint64_t N, uint64_t R) { return (size_t)((N + KA_PAD_COLS) * R + KA_PAD_VECS); }
 static int load_witness(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, uint32_t **dS, uint32_t **What) {
     const size_t n = c->R * c->N;
     TRY(upload(ctx, S, n * 64, dS));
-    TRY(arena_alloc(ctx, n * 32, What));
+    TRY(arena_alloc(ctx, what_hats(c->N, c->R) * 32, What));
     return d_fwd_hat(ctx, *dS, *What, n, c->N, c->R);     // p = i*N + n  ->  n*R + i
 }
 extern "C" int lab_commit_inner(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], const uint32_t *S, uint64_t row0, uint64_t nrows, uint32_t *T) {
@@ -830,7 +836,7 @@ extern "C" int lab_prove_batch(lab_ctx *ctx, const lab_constants *c, size_t n_st
 extern "C" int lab_witness_load_dev(lab_ctx *ctx, const lab_constants *c, const uint32_t *S_dev) {
     cudaSetDevice(ctx->device);
     TRY(check_consts(ctx, c, false));
-    const size_t bytes = c->R * c->N * 32 * sizeof(uint32_t);
+    const size_t bytes = what_hats(c->N, c->R) * 32 * sizeof(uint32_t);
     if (bytes > ctx->What_bytes) {
         if (ctx->What) cudaFree(ctx->What);
         ctx->What = nullptr; ctx->What_bytes = 0;

@@ -10,6 +10,10 @@
 
 struct LabSeed {
     uint64_t limb[4];   // the 256-bit big-endian base seed as an integer, limb[0] least significant
+    uint32_t one;       // always 1, but only known at run time (kernel parameter / constant bank): a + b is written
+                        // b * one + a so that ChaCha20's 320 additions per block issue as IMAD on the FMA pipe instead of
+                        // IADD3 on the ALU pipe, which the xors and rotates already saturate
+    uint32_t pad;
 };
 
 #ifdef __CUDACC__
@@ -38,13 +42,13 @@ __device__ __forceinline__ void lab_key_from_counter(const LabSeed &s, uint64_t 
     key[7] = lab_bswap32((uint32_t)s0);
 }
 
-#define LAB_QR(a, b, c, d)                                                   \
-    a += b; d ^= a; d = lab_rotl(d, 16); c += d; b ^= c; b = lab_rotl(b, 12); \
-    a += b; d ^= a; d = lab_rotl(d, 8);  c += d; b ^= c; b = lab_rotl(b, 7);
+#define LAB_QR(a, b, c, d)                                                                       \
+    a = b * one + a; d ^= a; d = lab_rotl(d, 16); c = d * one + c; b ^= c; b = lab_rotl(b, 12);  \
+    a = b * one + a; d ^= a; d = lab_rotl(d, 8);  c = d * one + c; b ^= c; b = lab_rotl(b, 7);
 
-// the 10 double rounds on NB independent states (interleaved for ILP)
+// the 10 double rounds on NB independent states (interleaved for ILP); `one` == 1 (see LabSeed)
 template <int NB>
-__device__ __forceinline__ void lab_chacha_rounds(uint32_t (&x)[NB][16]) {
+__device__ __forceinline__ void lab_chacha_rounds(uint32_t (&x)[NB][16], const uint32_t one) {
 #pragma unroll 1
     for (int r = 0; r < 10; r++) {
 #pragma unroll
@@ -91,7 +95,7 @@ __device__ __noinline__ uint32_t lab_crs_coeff_slow(const LabSeed &seed, uint64_
         lab_chacha_init(x[0], key, (uint64_t)(a >> 2));
 #pragma unroll
         for (int i = 0; i < 16; i++) init[i] = x[0][i];
-        lab_chacha_rounds<1>(x);
+        lab_chacha_rounds<1>(x, seed.one);
         uint32_t w[4];
 #pragma unroll
         for (int i = 0; i < 16; i++) {
@@ -116,7 +120,7 @@ __device__ __forceinline__ void lab_crs_coeffs(const LabSeed &seed, uint64_t clo
         lab_key_from_counter(seed, lo, hi, key);
         lab_chacha_init(x[b], key, 0);
     }
-    lab_chacha_rounds<NB>(x);
+    lab_chacha_rounds<NB>(x, seed.one);
 #pragma unroll
     for (int b = 0; b < NB; b++) {
         uint32_t w0 = x[b][0] + 0x61707865u, w1 = x[b][1] + 0x3320646eu, w2 = x[b][2] + 0x79622d32u, w3 = x[b][3] + 0x6b206574u;

@@ -381,7 +381,7 @@ __device__ __forceinline__ void crs_poly_hat(const LabSeed &seed, uint64_t lo, u
     uint32_t c[2];
     lab_crs_coeffs<2>(seed, lo, hi, off, c);
     re = c[0]; im = c[1];
-    lab_ntt32_fwd_warp(re, im, tw, lane);
+    lab_ntt32_fwd_warp(re, im, tw, lane, seed.one);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -392,118 +392,128 @@ __device__ __forceinline__ void crs_poly_hat(const LabSeed &seed, uint64_t lo, u
 // against the n-major transformed witness (128 B coalesced per (n, i), L2 resident).
 // ChaCha runs on the ALU pipe, the MACs on the FMA pipe.  A is generated exactly once.
 // ------------------------------------------------------------------------------------------------
-constexpr int KA_RT = 4;
+constexpr int KA_RT = 4;        // rows of A per CTA
+constexpr int KA_COLS = 3;      // columns of A per tile: 4 x 3 = 12 polynomials = one per producer warp
+constexpr int KA_PROD = 12;     // producer warps (three warpgroups)
+constexpr int KA_CONS = 4;      // consumer warps (one warpgroup)
+constexpr int KA_DEPTH = 4;     // ring slots between producer and consumer warps
+constexpr int KA_THREADS = 32 * (KA_PROD + KA_CONS);
+// hats of padding the transformed witness needs after its N*R entries: the consumers read up to KA_COLS columns past
+// the end (ring tail + one-column prefetch) and up to KA_CONS*16 vectors past R without predicates
+constexpr size_t KA_PAD_COLS = KA_COLS + 1;
+constexpr size_t KA_PAD_VECS = KA_CONS * 16;
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_named(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive_named(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
+// Warp-specialised: warps 0-11 ("producers", three warpgroups, registers trimmed with setmaxnreg) do nothing but
+// ChaCha20 + the warp transform, one polynomial of A per tile each (tile = 4 rows x 3 columns), and park it in a
+// 4-deep shared-memory ring; warps 12-15 ("consumers", one warpgroup with a raised register budget) hold the
+// accumulators (4 rows x IC witness vectors per thread, lane = slot) and multiply-accumulate every tile against the
+// n-major transformed witness, fetched from L2 one column ahead.  Producers never wait for the MACs (ring + named
+// barriers FULL/EMPTY), so the ALU pipe sees an uninterrupted ChaCha20 stream from three warps per scheduler while
+// the consumers' IMADs use the FMA pipe.
 template <int IC>
-__global__ void __launch_bounds__(256, 2) k_commit_inner(LabSeed seed, const uint32_t *__restrict__ What, uint32_t N, uint32_t R,
-                                                          uint64_t row0, uint64_t nrows, uint32_t i_base, uint32_t *__restrict__ T) {
-    constexpr int IT = 8 * IC;                                   // witness vectors per CTA pass
-    constexpr int NCP = (2 * IT * 8 + 255) / 256;                // 16-byte cp.async chunks per thread per step
-    __shared__ uint32_t Are[2][8][32], Aim[2][8][32], Anim[2][8][32];   // generated polys: re, im, Q - im
-    __shared__ __align__(16) uint32_t Sbuf[2][2][IT][32];        // [buffer][column][i][slot] packed, filled by cp.async
+__global__ void __launch_bounds__(KA_THREADS, 1) k_commit_inner(LabSeed seed, const uint32_t *__restrict__ What, uint32_t N, uint32_t R,
+                                                                 uint64_t row0, uint64_t nrows, uint32_t i_base, uint32_t *__restrict__ T) {
+    __shared__ uint32_t Are[KA_DEPTH][KA_PROD][32], Aim[KA_DEPTH][KA_PROD][32], Anim[KA_DEPTH][KA_PROD][32];   // re, im, Q - im
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const LabWarpTw tw = lab_warp_tw(lane);
     const uint64_t rblk = (uint64_t)blockIdx.x * KA_RT;          // first row of this CTA, relative to row0
-    const int grow = w & 3, gcol = w >> 2;                       // generation role
-    const int il0 = w * IC;                                      // MAC role: local witness vectors il0..il0+IC
-    const bool gen_row_ok = rblk + grow < nrows;
-    // counter of coefficient 0 of A[row][n]: (row * N + n) * 64 (structs.rs:55-72); < 2^64 for every supported shape
-    uint64_t ctr = ((row0 + rblk + grow) * (uint64_t)N + gcol) * 64ull;
-    // per-thread cp.async sources / destinations (advance by two witness columns per step)
-    const uint32_t *src[NCP];
-    uint32_t dsto[NCP], cp_nn[NCP];
-    bool cp_ok[NCP];
-#pragma unroll
-    for (int t = 0; t < NCP; t++) {
-        const int q = threadIdx.x + 256 * t;
-        const int nn = q / (IT * 8), rem = q % (IT * 8), il = rem >> 3, chk = rem & 7;
-        cp_ok[t] = q < 2 * IT * 8 && i_base + il < R;
-        cp_nn[t] = nn;
-        src[t] = What + ((size_t)nn * R + i_base + il) * 32 + chk * 4;
-        dsto[t] = ((nn * IT + il) * 32 + chk * 4);
-    }
-    uint32_t accr[KA_RT][IC], acci[KA_RT][IC];
-#pragma unroll
-    for (int r = 0; r < KA_RT; r++)
-#pragma unroll
-        for (int ii = 0; ii < IC; ii++) { accr[r][ii] = 0; acci[r][ii] = 0; }
-
-    int pending = 0;
-    for (uint32_t n0 = 0, step = 0; n0 < N; n0 += 2, step++) {
-        const int buf = step & 1;
-        // 1. start fetching this step's slice of the transformed witness (L2 -> smem); it lands while
-        //    the ChaCha blocks below are computed
-#pragma unroll
-        for (int t = 0; t < NCP; t++) {
-            if (cp_ok[t] && n0 + cp_nn[t] < N) cp_async16(&Sbuf[buf][0][0][0] + dsto[t], src[t]);
-            src[t] += (size_t)2 * R * 32;
-        }
-        cp_async_commit();
-        {   // 2. generate one CRS polynomial per warp, transformed
+    const uint32_t ntiles = (N + KA_COLS - 1) / KA_COLS;
+    // barrier ids: FULL[s] = 1 + s, EMPTY[s] = 1 + KA_DEPTH + s (0 is __syncthreads)
+    if (w < KA_PROD) {
+        // ---------------- producer ----------------
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        const LabWarpTw tw = lab_warp_tw(lane);
+        const int grow = w & 3, gcol = w >> 2;
+        const bool row_ok = rblk + grow < nrows;
+        // counter of coefficient 0 of A[row][n]: (row * N + n) * 64 (structs.rs:55-72); < 2^64 for every supported shape
+        uint64_t ctr = ((row0 + rblk + grow) * (uint64_t)N + gcol) * 64ull;
+        for (uint32_t t = 0; t < ntiles; t++) {
+            const int s = t % KA_DEPTH;
             uint32_t re = 0, im = 0;
-            if (gen_row_ok && n0 + gcol < N) crs_poly_hat(seed, ctr, 0ull, tw, lane, re, im);
-            ctr += 128ull;
-            Are[buf][w][lane] = re;
-            Aim[buf][w][lane] = im;
-            Anim[buf][w][lane] = LABQ - im;
+            if (row_ok && KA_COLS * t + gcol < N) crs_poly_hat(seed, ctr, 0ull, tw, lane, re, im);
+            ctr += 64ull * KA_COLS;
+            if (t >= KA_DEPTH) bar_sync_named(1 + KA_DEPTH + s, KA_THREADS);     // slot free again?
+            Are[s][w][lane] = re;
+            Aim[s][w][lane] = im;
+            Anim[s][w][lane] = LABQ - im;
+            bar_arrive_named(1 + s, KA_THREADS);                                 // slot full
         }
-        cp_async_wait_all();
-        __syncthreads();
-        // 3. multiply-accumulate: RT rows x IC witness vectors per thread, lane = slot.  Operands come out of
-        //    shared memory already split (LDS.U16 for the packed witness) so that no ALU-pipe unpacking is needed.
+    } else {
+        // ---------------- consumer ----------------
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        const int cw = w - KA_PROD;
+        const uint32_t i0 = i_base + (uint32_t)cw * IC;
+        uint32_t accr[KA_RT][IC], acci[KA_RT][IC];
 #pragma unroll
-        for (int nn = 0; nn < 2; nn++) {
-            if (n0 + nn < N) {
+        for (int r = 0; r < KA_RT; r++)
+#pragma unroll
+            for (int ii = 0; ii < IC; ii++) { accr[r][ii] = 0; acci[r][ii] = 0; }
+        // The transformed witness is read as two 16-bit halves per slot (re at +0, im at +2 bytes of the packed word):
+        // no ALU-pipe unpacking.  No bounds predicates either: What is padded (see KA_PAD_HATS) so that columns n >= N
+        // and vectors i >= R are readable; the producers emit zero polynomials for n >= N and results for i >= R are
+        // never stored, so whatever is read there cannot reach the output.
+        const uint16_t *sp = reinterpret_cast<const uint16_t *>(What + (size_t)i0 * 32 + lane);
+        const size_t col_stride = (size_t)R * 64;                 // 16-bit units per column n
+        uint32_t nsr[IC], nsm[IC];                                // next column, already split
+        auto fetch = [&]() {
+#pragma unroll
+            for (int ii = 0; ii < IC; ii++) { nsr[ii] = __ldg(sp + ii * 64); nsm[ii] = __ldg(sp + ii * 64 + 1); }
+            sp += col_stride;
+        };
+        int pending = 0;
+        fetch();
+        for (uint32_t t = 0; t < ntiles; t++) {
+            const int s = t % KA_DEPTH;
+            const uint32_t *a_re = &Are[s][0][lane], *a_im = &Aim[s][0][lane], *a_nim = &Anim[s][0][lane];
+            bar_sync_named(1 + s, KA_THREADS);                    // wait for the producers
+#pragma unroll
+            for (int nn = 0; nn < KA_COLS; nn++) {
+                uint32_t sr[IC], sm_[IC];
+#pragma unroll
+                for (int ii = 0; ii < IC; ii++) { sr[ii] = nsr[ii]; sm_[ii] = nsm[ii]; }
+                fetch();                                          // next column's witness slots land during these MACs
                 uint32_t ar[KA_RT], am[KA_RT], nam[KA_RT];
 #pragma unroll
                 for (int r = 0; r < KA_RT; r++) {
-                    ar[r] = Are[buf][nn * 4 + r][lane];
-                    am[r] = Aim[buf][nn * 4 + r][lane];
-                    nam[r] = Anim[buf][nn * 4 + r][lane];
+                    ar[r] = a_re[(nn * 4 + r) * 32];
+                    am[r] = a_im[(nn * 4 + r) * 32];
+                    nam[r] = a_nim[(nn * 4 + r) * 32];
                 }
 #pragma unroll
-                for (int ii = 0; ii < IC; ii++) {
-                    if (i_base + il0 + ii < R) {
-                        const uint16_t *sp = reinterpret_cast<const uint16_t *>(&Sbuf[buf][nn][il0 + ii][lane]);
-                        const uint32_t sr = sp[0], sm_ = sp[1];
+                for (int ii = 0; ii < IC; ii++)
 #pragma unroll
-                        for (int r = 0; r < KA_RT; r++) {
-                            accr[r][ii] += ar[r] * sr + nam[r] * sm_;
-                            acci[r][ii] += ar[r] * sm_ + am[r] * sr;
-                        }
+                    for (int r = 0; r < KA_RT; r++) {
+                        accr[r][ii] += ar[r] * sr[ii] + nam[r] * sm_[ii];
+                        acci[r][ii] += ar[r] * sm_[ii] + am[r] * sr[ii];
                     }
+            }
+            if (t + KA_DEPTH < ntiles) bar_arrive_named(1 + KA_DEPTH + s, KA_THREADS);   // slot may be overwritten
+            if (++pending == 5) {                                 // 5 tiles * 3 columns * 2 products < 2^5 * 2^26
+                pending = 0;
+#pragma unroll
+                for (int r = 0; r < KA_RT; r++)
+#pragma unroll
+                    for (int ii = 0; ii < IC; ii++) { accr[r][ii] = lab_fold(accr[r][ii]); acci[r][ii] = lab_fold(acci[r][ii]); }
+            }
+        }
+        // inverse transform and store T[i][row][.]  (T is [R][nrows][64])
+        const LabWarpTw tw = lab_warp_tw(lane);
+#pragma unroll
+        for (int ii = 0; ii < IC; ii++)
+#pragma unroll
+            for (int r = 0; r < KA_RT; r++) {
+                uint32_t re = lab_canon(accr[r][ii]), im = lab_canon(acci[r][ii]);
+                lab_ntt32_inv_warp(re, im, tw, lane);
+                const uint32_t i = i0 + ii;
+                if (rblk + r < nrows && i < R) {
+                    uint32_t *dst = T + ((size_t)i * nrows + rblk + r) * 64;
+                    dst[lane] = re;
+                    dst[lane + 32] = im;
                 }
             }
-        }
-        if (++pending == 8) {                                    // 8 steps * 2 columns * 2 products < 2^5 * 2^26
-            pending = 0;
-#pragma unroll
-            for (int r = 0; r < KA_RT; r++)
-#pragma unroll
-                for (int ii = 0; ii < IC; ii++) { accr[r][ii] = lab_fold(accr[r][ii]); acci[r][ii] = lab_fold(acci[r][ii]); }
-        }
     }
-    // inverse transform and store T[i][row][.]  (T is [R][nrows][64])
-#pragma unroll
-    for (int r = 0; r < KA_RT; r++)
-#pragma unroll
-        for (int ii = 0; ii < IC; ii++) {
-            uint32_t re = lab_canon(accr[r][ii]), im = lab_canon(acci[r][ii]);
-            lab_ntt32_inv_warp(re, im, tw, lane);
-            const uint32_t i = i_base + il0 + ii;
-            if (rblk + r < nrows && i < R) {
-                uint32_t *dst = T + ((size_t)i * nrows + rblk + r) * 64;
-                dst[lane] = re;
-                dst[lane + 32] = im;
-            }
-        }
 }
 
 // ------------------------------------------------------------------------------------------------

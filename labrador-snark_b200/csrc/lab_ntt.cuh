@@ -15,10 +15,13 @@ static __constant__ uint32_t LAB_TW_FWD[32] = LAB_TW_FWD_INIT;
 static __constant__ uint32_t LAB_TW_INV[32] = LAB_TW_INV_INIT;
 
 // per-lane multipliers: stage s (len = 16 >> s) uses tree node (1 << s) + (lane >> (5 - s)).
-// Lower lanes of a butterfly multiply by 1 (forward) so that the code is branch-free.
+// Lower lanes of a butterfly multiply by 1 so that the code is branch-free.  The forward constants are kept
+// unpacked (re, im, -im) together with the butterfly sign and offset, so that a stage costs only 8 ALU-pipe
+// instructions (6 fold shifts + 2 unpacks); everything else is IMAD on the FMA pipe.
 struct LabWarpTw {
-    uint32_t f[5];   // forward: upper lanes zeta^(e/2), lower lanes 1
-    uint32_t g[5];   // inverse: upper lanes zeta^-(e/2), lower lanes 1; last level also carries 2^8 = 32^-1
+    uint32_t fr[5], fi[5], nfi[5];   // forward: upper lanes zeta^(e/2), lower lanes 1; nfi = 2Q - fi
+    uint32_t sgn[5], off[5];         // forward butterfly: out = p * sgn + (recv + off); upper: (-1, 2Q), lower: (1, 0)
+    uint32_t g[5];                   // inverse: upper lanes zeta^-(e/2), lower lanes 1; last level also carries 2^8 = 32^-1
 };
 
 __device__ __forceinline__ LabWarpTw lab_warp_tw(int lane) {
@@ -28,7 +31,12 @@ __device__ __forceinline__ LabWarpTw lab_warp_tw(int lane) {
         const int len = 16 >> s;
         const bool upper = (lane & len) != 0;
         const int node = (1 << s) + (lane >> (5 - s));
-        t.f[s] = upper ? LAB_TW_FWD[node] : 1u;
+        const uint32_t f = upper ? LAB_TW_FWD[node] : 1u;
+        t.fr[s] = lab_re(f);
+        t.fi[s] = lab_im(f);
+        t.nfi[s] = 2u * LABQ - lab_im(f);
+        t.sgn[s] = upper ? 0xFFFFFFFFu : 1u;
+        t.off[s] = upper ? 2u * LABQ : 0u;
         uint32_t g = upper ? LAB_TW_INV[node] : 1u;
         if (s == 0) {   // len == 16 is the LAST inverse level: fold in 32^-1 = 256
             uint32_t gr = lab_canon(lab_re(g) * 256u), gi = lab_canon(lab_im(g) * 256u);
@@ -40,20 +48,20 @@ __device__ __forceinline__ LabWarpTw lab_warp_tw(int lane) {
 }
 
 // lane j holds g_j = f_j + i f_{j+32} (residues < 2Q); returns slot j = f(zeta^{e_j}), canonical.
-__device__ __forceinline__ void lab_ntt32_fwd_warp(uint32_t &re, uint32_t &im, const LabWarpTw &tw, int lane) {
+// `one` == 1 at run time (LabSeed::one): additions written as x * one + y issue on the FMA pipe.
+__device__ __forceinline__ void lab_ntt32_fwd_warp(uint32_t &re, uint32_t &im, const LabWarpTw &tw, int lane, uint32_t one = 1u) {
+    (void)lane;
 #pragma unroll
     for (int s = 0; s < 5; s++) {
         const int len = 16 >> s;
-        const bool upper = (lane & len) != 0;
-        uint32_t pr, pi;
-        lab_cmul(re, im, lab_re(tw.f[s]), lab_im(tw.f[s]), pr, pi);          // < 2Q
-        const uint32_t recv = __shfl_xor_sync(0xffffffffu, lab_pack(pr, pi), len);
-        const uint32_t rr = lab_re(recv), ri = lab_im(recv);
-        // lower: lo + t ; upper: lo - t  (t is the upper lane's product)
-        re = upper ? rr + 2u * LABQ - pr : pr + rr;
-        im = upper ? ri + 2u * LABQ - pi : pi + ri;
-        re = lab_fold(re);                                                   // < Q + 4
-        im = lab_fold(im);
+        uint32_t pr = re * tw.fr[s] + im * tw.nfi[s];                        // < 2^29
+        uint32_t pi = re * tw.fi[s] + im * tw.fr[s];
+        pr = lab_fold(lab_fold(pr));                                         // < 2Q
+        pi = lab_fold(lab_fold(pi));
+        const uint32_t recv = __shfl_xor_sync(0xffffffffu, pi * 65536u + pr, len);
+        // lower: lo + t ; upper: lo - t + 2Q  (t is the upper lane's product, lo the lower lane's value)
+        re = lab_fold(pr * tw.sgn[s] + (lab_re(recv) * one + tw.off[s]));    // < Q + 4
+        im = lab_fold(pi * tw.sgn[s] + (lab_im(recv) * one + tw.off[s]));
     }
     re = lab_csub(re);
     im = lab_csub(im);

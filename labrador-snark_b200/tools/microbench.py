@@ -58,7 +58,7 @@ def main():
                               "chacha_blocks_per_s": n * 64 / (med * 1e-3)}), flush=True)
             ctx.free(dout)
     if "commit1" in which:      # one mid-size launch pair, for ncu --set full captures
-        N, R, rows = 1024, 64, 2048
+        N, R, rows = 1024, 64, 148 * 4 * 6
         c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
         dS = ctx.malloc(R * N * 256)
         ctx.synth_zq_dev(synth.SEED, 1, 0, R * N * 64, dS)
@@ -69,7 +69,7 @@ def main():
                           "chacha_blocks_per_s": rows * N * 64 / (med * 1e-3)}), flush=True)
         ctx.free(dS); ctx.free(dT)
     if "commit" in which:
-        for (N, R, rows) in ((256, 2, 4096), (256, 8, 4096), (256, 32, 4096), (256, 64, 4096), (4096, 64, 1024)):
+        for (N, R, rows) in ((256, 2, 148 * 4 * 8), (256, 8, 148 * 4 * 8), (256, 32, 148 * 4 * 8), (256, 64, 148 * 4 * 8), (4096, 64, 148 * 4 * 4)):
             c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
             S = synth.uniform_witness(N, R)
             dS = ctx.malloc(S.nbytes)
