@@ -180,6 +180,12 @@ int lab_prove(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], cons
 int lab_prove_batch(lab_ctx *ctx, const lab_constants *c, size_t n_statements, const uint8_t *seeds, int shared_crs,
                     const uint32_t *S, const lab_state *st, const lab_challenges *ch, lab_transcript *out);
 
+/* Verifier::verify (verification.rs:25-438) on the GPU: recomputes lines 3-7 and runs Checks 8-20 in the reference's
+ * order with early exit.  accepted = 1/0; failed_check = the reference's check number (8..20) or 0; norm_sum = the exact
+ * integer of Check 14.  ch->pi must hold the attempts the transcript's jl_attempt indexes. */
+int lab_verify(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], const lab_state *st, const lab_challenges *ch,
+               const lab_transcript *tr, int *accepted, int *failed_check, uint64_t *norm_sum);
+
 /* ---- device-resident stage API (inputs already in HBM; used for sharded / pipelined proving) ---- */
 /* S_dev: uint32_t[R][N][64] on device.  Prepares the transformed witness inside ctx. */
 int lab_witness_load_dev(lab_ctx *ctx, const lab_constants *c, const uint32_t *S_dev);

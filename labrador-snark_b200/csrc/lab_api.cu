@@ -817,6 +817,181 @@ extern "C" int lab_prove(lab_ctx *ctx, const lab_constants *c, const uint8_t see
     TRY(check_consts(ctx, c, true));
     return prove_one(ctx, c, seed, S, st, ch, out);
 }
+// ---------------------------------------------------------------------------------------------
+// Verifier::verify (verification.rs:25-438) on the GPU.  Checks 15, 19, 20 re-run the prover's commitment kernels;
+// 16-18 are slot-wise sums in the transform domain; 14 is the exact-integer norm; 8-9 are host comparisons.
+// ---------------------------------------------------------------------------------------------
+static int dev_equal(lab_ctx *ctx, const uint32_t *x, const uint32_t *y, size_t n_words, unsigned long long *dcount, bool *equal) {
+    CK(cudaMemsetAsync(dcount, 0, sizeof *dcount, ctx->stream));
+    LAUNCH(k_count_diff, grid_for(n_words, 1024, ctx->sms * 8), 256, x, y, n_words, dcount);
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, dcount, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(lab_sync(ctx));
+    *equal = h == 0;
+    return LAB_OK;
+}
+extern "C" int lab_verify(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_bytes[32], const lab_state *st, const lab_challenges *ch,
+                          const lab_transcript *tr, int *accepted, int *failed_check, uint64_t *norm_sum) {
+    CallScope cs(ctx);
+    TRY(check_consts(ctx, c, true));
+    if (!st || !ch || !tr || !accepted) FAIL(LAB_ERR_PARAMS, "null argument");
+    const uint64_t R = c->R, N = c->N, K = c->KAPPA, K1 = c->KAPPA_1, K2 = c->KAPPA_2, ND = N * LAB_D;
+    const uint64_t T1 = (uint64_t)c->T_1, T2 = (uint64_t)c->T_2;
+    const LabSeed seed = make_seed(seed_bytes);
+    const uint32_t psi = ch->psi % LAB_Q;
+    int fc = 0;
+    *accepted = 0;
+    if (tr->jl_attempt < 0 || tr->jl_attempt >= ch->n_attempts) FAIL(LAB_ERR_PARAMS, "jl_attempt out of range");
+    // checks 8, 9: g and h symmetric (verification.rs:157-178)
+    for (uint64_t i = 0; i < R && !fc; i++)
+        for (uint64_t j = 0; j < R; j++)
+            if (std::memcmp(tr->g + (i * R + j) * 64, tr->g + (j * R + i) * 64, 256)) { fc = 8; break; }
+    for (uint64_t i = 0; i < R && !fc; i++)
+        for (uint64_t j = 0; j < R; j++)
+            if (std::memcmp(tr->h + (i * R + j) * 64, tr->h + (j * R + i) * 64, 256)) { fc = 9; break; }
+    // uploads
+    uint32_t *dz, *dT, *dG, *dH, *du1, *du2, *dphi, *dom, *da, *dsmall, *dc;
+    int8_t *dPi;
+    TRY(upload(ctx, tr->z, N * 64, &dz));
+    TRY(upload(ctx, tr->t, R * K * 64, &dT));
+    TRY(upload(ctx, tr->g, R * R * 64, &dG));
+    TRY(upload(ctx, tr->h, R * R * 64, &dH));
+    TRY(upload(ctx, tr->u_1, K1 * 64, &du1));
+    TRY(upload(ctx, tr->u_2, K2 * 64, &du2));
+    TRY(upload(ctx, st->phi, R * ND, &dphi));
+    TRY(upload(ctx, ch->omega, (size_t)LAB_JL_ROWS, &dom));
+    TRY(upload(ctx, st->a, R * R * 64, &da));
+    TRY(upload(ctx, ch->c, R * 64, &dc));
+    TRY(upload(ctx, ch->pi + (size_t)tr->jl_attempt * R * LAB_JL_ROWS * ND, R * LAB_JL_ROWS * ND, &dPi));
+    uint32_t small[4 * 64];                                     // alpha, beta, b, b''
+    std::memcpy(small, ch->alpha, 256); std::memcpy(small + 64, ch->beta, 256);
+    std::memcpy(small + 128, st->b, 256); std::memcpy(small + 192, tr->b_prime_prime, 256);
+    TRY(upload(ctx, small, (size_t)256, &dsmall));
+    unsigned long long *dcnt;
+    TRY(arena_alloc(ctx, (size_t)2, &dcnt));
+    // lines 10-14: exact integer norm of every digit (verification.rs:185-267)
+    CK(cudaMemsetAsync(dcnt + 1, 0, sizeof *dcnt, ctx->stream));
+    LAUNCH(k_digit_norm_sq, grid_for(N * 64, 2048, ctx->sms * 8), 256, dz, (size_t)(N * 64), (uint32_t)c->B, 2, dcnt + 1);
+    LAUNCH(k_digit_norm_sq, grid_for(R * K * 64, 2048, ctx->sms * 8), 256, dT, (size_t)(R * K * 64), (uint32_t)c->B_1, (int)T1, dcnt + 1);
+    LAUNCH(k_digit_norm_sq, grid_for(R * R * 64, 2048, ctx->sms * 8), 256, dG, (size_t)(R * R * 64), (uint32_t)c->B_2, (int)T2, dcnt + 1);
+    LAUNCH(k_digit_norm_sq, grid_for(R * R * 64, 2048, ctx->sms * 8), 256, dH, (size_t)(R * R * 64), (uint32_t)c->B_1, (int)T1, dcnt + 1);
+    unsigned long long hnorm = 0;
+    CK(cudaMemcpyAsync(&hnorm, dcnt + 1, sizeof hnorm, cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(lab_sync(ctx));
+    if (norm_sum) *norm_sum = hnorm;
+    if (!fc && (double)hnorm > c->BETA_PRIME) fc = 14;          // `sum > BETA_PRIME` (verification.rs:265)
+    if (fc) { if (failed_check) *failed_check = fc; return LAB_OK; }
+    // transform-domain operands
+    uint32_t *zhat, *That, *Ghat, *Hhat, *Ahat, *Chat, *SMhat, *Phihat, *PPhat, *PFhat, *dpp;
+    TRY(arena_alloc(ctx, what_hats(N, 1) * 32, &zhat));
+    TRY(arena_alloc(ctx, R * K * 32, &That));
+    TRY(arena_alloc(ctx, R * R * 32, &Ghat));
+    TRY(arena_alloc(ctx, R * R * 32, &Hhat));
+    TRY(arena_alloc(ctx, R * R * 32, &Ahat));
+    TRY(arena_alloc(ctx, R * 32, &Chat));
+    TRY(arena_alloc(ctx, (size_t)4 * 32, &SMhat));
+    TRY(arena_alloc(ctx, R * N * 32, &Phihat));
+    TRY(arena_alloc(ctx, R * N * 32, &PPhat));
+    TRY(arena_alloc(ctx, R * N * 32, &PFhat));
+    TRY(arena_alloc(ctx, R * ND, &dpp));
+    TRY(d_fwd_hat(ctx, dz, zhat, N, 0, 0));
+    TRY(d_fwd_hat(ctx, dT, That, R * K, K, R));                  // [y][i]
+    TRY(d_fwd_hat(ctx, dG, Ghat, R * R, 0, 0));
+    TRY(d_fwd_hat(ctx, dH, Hhat, R * R, 0, 0));
+    TRY(d_fwd_hat(ctx, da, Ahat, R * R, 0, 0));
+    TRY(d_fwd_hat(ctx, dc, Chat, R, 0, 0));
+    TRY(d_fwd_hat(ctx, dsmall, SMhat, 4, 0, 0));
+    const uint32_t *alpha_h = SMhat, *beta_h = SMhat + 32, *b_h = SMhat + 64, *bpp_h = SMhat + 96;
+    // lines 3-6: phi'' and phi = alpha phi + beta phi''
+    TRY(d_aggregate_phi(ctx, c, dphi, dPi, psi, dom, dpp));
+    TRY(d_fwd_hat(ctx, dphi, Phihat, R * N, N, R));
+    TRY(d_fwd_hat(ctx, dpp, PPhat, R * N, N, R));
+    LAUNCH(k_pointwise, grid_for(R * N * 32, 256, ctx->sms * 16), 256, alpha_h, (size_t)1, (size_t)0, Phihat, beta_h, (size_t)1, (size_t)0, PPhat, PFhat,
+           (size_t)(R * N));
+    bool eq = true;
+    // check 15: A z == sum_i c_i t_i (verification.rs:274-296)
+    {
+        uint32_t *lhs, *rhs_h, *rhs;
+        TRY(arena_alloc(ctx, K * 64, &lhs));
+        TRY(arena_alloc(ctx, K * 32, &rhs_h));
+        TRY(arena_alloc(ctx, K * 64, &rhs));
+        TRY(d_commit_inner(ctx, seed, zhat, N, 1, 0, K, lhs));
+        TRY(d_amortize(ctx, Chat, That, K, R, 0, R, rhs_h, rhs));
+        TRY(dev_equal(ctx, lhs, rhs, K * 64, dcnt, &eq));
+        if (!eq) fc = 15;
+    }
+    uint32_t *scal;                                              // a handful of single hats
+    TRY(arena_alloc(ctx, (size_t)16 * 32, &scal));
+    uint32_t *t1, *t2;
+    TRY(arena_alloc(ctx, R * R * 32, &t1));
+    TRY(arena_alloc(ctx, R * R * 32, &t2));
+    auto gcc_sum = [&](const uint32_t *M, uint32_t *out1) -> int {   // sum_ij M_ij c_i c_j
+        LAUNCH(k_pointwise, grid_for(R * R * 32, 256, ctx->sms * 16), 256, Chat, (size_t)R, (size_t)R, M, (const uint32_t *)nullptr, (size_t)1, (size_t)0,
+               (const uint32_t *)nullptr, t1, (size_t)(R * R));
+        LAUNCH(k_pointwise, grid_for(R * R * 32, 256, ctx->sms * 16), 256, Chat, (size_t)1, (size_t)R, t1, (const uint32_t *)nullptr, (size_t)1, (size_t)0,
+               (const uint32_t *)nullptr, t2, (size_t)(R * R));
+        LAUNCH(k_sum_hats, 1, 32, t2, (size_t)(R * R), (size_t)1, out1, (size_t)1);
+        return LAB_OK;
+    };
+    if (!fc) {   // check 16: <z,z> == sum g_ij c_i c_j (verification.rs:303-314)
+        LAUNCH(k_ip_hat, 1, 256, zhat, (size_t)1, (size_t)0, zhat, (size_t)1, (size_t)0, (size_t)N, (size_t)1, 1u, 0, scal);
+        TRY(gcc_sum(Ghat, scal + 32));
+        TRY(dev_equal(ctx, scal, scal + 32, 32, dcnt, &eq));
+        if (!eq) fc = 16;
+    }
+    if (!fc) {   // check 17: sum_i <phi_i, z> c_i == sum h_ij c_i c_j (verification.rs:320-334)
+        uint32_t *pz, *pzc;
+        TRY(arena_alloc(ctx, R * 32, &pz));
+        TRY(arena_alloc(ctx, R * 32, &pzc));
+        LAUNCH(k_ip_hat, (unsigned)R, 256, PFhat, (size_t)R, (size_t)1, zhat, (size_t)1, (size_t)0, (size_t)N, (size_t)1, 1u, 0, pz);
+        LAUNCH(k_pointwise, grid_for(R * 32, 256, ctx->sms * 16), 256, Chat, (size_t)1, (size_t)R, pz, (const uint32_t *)nullptr, (size_t)1, (size_t)0,
+               (const uint32_t *)nullptr, pzc, (size_t)R);
+        LAUNCH(k_sum_hats, 1, 32, pzc, (size_t)R, (size_t)1, scal + 64, (size_t)1);
+        TRY(gcc_sum(Hhat, scal + 96));
+        TRY(dev_equal(ctx, scal + 64, scal + 96, 32, dcnt, &eq));
+        if (!eq) fc = 17;
+    }
+    if (!fc) {   // check 18: sum a_ij g_ij + sum h_ii - b == 0 with a = alpha a + beta psi a, b = alpha b + beta b'' (lines 5, 7; :340-352)
+        uint32_t *psih;
+        TRY(arena_alloc(ctx, (size_t)64, &psih));
+        uint32_t psipoly[64] = {0};
+        psipoly[0] = psi;
+        uint32_t *dpsi;
+        TRY(upload(ctx, psipoly, (size_t)64, &dpsi));
+        TRY(d_fwd_hat(ctx, dpsi, psih, 1, 0, 0));
+        // acon = alpha * a + (beta * psi) * a
+        LAUNCH(k_pointwise, 1, 32, beta_h, (size_t)1, (size_t)0, psih, (const uint32_t *)nullptr, (size_t)1, (size_t)0, (const uint32_t *)nullptr, psih + 32, (size_t)1);
+        LAUNCH(k_pointwise, grid_for(R * R * 32, 256, ctx->sms * 16), 256, alpha_h, (size_t)1, (size_t)0, Ahat, psih + 32, (size_t)1, (size_t)0, Ahat, t1,
+               (size_t)(R * R));
+        LAUNCH(k_pointwise, grid_for(R * R * 32, 256, ctx->sms * 16), 256, t1, (size_t)1, (size_t)(R * R), Ghat, (const uint32_t *)nullptr, (size_t)1, (size_t)0,
+               (const uint32_t *)nullptr, t2, (size_t)(R * R));
+        LAUNCH(k_sum_hats, 1, 32, t2, (size_t)(R * R), (size_t)1, scal + 128, (size_t)1);                       // s1
+        LAUNCH(k_sum_hats, 1, 32, Hhat, (size_t)R, (size_t)(R + 1), scal + 160, (size_t)1);                     // s2 = sum h_ii
+        LAUNCH(k_pointwise, 1, 32, alpha_h, (size_t)1, (size_t)0, b_h, beta_h, (size_t)1, (size_t)0, bpp_h, scal + 192, (size_t)1);   // b
+        LAUNCH(k_addsub_hats, 1, 32, scal + 128, scal + 160, scal + 192, scal + 224, (size_t)32);
+        CK(cudaMemsetAsync(scal + 256, 0, 32 * sizeof(uint32_t), ctx->stream));
+        TRY(dev_equal(ctx, scal + 224, scal + 256, 32, dcnt, &eq));
+        if (!eq) fc = 18;
+    }
+    if (!fc) {   // check 19: u_1 (verification.rs:372-415)
+        uint32_t *cand;
+        TRY(arena_alloc(ctx, K1 * 64, &cand));
+        TRY(d_outer_u1(ctx, c, seed, dT, dG, cand));
+        TRY(dev_equal(ctx, cand, du1, K1 * 64, dcnt, &eq));
+        if (!eq) fc = 19;
+    }
+    if (!fc) {   // check 20: u_2 (verification.rs:421-435)
+        uint32_t *cand;
+        TRY(arena_alloc(ctx, K2 * 64, &cand));
+        TRY(d_outer_u2(ctx, c, seed, dH, cand));
+        TRY(dev_equal(ctx, cand, du2, K2 * 64, dcnt, &eq));
+        if (!eq) fc = 20;
+    }
+    if (failed_check) *failed_check = fc;
+    *accepted = fc == 0;
+    return LAB_OK;
+}
+
 extern "C" int lab_prove_batch(lab_ctx *ctx, const lab_constants *c, size_t n_statements, const uint8_t *seeds, int shared_crs, const uint32_t *S,
                                const lab_state *st, const lab_challenges *ch, lab_transcript *out) {
     TRY(check_consts(ctx, c, true));

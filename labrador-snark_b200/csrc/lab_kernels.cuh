@@ -328,6 +328,26 @@ __global__ void k_sum_hats(const uint32_t *__restrict__ in, size_t cnt, size_t s
     out[idx] = lab_pack(lab_canon(r), lab_canon(i));
 }
 
+// number of differing words between two buffers (verifier equality checks 15-20, verification.rs:291-435)
+__global__ void k_count_diff(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b, size_t n, unsigned long long *out) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    unsigned long long d = 0;
+    for (; idx < n; idx += stride) d += a[idx] != b[idx];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if ((threadIdx.x & 31) == 0 && d) atomicAdd(out, d);
+}
+// out[p] = X[p] + Y[p] - Z[p] (mod Q) over hats; Y or Z may be null
+__global__ void k_addsub_hats(const uint32_t *__restrict__ X, const uint32_t *__restrict__ Y, const uint32_t *__restrict__ Z, uint32_t *__restrict__ out, size_t n_words) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_words) return;
+    uint32_t x = X[idx], r = lab_re(x), i = lab_im(x);
+    if (Y) { uint32_t y = Y[idx]; r += lab_re(y); i += lab_im(y); }
+    if (Z) { uint32_t z = Z[idx]; r += 2u * LABQ - lab_re(z); i += 2u * LABQ - lab_im(z); }
+    out[idx] = lab_pack(lab_canon(r), lab_canon(i));
+}
+
 // exact sum of squares of canonical representatives (util.rs:195-202)
 __global__ void __launch_bounds__(256) k_norm_sq(const uint32_t *__restrict__ in, size_t n, unsigned long long *out) {
     unsigned long long acc = 0;

@@ -259,6 +259,59 @@ class Context:
         return z
 
 
+    # ---- Verifier::verify on the GPU and batched proving ----
+    def verify(self, c, seed, phi, a, b, ch, tr):
+        """tr: dict with u_1, projection_int, projection, b_prime_prime, u_2, z, t, g, h, jl_attempt (oracle layout).
+        Returns (accepted, failed_check, norm_sum) like the reference's Verifier::verify (verification.rs:25-438)."""
+        phi, a, b = _u32(phi), _u32(a), _u32(b)
+        pi = np.ascontiguousarray(ch["pi"], dtype=np.int8)
+        if pi.ndim == 3:
+            pi = pi[None]
+        omega, alpha, beta, cc = _u32(ch["omega"]), _u32(ch["alpha"]), _u32(ch["beta"]), _u32(ch["c"])
+        keep = {k: _u32(tr[k]) for k in ("u_1", "projection", "b_prime_prime", "u_2", "z", "t", "g", "h")}
+        pint = np.ascontiguousarray(tr["projection_int"], dtype=np.int64)
+        cst = _lib.CState(_p(phi), _p(a), _p(b))
+        cch = _lib.CChallenges(_p(pi), pi.shape[0], int(ch["psi"]), _p(omega), _p(alpha), _p(beta), _p(cc))
+        ctr = _lib.CTranscript(_p(keep["u_1"]), int(tr.get("jl_attempt", 0)), _p(pint), _p(keep["projection"]), _p(keep["b_prime_prime"]),
+                               _p(keep["u_2"]), _p(keep["z"]), _p(keep["t"]), _p(keep["g"]), _p(keep["h"]), None, 0)
+        acc, fc, ns = C.c_int(0), C.c_int(0), C.c_uint64(0)
+        self._ck(self.L.lab_verify(self._h, C.byref(c), _p(_seed_buf(seed)), C.byref(cst), C.byref(cch), C.byref(ctr),
+                                   C.byref(acc), C.byref(fc), C.byref(ns)))
+        return bool(acc.value), fc.value, ns.value
+
+    def prove_batch(self, c, seeds, shared_crs, S, phi, a, b, challenges):
+        """lab_prove_batch: S [B][R][N][64], phi [B][R][N][64], a [B][R][R][64], b [B][64]; challenges: list of dicts.
+        Returns a list of oracle-layout transcript dicts."""
+        S, phi, a, b = _u32(S), _u32(phi), _u32(a), _u32(b)
+        B = S.shape[0]
+        seedbuf = np.frombuffer(b"".join(bytes(s) for s in seeds), dtype=np.uint8).copy()
+        sts = (_lib.CState * B)()
+        chs = (_lib.CChallenges * B)()
+        trs = (_lib.CTranscript * B)()
+        keep, outs = [], []
+        for i in range(B):
+            ch = challenges[i]
+            pi = np.ascontiguousarray(ch["pi"], dtype=np.int8)
+            if pi.ndim == 3:
+                pi = pi[None]
+            arrs = [pi, _u32(ch["omega"]), _u32(ch["alpha"]), _u32(ch["beta"]), _u32(ch["c"])]
+            keep.append(arrs)
+            sts[i] = _lib.CState(_p(phi[i]), _p(a[i]), _p(b[i]))
+            chs[i] = _lib.CChallenges(_p(arrs[0]), pi.shape[0], int(ch["psi"]), _p(arrs[1]), _p(arrs[2]), _p(arrs[3]), _p(arrs[4]))
+            o = {"u_1": np.zeros((c.KAPPA_1, D), np.uint32), "projection_int": np.zeros(JL_ROWS, np.int64), "projection": np.zeros(JL_ROWS, np.uint32),
+                 "b_prime_prime": np.zeros(D, np.uint32), "u_2": np.zeros((c.KAPPA_2, D), np.uint32), "z": np.zeros((c.N, D), np.uint32),
+                 "t": np.zeros((c.R, c.KAPPA, D), np.uint32), "g": np.zeros((c.R, c.R, D), np.uint32), "h": np.zeros((c.R, c.R, D), np.uint32),
+                 "phi_final": np.zeros((c.R, c.N, D), np.uint32)}
+            outs.append(o)
+            trs[i] = _lib.CTranscript(_p(o["u_1"]), 0, _p(o["projection_int"]), _p(o["projection"]), _p(o["b_prime_prime"]), _p(o["u_2"]),
+                                      _p(o["z"]), _p(o["t"]), _p(o["g"]), _p(o["h"]), _p(o["phi_final"]), 0)
+        self._ck(self.L.lab_prove_batch(self._h, C.byref(c), C.c_size_t(B), _p(seedbuf), C.c_int(int(shared_crs)), _p(S), sts, chs, trs))
+        for i in range(B):
+            outs[i]["jl_attempt"] = trs[i].jl_attempt
+            outs[i]["norm_sum"] = int(trs[i].norm_sum)
+        return outs
+
+
 _default_ctx = None
 
 
