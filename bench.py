@@ -305,7 +305,8 @@ def main():
             ver = lb.Verifier.new(st2.b_prime_k, c2, seed=PRG_SEED, n_attempts=6)
             prover = lb.Prover.new(S2, ver, c2, ctx)
             crs = lb.CRS.from_seed(c2, SEED32, ctx)
-            prover.proof_gen(st2, crs)
+            for _ in range(3):       # warm-up (the scratch arena is sized after the first call)
+                prover.proof_gen(st2, crs)
             t0 = time.perf_counter()
             for _ in range(5):
                 prover.proof_gen(st2, crs)

@@ -16,6 +16,12 @@ typedef unsigned __int128 u128;
 
 static thread_local std::string g_create_err;
 
+// LAB_TRACE=1: print host-side timestamps of the stages of lab_prove (debug aid, no effect on results)
+#include <chrono>
+static const bool g_trace = std::getenv("LAB_TRACE") != nullptr;
+static double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+#define TRACE(tag) do { if (g_trace) std::fprintf(stderr, "[lab %10.1f us] %s\n", now_us() - t_trace0, tag); } while (0)
+
 struct lab_ctx {
     int device = 0;
     int sms = 148;
@@ -32,6 +38,10 @@ struct lab_ctx {
     uint32_t *What = nullptr;          // owned, [N][R][32]
     size_t What_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // K_MV work-item lists depend only on the shape: kept on the device so that a proof needs no mid-stream H2D copy
+    // (an H2D copy from pageable memory first synchronises the stream and would stall the enqueueing thread)
+    struct MvPlan { std::vector<unsigned char> host; void *dev; };
+    std::vector<MvPlan> mv_plans;
 };
 
 #define CK(call)                                                                                     \
@@ -158,6 +168,7 @@ extern "C" void lab_ctx_destroy(lab_ctx *ctx) {
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->What) cudaFree(ctx->What);
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
+    for (auto &p : ctx->mv_plans) cudaFree(p.dev);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -313,18 +324,33 @@ static int d_crs_matvec(lab_ctx *ctx, const LabSeed &seed, const std::vector<MvS
     for (const MvSeg &s : segs)
         for (uint32_t y = 0; y < s.count; y += (uint32_t)ch) {
             MvItem it;
+            std::memset(&it, 0, sizeof it);
             it.base_lo = (uint64_t)s.base; it.base_hi = (uint64_t)(s.base >> 64);
             it.row_stride = s.row_stride; it.sp = s.sp; it.sk = s.sk; it.nk = s.nk;
             it.y0 = y; it.cnt = (uint32_t)std::min<uint64_t>(ch, s.count - y); it.vec_off = s.vec_off;
             items.push_back(it);
         }
     const uint32_t ipr = (uint32_t)items.size();
-    MvItem *d_items;
+    MvItem *d_items = nullptr;
     uint32_t *partial;
-    TRY(arena_alloc(ctx, items.size(), &d_items));
+    const size_t ibytes = items.size() * sizeof(MvItem);
+    for (auto &p : ctx->mv_plans)
+        if (p.host.size() == ibytes && std::memcmp(p.host.data(), items.data(), ibytes) == 0) { d_items = (MvItem *)p.dev; break; }
+    if (!d_items) {
+        if (ctx->mv_plans.size() >= 32) {           // bounded cache; cudaFree synchronises, so nothing in flight uses it
+            cudaFree(ctx->mv_plans.front().dev);
+            ctx->mv_plans.erase(ctx->mv_plans.begin());
+        }
+        void *dev = nullptr;
+        CK(cudaMalloc(&dev, ibytes));
+        CK(cudaMemcpy(dev, items.data(), ibytes, cudaMemcpyHostToDevice));
+        lab_ctx::MvPlan plan;
+        plan.host.assign((const unsigned char *)items.data(), (const unsigned char *)items.data() + ibytes);
+        plan.dev = dev;
+        ctx->mv_plans.push_back(std::move(plan));
+        d_items = (MvItem *)dev;
+    }
     TRY(arena_alloc(ctx, (size_t)n_rows * ipr * 32, &partial));
-    // pageable source: cudaMemcpyAsync copies it to a staging buffer before returning
-    CK(cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(MvItem), cudaMemcpyHostToDevice, ctx->stream));
     const uint64_t warps = n_rows * ipr;
     LAUNCH(k_crs_matvec, (unsigned)((warps + 7) / 8), 256, seed, d_items, ipr, n_rows, x0, V, partial);
     LAUNCH(k_finish_rows, (unsigned)((n_rows + 7) / 8), 256, partial, ipr, n_rows, out);
@@ -684,22 +710,25 @@ static int prove_one(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_by
     if (ch->n_attempts < 1) FAIL(LAB_ERR_PARAMS, "need at least one JL attempt");
     const LabSeed seed = make_seed(seed_bytes);
     const uint32_t psi = ch->psi % LAB_Q;
+    const double t_trace0 = now_us();
 
-    // S1: inner commitments (proofgen.rs:35-49)
+    // All host->device copies come first: a copy from pageable host memory synchronises the stream, so none may follow
+    // the long kernels.  (The K_MV item lists are cached on the device per shape for the same reason.)
     uint32_t *dS, *What, *dT;
     TRY(load_witness(ctx, c, S, &dS, &What));
-    TRY(arena_alloc(ctx, R * K * 64, &dT));
-    TRY(d_commit_inner(ctx, seed, What, N, R, 0, K, dT));
-    // S2: g (proofgen.rs:59-70)
-    uint32_t *Ghat, *dG;
-    TRY(arena_alloc(ctx, R * R * 32, &Ghat));
-    TRY(arena_alloc(ctx, R * R * 64, &dG));
-    TRY(d_gram(ctx, What, N, R, 0, R, Ghat, dG));
-    // S3: u_1 (proofgen.rs:101-153)
-    uint32_t *du1;
-    TRY(arena_alloc(ctx, K1 * 64, &du1));
-    TRY(d_outer_u1(ctx, c, seed, dT, dG, du1));
-    // S4: JL with retries (proofgen.rs:161-186)
+    uint32_t *dc, *dphi, *dom, *da, *dab;
+    TRY(upload(ctx, ch->c, R * 64, &dc));
+    TRY(upload(ctx, st->phi, R * ND, &dphi));
+    TRY(upload(ctx, ch->omega, (size_t)LAB_JL_ROWS, &dom));
+    TRY(upload(ctx, st->a, R * R * 64, &da));
+    uint32_t ab[128];
+    std::memcpy(ab, ch->alpha, 64 * sizeof(uint32_t));
+    std::memcpy(ab + 64, ch->beta, 64 * sizeof(uint32_t));
+    TRY(upload(ctx, ab, (size_t)128, &dab));
+    TRACE("uploads done");
+    // S4: JL with retries (proofgen.rs:161-186: initial attempt + at most 5 retries).  It depends on the witness only, so it
+    // is enqueued FIRST: the host sync that the accept/reject decision needs then waits for a few microseconds of GPU work
+    // instead of for the outer commitment, and everything after it runs without another sync until the end.
     int8_t *dPi;
     unsigned long long *dp;
     TRY(arena_alloc(ctx, R * LAB_JL_ROWS * ND, &dPi));
@@ -716,92 +745,102 @@ static int prove_one(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_by
         att++;
     }
     out->jl_attempt = att;
-    for (int j = 0; j < LAB_JL_ROWS; j++) {
-        int64_t m = out->projection_int[j] % (int64_t)LAB_Q;
-        out->projection[j] = (uint32_t)(m < 0 ? m + (int64_t)LAB_Q : m);
-    }
-    // S5: aggregation (proofgen.rs:189-289), upper_bound = 1
-    uint32_t *dphi, *dom, *dpp, *Phihat, *PPhat;
-    TRY(upload(ctx, st->phi, R * ND, &dphi));
-    TRY(upload(ctx, ch->omega, (size_t)LAB_JL_ROWS, &dom));
-    TRY(arena_alloc(ctx, R * ND, &dpp));
-    TRY(d_aggregate_phi(ctx, c, dphi, dPi, psi, dom, dpp));
-    TRY(arena_alloc(ctx, R * N * 32, &Phihat));
-    TRY(arena_alloc(ctx, R * N * 32, &PPhat));
-    TRY(d_fwd_hat(ctx, dphi, Phihat, R * N, N, R));
-    TRY(d_fwd_hat(ctx, dpp, PPhat, R * N, N, R));
-    uint32_t *da, *Ahat, *AG, *diag, *sums, *dsums;
-    TRY(upload(ctx, st->a, R * R * 64, &da));
-    TRY(arena_alloc(ctx, R * R * 32, &Ahat));
-    TRY(arena_alloc(ctx, R * R * 32, &AG));
-    TRY(arena_alloc(ctx, R * 32, &diag));
-    TRY(arena_alloc(ctx, (size_t)2 * 32, &sums));
-    TRY(arena_alloc(ctx, (size_t)2 * 64, &dsums));
-    TRY(d_fwd_hat(ctx, da, Ahat, R * R, 0, 0));
-    LAUNCH(k_pointwise, grid_for(R * R * 32, 256, ctx->sms * 16), 256, Ahat, (size_t)1, (size_t)(R * R), Ghat, (const uint32_t *)nullptr, (size_t)1,
-           (size_t)0, (const uint32_t *)nullptr, AG, (size_t)(R * R));
-    LAUNCH(k_ip_hat, (unsigned)R, 256, PPhat, (size_t)R, (size_t)1, What, (size_t)R, (size_t)1, (size_t)N, (size_t)0, 1u, 2, diag);
-    LAUNCH(k_sum_hats, 1, 32, AG, (size_t)(R * R), (size_t)1, sums, (size_t)1);
-    LAUNCH(k_sum_hats, 1, 32, diag, (size_t)R, (size_t)1, sums + 32, (size_t)1);
-    TRY(d_inv_hat(ctx, sums, dsums, 2));
-    uint32_t hs[128];
-    TRY(download(ctx, hs, dsums, (size_t)128));
-    // S6: phi_final = alpha phi + beta phi'' (proofgen.rs:295-314)
-    uint32_t *dab, *ABhat, *PFhat;
-    uint32_t ab[128];
-    std::memcpy(ab, ch->alpha, 64 * sizeof(uint32_t));
-    std::memcpy(ab + 64, ch->beta, 64 * sizeof(uint32_t));
-    TRY(upload(ctx, ab, (size_t)128, &dab));
-    TRY(arena_alloc(ctx, (size_t)64, &ABhat));
-    TRY(arena_alloc(ctx, R * N * 32, &PFhat));
-    TRY(d_fwd_hat(ctx, dab, ABhat, 2, 0, 0));
-    LAUNCH(k_pointwise, grid_for(R * N * 32, 256, ctx->sms * 16), 256, ABhat, (size_t)1, (size_t)0, Phihat, ABhat + 32, (size_t)1, (size_t)0, PPhat,
-           PFhat, (size_t)(R * N));
-    // S7: h (proofgen.rs:320-358)
-    uint32_t *Hhat, *dH;
-    TRY(arena_alloc(ctx, R * R * 32, &Hhat));
-    TRY(arena_alloc(ctx, R * R * 64, &dH));
-    TRY(d_h_gram(ctx, PFhat, What, N, R, Hhat, dH));
-    // S8: u_2 (proofgen.rs:364-378)
-    uint32_t *du2;
-    TRY(arena_alloc(ctx, K2 * 64, &du2));
-    TRY(d_outer_u2(ctx, c, seed, dH, du2));
-    // S9: z (proofgen.rs:380-399)
-    uint32_t *dc, *Chat, *zhat, *dz;
-    TRY(upload(ctx, ch->c, R * 64, &dc));
+    TRACE("jl accepted");
+    // S1: inner commitments (proofgen.rs:35-49)
+    TRY(arena_alloc(ctx, R * K * 64, &dT));
+    TRY(d_commit_inner(ctx, seed, What, N, R, 0, K, dT));
+    // S2: g (proofgen.rs:59-70)
+    uint32_t *Ghat, *dG;
+    TRY(arena_alloc(ctx, R * R * 32, &Ghat));
+    TRY(arena_alloc(ctx, R * R * 64, &dG));
+    TRY(d_gram(ctx, What, N, R, 0, R, Ghat, dG));
+    // S3: u_1 (proofgen.rs:101-153)
+    uint32_t *du1;
+    TRY(arena_alloc(ctx, K1 * 64, &du1));
+    TRY(d_outer_u1(ctx, c, seed, dT, dG, du1));
+    TRACE("u1 enqueued");
+    // S9: z (proofgen.rs:380-399) -- independent of the JL outcome, enqueued first
+    uint32_t *Chat, *zhat, *dz;
     TRY(arena_alloc(ctx, R * 32, &Chat));
     TRY(arena_alloc(ctx, N * 32, &zhat));
     TRY(arena_alloc(ctx, N * 64, &dz));
     TRY(d_fwd_hat(ctx, dc, Chat, R, 0, 0));
     TRY(d_amortize(ctx, Chat, What, N, R, 0, R, zhat, dz));
-    // exact integer of Check 14 (verification.rs:185-267): digits of z (B, 2), t (B_1, T_1), all g (B_2, T_2), all h (B_1, T_1)
+    // (all device->host copies are issued at the very end: a copy into pageable host memory blocks the calling thread
+    //  until the stream reaches it, which would serialise the enqueueing of the remaining stages behind u_1)
+    // statement / challenge operands of S5-S8
     unsigned long long *dnorm;
+    uint32_t *dpp, *Phihat, *PPhat, *Ahat, *AG, *diag, *sums, *dsums, *ABhat, *PFhat, *Hhat, *dH, *du2, *pf_tmp = nullptr;
     TRY(arena_alloc(ctx, (size_t)1, &dnorm));
-    CK(cudaMemsetAsync(dnorm, 0, sizeof *dnorm, ctx->stream));
-    LAUNCH(k_digit_norm_sq, grid_for(N * 64, 2048, ctx->sms * 8), 256, dz, (size_t)(N * 64), (uint32_t)c->B, 2, dnorm);
-    LAUNCH(k_digit_norm_sq, grid_for(R * K * 64, 2048, ctx->sms * 8), 256, dT, (size_t)(R * K * 64), (uint32_t)c->B_1, (int)T1, dnorm);
-    LAUNCH(k_digit_norm_sq, grid_for(R * R * 64, 2048, ctx->sms * 8), 256, dG, (size_t)(R * R * 64), (uint32_t)c->B_2, (int)T2, dnorm);
-    LAUNCH(k_digit_norm_sq, grid_for(R * R * 64, 2048, ctx->sms * 8), 256, dH, (size_t)(R * R * 64), (uint32_t)c->B_1, (int)T1, dnorm);
-    // outputs
-    if (out->phi_final) {
-        uint32_t *tmp;
-        TRY(arena_alloc(ctx, R * N * 64, &tmp));
-        TRY(d_inv_hat(ctx, PFhat, tmp, R * N));
-        // n-major polys (n*R + i) -> [R][N][64]: one strided 2D copy per i
-        for (uint64_t i = 0; i < R; i++)
-            CK(cudaMemcpy2DAsync(out->phi_final + i * N * 64, 64 * sizeof(uint32_t), tmp + i * 64, R * 64 * sizeof(uint32_t), 64 * sizeof(uint32_t), N,
-                                 cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    TRY(download(ctx, out->u_1, du1, K1 * 64));
-    TRY(download(ctx, out->u_2, du2, K2 * 64));
-    TRY(download(ctx, out->z, dz, N * 64));
-    TRY(download(ctx, out->t, dT, R * K * 64));
-    TRY(download(ctx, out->g, dG, R * R * 64));
-    TRY(download(ctx, out->h, dH, R * R * 64));
+    TRY(arena_alloc(ctx, R * ND, &dpp));
+    TRY(arena_alloc(ctx, R * N * 32, &Phihat));
+    TRY(arena_alloc(ctx, R * N * 32, &PPhat));
+    TRY(arena_alloc(ctx, R * R * 32, &Ahat));
+    TRY(arena_alloc(ctx, R * R * 32, &AG));
+    TRY(arena_alloc(ctx, R * 32, &diag));
+    TRY(arena_alloc(ctx, (size_t)2 * 32, &sums));
+    TRY(arena_alloc(ctx, (size_t)2 * 64, &dsums));
+    TRY(arena_alloc(ctx, (size_t)64, &ABhat));
+    TRY(arena_alloc(ctx, R * N * 32, &PFhat));
+    TRY(arena_alloc(ctx, R * R * 32, &Hhat));
+    TRY(arena_alloc(ctx, R * R * 64, &dH));
+    TRY(arena_alloc(ctx, K2 * 64, &du2));
+    if (out->phi_final) TRY(arena_alloc(ctx, R * N * 64, &pf_tmp));
+    TRY(d_fwd_hat(ctx, dphi, Phihat, R * N, N, R));
+    TRY(d_fwd_hat(ctx, da, Ahat, R * R, 0, 0));
+    TRY(d_fwd_hat(ctx, dab, ABhat, 2, 0, 0));
+    // a_ij g_ij does not depend on the JL outcome either
+    LAUNCH(k_pointwise, grid_for(R * R * 32, 256, ctx->sms * 16), 256, Ahat, (size_t)1, (size_t)(R * R), Ghat, (const uint32_t *)nullptr, (size_t)1,
+           (size_t)0, (const uint32_t *)nullptr, AG, (size_t)(R * R));
+    LAUNCH(k_sum_hats, 1, 32, AG, (size_t)(R * R), (size_t)1, sums, (size_t)1);
+    // S5-S8 with the accepted Pi (already resident in dPi)
+    uint32_t hs[128];
     unsigned long long hnorm = 0;
-    CK(cudaMemcpyAsync(&hnorm, dnorm, sizeof hnorm, cudaMemcpyDeviceToHost, ctx->stream));
-    TRY(lab_sync(ctx));
+    {
+        // S5: aggregation (proofgen.rs:189-289), upper_bound = 1
+        TRY(d_aggregate_phi(ctx, c, dphi, dPi, psi, dom, dpp));
+        TRY(d_fwd_hat(ctx, dpp, PPhat, R * N, N, R));
+        LAUNCH(k_ip_hat, (unsigned)R, 256, PPhat, (size_t)R, (size_t)1, What, (size_t)R, (size_t)1, (size_t)N, (size_t)0, 1u, 2, diag);
+        LAUNCH(k_sum_hats, 1, 32, diag, (size_t)R, (size_t)1, sums + 32, (size_t)1);
+        TRY(d_inv_hat(ctx, sums, dsums, 2));
+        // S6: phi_final = alpha phi + beta phi'' (proofgen.rs:295-314)
+        LAUNCH(k_pointwise, grid_for(R * N * 32, 256, ctx->sms * 16), 256, ABhat, (size_t)1, (size_t)0, Phihat, ABhat + 32, (size_t)1, (size_t)0, PPhat,
+               PFhat, (size_t)(R * N));
+        // S7: h (proofgen.rs:320-358)
+        TRY(d_h_gram(ctx, PFhat, What, N, R, Hhat, dH));
+        // S8: u_2 (proofgen.rs:364-378)
+        TRY(d_outer_u2(ctx, c, seed, dH, du2));
+        // exact integer of Check 14 (verification.rs:185-267): digits of z (B, 2), t (B_1, T_1), all g (B_2, T_2), all h (B_1, T_1)
+        CK(cudaMemsetAsync(dnorm, 0, sizeof *dnorm, ctx->stream));
+        LAUNCH(k_digit_norm_sq, grid_for(N * 64, 2048, ctx->sms * 8), 256, dz, (size_t)(N * 64), (uint32_t)c->B, 2, dnorm);
+        LAUNCH(k_digit_norm_sq, grid_for(R * K * 64, 2048, ctx->sms * 8), 256, dT, (size_t)(R * K * 64), (uint32_t)c->B_1, (int)T1, dnorm);
+        LAUNCH(k_digit_norm_sq, grid_for(R * R * 64, 2048, ctx->sms * 8), 256, dG, (size_t)(R * R * 64), (uint32_t)c->B_2, (int)T2, dnorm);
+        LAUNCH(k_digit_norm_sq, grid_for(R * R * 64, 2048, ctx->sms * 8), 256, dH, (size_t)(R * R * 64), (uint32_t)c->B_1, (int)T1, dnorm);
+        if (out->phi_final) TRY(d_inv_hat(ctx, PFhat, pf_tmp, R * N));
+        TRACE("all kernels enqueued");
+        // ---- downloads ----
+        TRY(download(ctx, out->u_1, du1, K1 * 64));
+        TRY(download(ctx, out->z, dz, N * 64));
+        TRY(download(ctx, out->t, dT, R * K * 64));
+        TRY(download(ctx, out->g, dG, R * R * 64));
+        TRY(download(ctx, hs, dsums, (size_t)128));
+        if (out->phi_final) {
+            // n-major polys (n*R + i) -> [R][N][64]: one strided 2D copy per i
+            for (uint64_t i = 0; i < R; i++)
+                CK(cudaMemcpy2DAsync(out->phi_final + i * N * 64, 64 * sizeof(uint32_t), pf_tmp + i * 64, R * 64 * sizeof(uint32_t), 64 * sizeof(uint32_t), N,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        TRY(download(ctx, out->u_2, du2, K2 * 64));
+        TRY(download(ctx, out->h, dH, R * R * 64));
+        CK(cudaMemcpyAsync(&hnorm, dnorm, sizeof hnorm, cudaMemcpyDeviceToHost, ctx->stream));
+        TRY(lab_sync(ctx));
+        TRACE("downloads + final sync done");
+    }
     out->norm_sum = hnorm;
+    for (int j = 0; j < LAB_JL_ROWS; j++) {
+        int64_t m = out->projection_int[j] % (int64_t)LAB_Q;
+        out->projection[j] = (uint32_t)(m < 0 ? m + (int64_t)LAB_Q : m);
+    }
     // b'' = psi * sum a_ij g_ij + sum <phi''_i, s_i> (proofgen.rs:258-278); check (verification.rs:532-551)
     for (int d = 0; d < 64; d++) out->b_prime_prime[d] = (uint32_t)(((uint64_t)hs[d] * psi + hs[64 + d]) % LAB_Q);
     uint64_t acc = 0;

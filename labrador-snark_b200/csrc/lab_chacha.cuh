@@ -109,25 +109,50 @@ __device__ __noinline__ uint32_t lab_crs_coeff_slow(const LabSeed &seed, uint64_
 
 // NB coefficients at counters (chi:clo) + off[b]; only keystream words 0..3 of block 0 are finished
 // on the fast path (the compiler drops the dead tail of the last round).
+// Key setup: the 256-bit sum seed + (chi:clo) and the byte swaps of its upper six key words are done once for all NB
+// blocks; a block only adds its small offset to the low 64-bit limb and swaps two words.  If that addition carries out
+// of the low limb (possible only for seeds whose low limb is within `off` of 2^64) the block is recomputed by the
+// generic slow path, which also handles rejected draws.
 template <int NB>
 __device__ __forceinline__ void lab_crs_coeffs(const LabSeed &seed, uint64_t clo, uint64_t chi, const uint32_t (&off)[NB], uint32_t (&out)[NB]) {
+    const uint64_t s0 = seed.limb[0] + clo;
+    const uint64_t c0 = s0 < clo;
+    uint64_t s1 = seed.limb[1] + chi;
+    uint64_t c1 = s1 < chi;
+    s1 += c0;
+    c1 += (s1 < c0);
+    const uint64_t s2 = seed.limb[2] + c1;
+    const uint64_t c2 = s2 < c1;
+    const uint64_t s3 = seed.limb[3] + c2;
+    uint32_t khi[6];
+    khi[0] = lab_bswap32((uint32_t)(s3 >> 32));
+    khi[1] = lab_bswap32((uint32_t)s3);
+    khi[2] = lab_bswap32((uint32_t)(s2 >> 32));
+    khi[3] = lab_bswap32((uint32_t)s2);
+    khi[4] = lab_bswap32((uint32_t)(s1 >> 32));
+    khi[5] = lab_bswap32((uint32_t)s1);
     uint32_t x[NB][16];
+    bool carry[NB];
 #pragma unroll
     for (int b = 0; b < NB; b++) {
-        uint64_t lo = clo + off[b];
-        uint64_t hi = chi + (lo < clo);
-        uint32_t key[8];
-        lab_key_from_counter(seed, lo, hi, key);
-        lab_chacha_init(x[b], key, 0);
+        const uint64_t t = s0 + off[b];
+        carry[b] = t < s0;
+        x[b][0] = 0x61707865u; x[b][1] = 0x3320646eu; x[b][2] = 0x79622d32u; x[b][3] = 0x6b206574u;
+#pragma unroll
+        for (int i = 0; i < 6; i++) x[b][4 + i] = khi[i];
+        x[b][10] = lab_bswap32((uint32_t)(t >> 32));
+        x[b][11] = lab_bswap32((uint32_t)t);
+        x[b][12] = 0u; x[b][13] = 0u; x[b][14] = 0u; x[b][15] = 0u;
     }
     lab_chacha_rounds<NB>(x, seed.one);
 #pragma unroll
     for (int b = 0; b < NB; b++) {
         uint32_t w0 = x[b][0] + 0x61707865u, w1 = x[b][1] + 0x3320646eu, w2 = x[b][2] + 0x79622d32u, w3 = x[b][3] + 0x6b206574u;
-        if (!lab_sample_u128(w0, w1, w2, w3, out[b])) {
+        const bool ok = lab_sample_u128(w0, w1, w2, w3, out[b]);
+        if (carry[b] || !ok) {
             uint64_t lo = clo + off[b];
             uint64_t hi = chi + (lo < clo);
-            out[b] = lab_crs_coeff_slow(seed, lo, hi, 1u);
+            out[b] = lab_crs_coeff_slow(seed, lo, hi, carry[b] ? 0u : 1u);
         }
     }
 }

@@ -425,6 +425,23 @@ constexpr size_t KA_PAD_VECS = KA_CONS * 16;
 
 __device__ __forceinline__ void bar_sync_named(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive_named(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
 
 // Warp-specialised: warps 0-11 ("producers", three warpgroups, registers trimmed with setmaxnreg) do nothing but
 // ChaCha20 + the warp transform, one polynomial of A per tile each (tile = 4 rows x 3 columns), and park it in a
@@ -437,10 +454,17 @@ template <int IC>
 __global__ void __launch_bounds__(KA_THREADS, 1) k_commit_inner(LabSeed seed, const uint32_t *__restrict__ What, uint32_t N, uint32_t R,
                                                                  uint64_t row0, uint64_t nrows, uint32_t i_base, uint32_t *__restrict__ T) {
     __shared__ uint32_t Are[KA_DEPTH][KA_PROD][32], Aim[KA_DEPTH][KA_PROD][32], Anim[KA_DEPTH][KA_PROD][32];   // re, im, Q - im
+    __shared__ uint64_t empty_bar[KA_DEPTH];                     // consumers -> producers: slot may be overwritten
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < KA_DEPTH; s++) mbar_init(&empty_bar[s], 32 * KA_CONS);
+    }
+    __syncthreads();
     const uint64_t rblk = (uint64_t)blockIdx.x * KA_RT;          // first row of this CTA, relative to row0
     const uint32_t ntiles = (N + KA_COLS - 1) / KA_COLS;
-    // barrier ids: FULL[s] = 1 + s, EMPTY[s] = 1 + KA_DEPTH + s (0 is __syncthreads)
+    // FULL[s] is named barrier 1 + s (producers arrive, consumers sync); EMPTY[s] is an mbarrier only the consumers
+    // arrive on, so producer warps never wait for each other
     if (w < KA_PROD) {
         // ---------------- producer ----------------
         asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
@@ -454,7 +478,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_commit_inner(LabSeed seed, co
             uint32_t re = 0, im = 0;
             if (row_ok && KA_COLS * t + gcol < N) crs_poly_hat(seed, ctr, 0ull, tw, lane, re, im);
             ctr += 64ull * KA_COLS;
-            if (t >= KA_DEPTH) bar_sync_named(1 + KA_DEPTH + s, KA_THREADS);     // slot free again?
+            if (t >= KA_DEPTH) mbar_wait(&empty_bar[s], (t / KA_DEPTH - 1) & 1);  // slot free again?
             Are[s][w][lane] = re;
             Aim[s][w][lane] = im;
             Anim[s][w][lane] = LABQ - im;
@@ -509,7 +533,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_commit_inner(LabSeed seed, co
                         acci[r][ii] += ar[r] * sm_[ii] + am[r] * sr[ii];
                     }
             }
-            if (t + KA_DEPTH < ntiles) bar_arrive_named(1 + KA_DEPTH + s, KA_THREADS);   // slot may be overwritten
+            mbar_arrive(&empty_bar[s]);                          // slot may be overwritten
             if (++pending == 5) {                                 // 5 tiles * 3 columns * 2 products < 2^5 * 2^26
                 pending = 0;
 #pragma unroll

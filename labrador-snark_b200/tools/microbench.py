@@ -68,6 +68,38 @@ def main():
         print(json.dumps({"kernel": "commit_inner", "N": N, "R": R, "rows": rows, "ms_median": med,
                           "chacha_blocks_per_s": rows * N * 64 / (med * 1e-3)}), flush=True)
         ctx.free(dS); ctx.free(dT)
+    if "prove" in which:        # default-size full proofs: latency, launch count, and the u_1 stage alone
+        import time
+        for (N, R) in ((2, 2), (4, 4), (8, 8)):
+            c = lb.RuntimeConstants.new(N, R)
+            S = synth.generate_witness(N, R, c.BETA_BOUND, synth.SEED)
+            st = lb.State.new(S, c, synth.SEED, ctx)
+            ver = lb.Verifier.new(st.b_prime_k, c, seed=synth.SEED, n_attempts=6)
+            prover = lb.Prover.new(S, ver, c, ctx)
+            crs = lb.CRS.from_seed(c, SEED32, ctx)
+            tr = prover.proof_gen(st, crs)
+            tr = prover.proof_gen(st, crs)      # second warm-up: the scratch arena is sized after the first call
+            l0 = ctx.kernel_launches
+            t0 = time.perf_counter()
+            reps = 10 if N <= 4 else 3
+            per = []
+            for _ in range(reps):
+                t1 = time.perf_counter()
+                tr = prover.proof_gen(st, crs)
+                per.append(round((time.perf_counter() - t1) * 1e3, 3))
+            dt = (time.perf_counter() - t0) / reps
+            print("per-call ms", per, "jl_attempt", tr.jl_attempt, flush=True)
+            launches = (ctx.kernel_launches - l0) // reps
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                ctx.commit_outer_u1(c, SEED32, tr.t_i_all, tr.g_mat)
+            du1 = (time.perf_counter() - t0) / reps
+            blocks = (c.R * c.T_1 * c.KAPPA_1 * c.KAPPA + c.KAPPA * c.N + (c.R * (c.R + 1) // 2) * (c.T_1 + c.T_2) * c.KAPPA_2) * 64
+            t0 = time.perf_counter()
+            ok = ctx.verify(c, SEED32, st.phi_k[0], st.a_k[0], st.b_k[0], ver.challenges, tr.as_oracle_dict())
+            dv = time.perf_counter() - t0
+            print(json.dumps({"kernel": "prove", "N": N, "R": R, "ms_per_proof": dt * 1e3, "launches_per_proof": launches, "u1_stage_ms": du1 * 1e3,
+                              "chacha_blocks": blocks, "blocks_per_s_whole_proof": blocks / dt, "verify_ms": dv * 1e3, "verify_ok": ok[0]}), flush=True)
     if "commit" in which:
         for (N, R, rows) in ((256, 2, 148 * 4 * 8), (256, 8, 148 * 4 * 8), (256, 32, 148 * 4 * 8), (256, 64, 148 * 4 * 8), (4096, 64, 148 * 4 * 4)):
             c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)

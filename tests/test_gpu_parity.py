@@ -134,6 +134,21 @@ def test_commit_inner(ctx, orc, N, R):
     assert np.array_equal(got, ref)
 
 
+def test_commit_inner_counter_carry_inside_a_polynomial(ctx, orc):
+    """Seed whose low 64-bit limb overflows in the middle of polynomial 3 (lanes >= 10): the per-lane offset addition
+    carries into the upper key words and must take the generic path."""
+    N, R = 2, 2
+    low = (1 << 64) - 64 * 3 - 10
+    seed = bytes(range(1, 25)) + low.to_bytes(8, "big")
+    c = lb.RuntimeConstants.new(N, R)
+    co, _ = orc.constants(N, R)
+    S = synth.uniform_witness(N, R, seed=5)
+    assert np.array_equal(ctx.commit_inner(c, seed, S, 0, 8), orc.commit_inner_rows(co, seed, S, 0, 8))
+    assert np.array_equal(ctx.crs_expand(seed, 64 * 2, 4), orc.crs_polys(seed, 64 * 2, 4))
+    crs = lb.CRS.from_seed(c, seed, ctx)
+    assert np.array_equal(crs.fetch_B_ik_row(0, 0, 0), orc.fetch_B_ik_row(co, seed, 0, 0, 0))
+
+
 @pytest.mark.parametrize("N,R", [(1, 1), (2, 2), (7, 3), (33, 5)])
 def test_gram_z_jl(ctx, orc, N, R):
     c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
@@ -262,3 +277,28 @@ def test_prove_batch(ctx, orc):
             assert rc == 0
             for k in ("t", "g", "u_1", "projection_int", "b_prime_prime", "h", "u_2", "z"):
                 assert np.array_equal(outs[i][k], ref[k]), (shared, i, k)
+
+
+def test_large_shape_sampled_rows(ctx, orc):
+    """BASELINE config 4 shape (N = 2^16, R = 2^8, kappa = 2^22): sampled commitment rows, z and the exact witness norm
+    against the oracle (the full T is 275 GB and never materialised, SURVEY 8d cfg 4).  Exercises R > 64 (several
+    consumer passes), 64-bit counters and 4 GB operands."""
+    N, R = 1 << 16, 1 << 8
+    c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
+    co, _ = orc.constants(N, R)
+    dS = ctx.malloc(R * N * 256)
+    ctx.synth_zq_dev(synth.SEED, 1, 0, R * N * 64, dS)
+    ctx.witness_load_dev(c, dS)
+    rows = [0, c.KAPPA - 1]
+    S = np.empty((R, N, 64), np.uint32)
+    ctx.d2h(S, dS); ctx.sync()
+    assert np.array_equal(S[3, 77], synth.prg_zq(synth.SEED, 1, 64, start=(3 * N + 77) * 64))      # device PRG == host PRG
+    dT = ctx.malloc(R * 1 * 256)
+    for row in rows:
+        ctx.commit_inner_dev(SEED32, row, 1, dT)
+        T = np.empty((R, 1, 64), np.uint32)
+        ctx.d2h(T, dT); ctx.sync()
+        ref = orc.commit_inner_rows(co, SEED32, S, row, 1, ntt=True, nthreads=8)
+        assert np.array_equal(T, ref), row
+    assert ctx.norm_sq_dev(dS, R * N * 64) == int((S.astype(np.uint64) ** 2).sum())
+    ctx.free(dS); ctx.free(dT)
