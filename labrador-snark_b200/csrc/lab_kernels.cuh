@@ -29,6 +29,27 @@ constexpr int NTT_TPB = 128;
 
 __device__ __forceinline__ int swz(int p, int c) { return p * 16 + (c ^ (p & 7)); }
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+// asynchronous variant of stage_in: global -> shared without passing through registers, so the issuing thread can go on
+// computing; complete with cp_async_wait_all() + __syncthreads().  Out-of-range chunks are zero-filled synchronously.
+__device__ __forceinline__ void stage_in_async(uint4 *sm, const uint32_t *__restrict__ g, size_t base_poly, size_t n_polys, int tid) {
+    const uint4 *g4 = reinterpret_cast<const uint4 *>(g) + base_poly * 16;
+    const size_t avail = (n_polys - base_poly) * 16;
+#pragma unroll
+    for (int it = 0; it < 16; it++) {
+        int q = it * 128 + tid;
+        uint4 *dst = &sm[swz(q >> 4, q & 15)];
+        if ((size_t)q < avail) cp_async16(dst, g4 + q);
+        else *dst = make_uint4(0, 0, 0, 0);
+    }
+    cp_async_commit();
+}
+
 __device__ __forceinline__ void stage_in(uint4 *sm, const uint32_t *__restrict__ g, size_t base_poly, size_t n_polys, int tid) {
     // 128 polys * 16 chunks = 2048 chunks, 16 per thread, coalesced
     const uint4 *g4 = reinterpret_cast<const uint4 *>(g) + base_poly * 16;
@@ -79,9 +100,16 @@ __device__ __forceinline__ void store_slots(uint4 *sm, int p, const uint32_t (&r
     for (int c = 0; c < 16; c++) sm[swz(p, c)] = make_uint4(re[2 * c], im[2 * c], re[2 * c + 1], im[2 * c + 1]);
 }
 __device__ __forceinline__ void canon_in(uint32_t (&re)[32], uint32_t (&im)[32]) {
-    // API inputs are documented canonical; a fold keeps any u32 input well-defined (value mod Q)
+    // API inputs are documented canonical (< Q).  The generated transforms are bound-checked for 14-bit inputs, so
+    // canonical data passes untouched; if any value is larger (caller error, but still well defined: the value mod Q
+    // is what counts) this lane reduces its polynomial first.  The branch is uniform on valid data.
+    uint32_t any = 0;
 #pragma unroll
-    for (int j = 0; j < 32; j++) { re[j] = lab_fold(lab_fold(re[j])); im[j] = lab_fold(lab_fold(im[j])); }
+    for (int j = 0; j < 32; j++) any |= re[j] | im[j];
+    if (any >> 14) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) { re[j] = lab_fold(lab_fold(re[j])); im[j] = lab_fold(lab_fold(im[j])); }
+    }
 }
 
 __global__ void __launch_bounds__(NTT_TPB) k_ntt_fwd_regs(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t n_polys) {
@@ -118,34 +146,38 @@ __global__ void __launch_bounds__(NTT_TPB) k_ntt_inv_regs(const uint32_t *__rest
         __syncthreads();
     }
 }
-// c = a * b in R_q: two forward transforms, 32 slot products, one inverse -- &Rq * &Rq (algebraic.rs:517-523)
-__global__ void __launch_bounds__(NTT_TPB) k_polymul_regs(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
-                                                           uint32_t *__restrict__ c, size_t n_polys) {
+// c = a * b in R_q: two forward transforms, 32 slot products, one inverse -- &Rq * &Rq (algebraic.rs:517-523).
+// The transformed first operand waits in shared memory (packed, [slot][thread]: conflict free) while the second one is
+// transformed, which keeps the kernel at 4 CTAs per SM without spills.
+__global__ void __launch_bounds__(NTT_TPB, 4) k_polymul_regs(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
+                                                              uint32_t *__restrict__ c, size_t n_polys) {
     __shared__ uint4 sm[NTT_TPB * 16];
+    __shared__ uint32_t ahat[32][NTT_TPB];
     const int tid = threadIdx.x;
     for (size_t base = (size_t)blockIdx.x * NTT_TPB; base < n_polys; base += (size_t)gridDim.x * NTT_TPB) {
-        uint32_t re[32], im[32], pk[32];
-        stage_in(sm, a, base, n_polys, tid);
+        uint32_t re[32], im[32];
+        stage_in_async(sm, a, base, n_polys, tid);
+        cp_async_wait_all();
         __syncthreads();
         load_coeffs(sm, tid, re, im);
         __syncthreads();
-        stage_in(sm, b, base, n_polys, tid);     // overlaps with the first transform
+        stage_in_async(sm, b, base, n_polys, tid);   // lands while the first operand is transformed
         canon_in(re, im);
-        lab_ntt32_fwd_regs(re, im);
+        lab_ntt32_fwd_regs_lazy(re, im);             // < 2Q is enough for the slot products
 #pragma unroll
-        for (int j = 0; j < 32; j++) pk[j] = lab_pack(re[j], im[j]);
+        for (int j = 0; j < 32; j++) ahat[j][tid] = lab_pack(re[j], im[j]);
+        cp_async_wait_all();
         __syncthreads();
         load_coeffs(sm, tid, re, im);
         canon_in(re, im);
-        lab_ntt32_fwd_regs(re, im);
+        lab_ntt32_fwd_regs_lazy(re, im);
 #pragma unroll
         for (int j = 0; j < 32; j++) {
+            const uint32_t pk = ahat[j][tid];
             uint32_t r, i;
-            lab_cmul(lab_re(pk[j]), lab_im(pk[j]), re[j], im[j], r, i);
-            re[j] = r; im[j] = i;                // < 2Q, fine for the generated inverse (bound Q+8 <= 8199)
+            lab_cmul(lab_re(pk), lab_im(pk), re[j], im[j], r, i);
+            re[j] = r; im[j] = i;                // < 2Q, inside the generated inverse's input bound
         }
-#pragma unroll
-        for (int j = 0; j < 32; j++) { re[j] = lab_csub(re[j]); im[j] = lab_csub(im[j]); }
         lab_ntt32_inv_regs(re, im);
         __syncthreads();
         store_coeffs(sm, tid, re, im);

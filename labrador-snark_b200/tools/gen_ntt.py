@@ -77,8 +77,8 @@ class Emitter:
         self.bound[v] = Q - 1
 
 
-def cmul_const(E, dst_re, dst_im, a_re, a_im, c):
-    """(dst) = (a) * c, c = (cr, ci) canonical constants; result folded to < 2*Q."""
+def cmul_const(E, dst_re, dst_im, a_re, a_im, c, tfolds=2):
+    """(dst) = (a) * c, c = (cr, ci) canonical constants; result folded `tfolds` times (2 => < 2*Q)."""
     cr, ci = c
     nci = (Q - ci) % Q
     # make sure the product sums fit in 32 bits
@@ -95,8 +95,12 @@ def cmul_const(E, dst_re, dst_im, a_re, a_im, c):
     E.nmul += 4
     E.bound[dst_re] = worst_re
     E.bound[dst_im] = worst_im
-    E.fold_to(dst_re, 2 * Q - 1)
-    E.fold_to(dst_im, 2 * Q - 1)
+    if tfolds >= 2:
+        E.fold_to(dst_re, 2 * Q - 1)
+        E.fold_to(dst_im, 2 * Q - 1)
+    else:
+        E.fold(dst_re)
+        E.fold(dst_im)
 
 
 def kmult(bound):
@@ -104,21 +108,34 @@ def kmult(bound):
     return ((bound + Q - 1) // Q) * Q
 
 
-def gen_fwd(fwd):
+IN_BOUND = (1 << 14) - 1      # callers guarantee 14-bit inputs (canonical input passes as is; anything larger is folded twice first)
+
+
+def finish(E, lazy):
+    for j in range(32):
+        for v in (f"re[{j}]", f"im[{j}]"):
+            if lazy:
+                E.fold_to(v, 2 * Q - 1)      # < 2Q: good enough for lab_cmul operands and for packing into 16 bits
+            else:
+                E.canon(v)
+
+
+def gen_fwd(fwd, lazy=False, policy=(2, 2, 2, 2, 2)):
     E = Emitter()
     for j in range(32):
-        E.bound[f"re[{j}]"] = Q
-        E.bound[f"im[{j}]"] = Q
+        E.bound[f"re[{j}]"] = IN_BOUND
+        E.bound[f"im[{j}]"] = IN_BOUND
     E.emit("uint32_t tr, ti;")
     k = 1
     length = 16
+    stage = 0
     while length >= 1:
         for start in range(0, 32, 2 * length):
             c = fwd[k]
             k += 1
             for j in range(start, start + length):
                 lo_r, lo_i, hi_r, hi_i = f"re[{j}]", f"im[{j}]", f"re[{j+length}]", f"im[{j+length}]"
-                cmul_const(E, "tr", "ti", hi_r, hi_i, c)
+                cmul_const(E, "tr", "ti", hi_r, hi_i, c, policy[stage])
                 for lo, hi, t in ((lo_r, hi_r, "tr"), (lo_i, hi_i, "ti")):
                     K = kmult(E.bound[t])
                     bl = E.bound[lo]
@@ -128,19 +145,19 @@ def gen_fwd(fwd):
                     E.bound[hi] = bl + K
                     E.bound[lo] = bl + E.bound[t]
         length //= 2
-    for j in range(32):
-        E.canon(f"re[{j}]")
-        E.canon(f"im[{j}]")
+        stage += 1
+    finish(E, lazy)
     return E
 
 
-def gen_inv(inv):
+def gen_inv(inv, policy=(2, 2, 2, 2, 2)):
     E = Emitter()
     for j in range(32):
-        E.bound[f"re[{j}]"] = Q
-        E.bound[f"im[{j}]"] = Q
+        E.bound[f"re[{j}]"] = IN_BOUND
+        E.bound[f"im[{j}]"] = IN_BOUND
     E.emit("uint32_t ur, ui;")
     length = 1
+    stage = 0
     while length <= 16:
         k = 16 // length
         for start in range(0, 32, 2 * length):
@@ -159,8 +176,9 @@ def gen_inv(inv):
                     E.bound[u] = E.bound[lo] + K
                     E.emit(f"{lo} = {lo} + {hi};")
                     E.bound[lo] = E.bound[lo] + E.bound[hi]
-                cmul_const(E, hi_r, hi_i, "ur", "ui", c)
+                cmul_const(E, hi_r, hi_i, "ur", "ui", c, policy[stage])
         length *= 2
+        stage += 1
     for j in range(16):                        # the sum halves still need the 2^8 factor
         for v in (f"re[{j}]", f"im[{j}]"):
             E.fold_to(v, (1 << 24) - 1)
@@ -177,7 +195,21 @@ def main():
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc", "lab_ntt_gen.cuh")
     if len(sys.argv) > 1:
         out = sys.argv[1]
-    F, I = gen_fwd(fwd), gen_inv(inv)
+    import itertools
+
+    def best(fn, **kw):
+        cands = []
+        for pol in itertools.product((1, 2), repeat=5):
+            try:
+                e = fn(policy=pol, **kw)
+            except AssertionError:
+                continue
+            cands.append((e.nfold, pol, e))
+        cands.sort(key=lambda t: (t[0], t[1]))
+        return cands[0][2], cands[0][1]
+
+    (F, pf), (FL, pfl), (I, pi_) = best(lambda policy: gen_fwd(fwd, policy=policy)), best(lambda policy: gen_fwd(fwd, lazy=True, policy=policy)), best(lambda policy: gen_inv(inv, policy=policy))
+    print("fold policies (folds of the twiddle product per stage):", pf, pfl, pi_)
     pk = lambda c: c[0] | (c[1] << 16)
     with open(out, "w") as f:
         f.write("// GENERATED by tools/gen_ntt.py -- do not edit.  See that file for the math.\n")
@@ -188,11 +220,15 @@ def main():
         f.write("#define LAB_TW_INV_INIT {0u, " + ", ".join(f"{pk(inv[k])}u" for k in range(1, 32)) + "}\n")
         f.write("// slot j holds f(zeta^e_j)\n")
         f.write("#define LAB_SLOT_EXP_INIT {" + ", ".join(str(e) for e in slot) + "}\n\n")
-        f.write("// in: canonical-or-Q residues (<= 8191); out: canonical [0,Q)\n")
+        f.write(f"// in: residues <= {IN_BOUND} (14 bits); out: canonical [0,Q)\n")
         f.write("__device__ __forceinline__ void lab_ntt32_fwd_regs(uint32_t (&re)[32], uint32_t (&im)[32]) {\n")
         f.write("\n".join(F.lines))
         f.write("\n}\n\n")
-        f.write("// in: residues <= 8191 in slot order; out: canonical coefficients g_d = f_d + i f_{d+32}, scaled by 1/32\n")
+        f.write("// same, but outputs are only reduced to < 2Q (operands of lab_cmul / 16-bit packing)\n")
+        f.write("__device__ __forceinline__ void lab_ntt32_fwd_regs_lazy(uint32_t (&re)[32], uint32_t (&im)[32]) {\n")
+        f.write("\n".join(FL.lines))
+        f.write("\n}\n\n")
+        f.write(f"// in: residues <= {IN_BOUND} in slot order; out: canonical coefficients g_d = f_d + i f_{{d+32}}, scaled by 1/32\n")
         f.write("__device__ __forceinline__ void lab_ntt32_inv_regs(uint32_t (&re)[32], uint32_t (&im)[32]) {\n")
         f.write("\n".join(I.lines))
         f.write("\n}\n")

@@ -42,6 +42,22 @@ def test_polymul_edge_cases(ctx, orc):
     assert ctx.polymul_batch(np.zeros((0, D), np.uint32), np.zeros((0, D), np.uint32)).shape == (0, D)
 
 
+def test_noncanonical_inputs_are_reduced(ctx, orc):
+    """Inputs are documented canonical, but any u32 is still well defined (its value mod q): lanes that see a value of
+    more than 14 bits reduce first.  Mixed batches exercise both sides of that branch within one warp."""
+    rng = np.random.default_rng(7)
+    a = rng.integers(0, 2**32, size=(300, D), dtype=np.uint64).astype(np.uint32)
+    a[::3] = rand_polys(100, 31)                      # every third polynomial canonical
+    a[1, 5] = 8191; a[4, 0] = 16383; a[7, 63] = 16384
+    b = rand_polys(300, 32)
+    ar = (a.astype(np.uint64) % Q).astype(np.uint32)
+    assert np.array_equal(ctx.polymul_batch(a, b), orc.rq_mul_batch(ar, b))
+    assert np.array_equal(ctx.ntt_fwd_batch(a), np.stack([orc.ntt_fwd(p) for p in ar]))
+    f = ctx.ntt_fwd_batch(ar)
+    g = f + np.uint32(Q) * rng.integers(0, 4, size=f.shape, dtype=np.uint64).astype(np.uint32)   # same residues, non-canonical
+    assert np.array_equal(ctx.ntt_inv_batch(g), ar)
+
+
 def test_ntt_matches_oracle_and_roundtrips(ctx, orc):
     a = np.concatenate([rand_polys(300, 3), edge_polys()])
     f = ctx.ntt_fwd_batch(a)
