@@ -311,6 +311,20 @@ def main():
             for _ in range(5):
                 prover.proof_gen(st2, crs)
             extra["prove_default_N2_R2_ms"] = (time.perf_counter() - t0) / 5 * 1e3
+            tr2 = prover.proof_gen(st2, crs)
+            t0 = time.perf_counter()
+            okv = ctx.verify(c2, SEED32, st2.phi_k[0], st2.a_k[0], st2.b_k[0], ver.challenges, tr2.as_oracle_dict())
+            extra["verify_default_N2_R2_ms"] = (time.perf_counter() - t0) * 1e3
+            extra["verify_default_accepts"] = bool(okv[0])
+            # BASELINE config 5 flavour: independent default-size statements on this GPU (per-statement CRS seeds)
+            nb = 128
+            Sb = np.stack([S2] * nb); phib = np.stack([st2.phi_k[0]] * nb); ab_ = np.stack([st2.a_k[0]] * nb); bb = np.stack([st2.b_k[0]] * nb)
+            seeds = [bytes([i]) * 32 for i in range(nb)]
+            ctx.prove_batch(c2, seeds, False, Sb[:8], phib[:8], ab_[:8], bb[:8], [ver.challenges] * 8)
+            ctx.prove_batch(c2, seeds, False, Sb[:8], phib[:8], ab_[:8], bb[:8], [ver.challenges] * 8)
+            t0 = time.perf_counter()
+            ctx.prove_batch(c2, seeds, False, Sb, phib, ab_, bb, [ver.challenges] * nb)
+            extra["batch_default_proofs_per_s_per_gpu"] = nb / (time.perf_counter() - t0)
         except Exception as e:       # reported, never hidden
             extra["prove_default_error"] = repr(e)
 

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace lab;
@@ -42,6 +43,9 @@ struct lab_ctx {
     // (an H2D copy from pageable memory first synchronises the stream and would stall the enqueueing thread)
     struct MvPlan { std::vector<unsigned char> host; void *dev; };
     std::vector<MvPlan> mv_plans;
+    // worker contexts (own stream + arena each) for lab_prove_batch: independent statements overlap host-side
+    // enqueueing of one proof with the GPU work of the others
+    std::vector<lab_ctx *> workers;
 };
 
 #define CK(call)                                                                                     \
@@ -169,6 +173,7 @@ extern "C" void lab_ctx_destroy(lab_ctx *ctx) {
     if (ctx->What) cudaFree(ctx->What);
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
     for (auto &p : ctx->mv_plans) cudaFree(p.dev);
+    for (lab_ctx *w : ctx->workers) lab_ctx_destroy(w);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1034,12 +1039,31 @@ extern "C" int lab_verify(lab_ctx *ctx, const lab_constants *c, const uint8_t se
 extern "C" int lab_prove_batch(lab_ctx *ctx, const lab_constants *c, size_t n_statements, const uint8_t *seeds, int shared_crs, const uint32_t *S,
                                const lab_state *st, const lab_challenges *ch, lab_transcript *out) {
     TRY(check_consts(ctx, c, true));
+    if (!n_statements) return LAB_OK;
     const size_t wsz = c->R * c->N * 64;
-    (void)wsz;
-    for (size_t b = 0; b < n_statements; b++) {
-        CallScope cs(ctx);
-        const uint8_t *seed = shared_crs ? seeds : seeds + 32 * b;
-        TRY(prove_one(ctx, c, seed, S + b * wsz, &st[b], &ch[b], &out[b]));
+    const size_t nw = std::min<size_t>(n_statements, 4);
+    while (ctx->workers.size() < nw) {
+        lab_ctx *w = nullptr;
+        if (lab_ctx_create(ctx->device, &w) != LAB_OK) FAIL(LAB_ERR_CUDA, "cannot create batch worker context");
+        ctx->workers.push_back(w);
+    }
+    std::vector<int> status(nw, LAB_OK);
+    std::vector<std::thread> threads;
+    for (size_t t = 0; t < nw; t++)
+        threads.emplace_back([&, t]() {
+            lab_ctx *w = ctx->workers[t];
+            for (size_t b = t; b < n_statements; b += nw) {
+                CallScope cs(w);
+                const uint8_t *seed = shared_crs ? seeds : seeds + 32 * b;
+                int rc = prove_one(w, c, seed, S + b * wsz, &st[b], &ch[b], &out[b]);
+                if (rc != LAB_OK) { status[t] = rc; return; }
+            }
+        });
+    for (auto &th : threads) th.join();
+    for (size_t t = 0; t < nw; t++) {
+        ctx->launches += ctx->workers[t]->launches;
+        ctx->workers[t]->launches = 0;
+        if (status[t] != LAB_OK) { ctx->err = "statement failed in batch worker: " + ctx->workers[t]->err; return status[t]; }
     }
     return LAB_OK;
 }

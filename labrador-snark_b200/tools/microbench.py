@@ -100,6 +100,22 @@ def main():
             dv = time.perf_counter() - t0
             print(json.dumps({"kernel": "prove", "N": N, "R": R, "ms_per_proof": dt * 1e3, "launches_per_proof": launches, "u1_stage_ms": du1 * 1e3,
                               "chacha_blocks": blocks, "blocks_per_s_whole_proof": blocks / dt, "verify_ms": dv * 1e3, "verify_ok": ok[0]}), flush=True)
+    if "batch" in which:        # BASELINE config 5 shape: independent default-size statements, one GPU
+        import time
+        N, R, B = 2, 2, 256
+        c = lb.RuntimeConstants.new(N, R)
+        S0 = synth.generate_witness(N, R, c.BETA_BOUND, synth.SEED)
+        st0 = lb.State.new(S0, c, synth.SEED, ctx)
+        ch0 = synth.sample_challenges(N, R, synth.SEED, 6)
+        S = np.stack([S0] * B); phi = np.stack([st0.phi_k[0]] * B); a = np.stack([st0.a_k[0]] * B); b = np.stack([st0.b_k[0]] * B)
+        seeds = [bytes([i % 256]) * 32 for i in range(B)]
+        for shared in (False, True):
+            ctx.prove_batch(c, seeds, shared, S[:8], phi[:8], a[:8], b[:8], [ch0] * 8)
+            ctx.prove_batch(c, seeds, shared, S[:8], phi[:8], a[:8], b[:8], [ch0] * 8)
+            t0 = time.perf_counter()
+            ctx.prove_batch(c, seeds, shared, S, phi, a, b, [ch0] * B)
+            dt = time.perf_counter() - t0
+            print(json.dumps({"kernel": "prove_batch", "N": N, "R": R, "statements": B, "shared_crs": shared, "proofs_per_s": B / dt, "ms_per_proof": dt / B * 1e3}), flush=True)
     if "commit" in which:
         for (N, R, rows) in ((256, 2, 148 * 4 * 8), (256, 8, 148 * 4 * 8), (256, 32, 148 * 4 * 8), (256, 64, 148 * 4 * 8), (4096, 64, 148 * 4 * 4)):
             c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
