@@ -336,15 +336,9 @@ def main():
         hS = pin((R, N, D), torch.int32); hS.copy_(S.cpu())
         hT = pin((R, max(nrows, 1), D), torch.int32)
         hch = pin((R, D), torch.int32); hch.copy_(ch.cpu())
-        do_small = rank == 0           # the ~1% stages run on rank 0 (their host API has no shard arguments)
-        if do_small:
-            hPi = pin((R, JL, ND), torch.int8)
-            if world == 1:
-                hPi.copy_(Pi.cpu())
-            else:
-                tmp = torch.empty((R, JL, ND), dtype=torch.int8, device=dev)
-                ctx.synth_pi_dev(PRG_SEED, 0, 0, R * JL * ND, tmp.data_ptr()); ctx.sync()
-                hPi.copy_(tmp.cpu()); del tmp
+        do_small = rank == 0           # g and z (~0.1% of the step) run on rank 0: their host API has no shard arguments
+        hPi = pin((max(ni, 1), JL, ND), torch.int8)      # JL is sharded by witness vector like the device path
+        hPi.copy_(Pi.cpu())
         S_np, T_np, ch_np = hS.numpy().view(np.uint32), hT.numpy().view(np.uint32), hch.numpy().view(np.uint32)
         import ctypes as C
         L, h = ctx.L, ctx._h
@@ -354,10 +348,13 @@ def main():
 
         def e2e_step():
             ctx._ck(L.lab_commit_inner(h, C.byref(c), seedbuf.ctypes.data_as(C.c_void_p), vp(hS), C.c_uint64(row0), C.c_uint64(nrows), vp(hT)))
+            ctx._ck(L.lab_jl_project_part(h, C.byref(c), vp(hS), vp(hPi), C.c_uint64(i0), C.c_uint64(ni), vp(hp)))
+            if world > 1:
+                pd = hp.to(dev, non_blocking=True)
+                dist.all_reduce(pd)                                   # int64 partial sums over NVLink
+                hp.copy_(pd)
             if do_small:
-                acc = C.c_int(0)
                 ctx._ck(L.lab_gram(h, C.byref(c), vp(hS), vp(hG)))
-                ctx._ck(L.lab_jl_project(h, C.byref(c), vp(hS), vp(hPi), vp(hp), C.byref(acc)))
                 ctx._ck(L.lab_amortize_z(h, C.byref(c), vp(hS), vp(hch), vp(hz)))
         e2e_step()
         barrier()
@@ -373,14 +370,16 @@ def main():
         if world > 1:
             dist.all_reduce(et, op=dist.ReduceOp.MAX)
         s_bytes = R * N * D * 4
-        h2d = s_bytes + (3 * s_bytes + R * JL * ND + R * D * 4 if do_small else 0)
-        d2h = R * nrows * D * 4 + (R * R * D * 4 + JL * 8 + N * D * 4 if do_small else 0)
+        h2d = s_bytes + ni * ND * 4 + ni * JL * ND + (2 * s_bytes + R * D * 4 if do_small else 0)
+        d2h = R * nrows * D * 4 + JL * 8 + (R * R * D * 4 + N * D * 4 if do_small else 0)
         e2e = {"value": N * R * D / (float(et.item()) * 1e-3), "unit": "coeffs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": float(et.item()), "steps": nst,
-               "note": "lab_commit_inner + lab_gram + lab_jl_project + lab_amortize_z with pinned HOST buffers; byte counts are rank 0's"}
+               "note": "lab_commit_inner (row shard) + lab_jl_project_part (vector shard, int64 all-reduce) + lab_gram + lab_amortize_z (rank 0) with pinned HOST buffers; byte counts are rank 0's"}
         # the host path and the device-resident path must agree bit for bit
         if not np.array_equal(T_np[:, :nrows], T.cpu().numpy().view(np.uint32)[:, :nrows]):
             raise SystemExit("e2e host path and device-resident path disagree on T")
+        if not np.array_equal(hp.numpy(), out["p"].cpu().numpy()):
+            raise SystemExit("e2e host path and device-resident path disagree on the JL projection")
 
     # ---- CPU baseline (rank 0, N = 1) ----
     cpu = None

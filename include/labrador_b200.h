@@ -123,6 +123,10 @@ int lab_gram(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, uint32_t *
 /* S4 one JL attempt: p = sum_i Pi_i * coeffs(s_i) exact (proofgen.rs:429-457; util.rs:511-526).
  * pi: int8[R][256][N*64] in {-1,0,1}.  accepted receives Verifier::valid_projection (verification.rs:568-579). */
 int lab_jl_project(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, const int8_t *pi, int64_t p[LAB_JL_ROWS], int *accepted);
+/* the same for the witness vectors i in [i0,i0+ni) only: pi_part is int8[ni][256][N*64] (rows of Pi for those vectors),
+ * p_partial the exact partial sums -- the per-rank piece of the int64 all-reduce when S4 is sharded by i */
+int lab_jl_project_part(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, const int8_t *pi_part, uint64_t i0, uint64_t ni,
+                        int64_t p_partial[LAB_JL_ROWS]);
 /* S3 u_1 = sum B_ik dig_k(t_i) + sum_{i<=j} dig_k(g_ij) C_ijk (proofgen.rs:101-153) */
 int lab_commit_outer_u1(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], const uint32_t *T, const uint32_t *G, uint32_t *u1);
 /* S8 u_2 = sum_{i<=j,k<T_1} dig_k(h_ij) D_ijk (proofgen.rs:364-378) */

@@ -623,6 +623,25 @@ extern "C" int lab_jl_project(lab_ctx *ctx, const lab_constants *c, const uint32
     if (accepted) *accepted = valid_projection(c, p) ? 1 : 0;
     return LAB_OK;
 }
+extern "C" int lab_jl_project_part(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, const int8_t *pi_part, uint64_t i0, uint64_t ni,
+                                   int64_t p_partial[LAB_JL_ROWS]) {
+    CallScope cs(ctx);
+    TRY(check_consts(ctx, c, false));
+    if (i0 + ni > c->R) FAIL(LAB_ERR_SHAPE, "witness range exceeds R");
+    const uint64_t ND = c->N * LAB_D;
+    uint32_t *dS = nullptr;
+    int8_t *dPi = nullptr;
+    unsigned long long *dp;
+    TRY(arena_alloc(ctx, LAB_JL_ROWS, &dp));
+    if (ni) {
+        // only the witness vectors of this part travel: device buffer indexed from i0
+        TRY(upload(ctx, S + i0 * ND, ni * ND, &dS));
+        TRY(upload(ctx, pi_part, ni * LAB_JL_ROWS * ND, &dPi));
+    }
+    TRY(d_jl(ctx, dPi, dS, ND, 0, ni, dp));
+    CK(cudaMemcpyAsync(p_partial, dp, LAB_JL_ROWS * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    return lab_sync(ctx);
+}
 extern "C" int lab_commit_outer_u1(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], const uint32_t *T, const uint32_t *G, uint32_t *u1) {
     CallScope cs(ctx);
     TRY(check_consts(ctx, c, true));

@@ -57,7 +57,7 @@ SYMBOLS = [
     "lab_ntt_fwd_batch_dev", "lab_ntt_inv_batch_dev", "lab_polymul_batch_dev", "lab_ntt_slot_exponents",
     "lab_inner_product_batch", "lab_decompose", "lab_norm_sq", "lab_norm_sq_dev", "lab_sigma_inv",
     "lab_crs_expand", "lab_crs_expand_dev", "lab_crs_fetch", "lab_crs_offset",
-    "lab_commit_inner", "lab_gram", "lab_jl_project", "lab_commit_outer_u1", "lab_commit_outer_u2",
+    "lab_commit_inner", "lab_gram", "lab_jl_project", "lab_jl_project_part", "lab_commit_outer_u1", "lab_commit_outer_u2",
     "lab_aggregate_phi", "lab_h_gram", "lab_amortize_z", "lab_prove", "lab_prove_batch", "lab_verify",
     "lab_witness_load_dev", "lab_commit_inner_dev", "lab_gram_dev", "lab_jl_project_dev", "lab_amortize_z_dev",
     "lab_synth_zq_dev", "lab_synth_pi_dev", "lab_bench_alu_peak",

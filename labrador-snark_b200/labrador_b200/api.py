@@ -227,6 +227,13 @@ class Context:
         self._ck(self.L.lab_jl_project(self._h, C.byref(c), _p(S), _p(pi), _p(p), C.byref(acc)))
         return p, bool(acc.value)
 
+    def jl_project_part(self, c, S, pi_part, i0, ni):
+        S = _u32(S)
+        pi_part = np.ascontiguousarray(pi_part, dtype=np.int8)
+        p = np.empty(JL_ROWS, np.int64)
+        self._ck(self.L.lab_jl_project_part(self._h, C.byref(c), _p(S), _p(pi_part), C.c_uint64(i0), C.c_uint64(ni), _p(p)))
+        return p
+
     def commit_outer_u1(self, c, seed, T, G):
         T, G = _u32(T), _u32(G)
         u1 = np.empty((c.KAPPA_1, D), np.uint32)

@@ -177,6 +177,10 @@ def test_gram_z_jl(ctx, orc, N, R):
     p, acc = ctx.jl_project(c, S, pi)
     assert np.array_equal(p, orc.jl_project(co, S, pi))
     assert acc == orc.valid_projection(co, p)
+    # sharded by witness vector: the partial sums add up exactly (the multi-GPU combine)
+    h = R // 2
+    parts = ctx.jl_project_part(c, S, pi[:h], 0, h) + ctx.jl_project_part(c, S, pi[h:], h, R - h)
+    assert np.array_equal(parts, p)
 
 
 def full_case(orc, N, R, seed, n_attempts=2):
