@@ -124,7 +124,8 @@ static LabSeed make_seed(const uint8_t seed[32]) {
         s.limb[l] = v;
     }
     s.one = 1u;
-    s.pad = 0u;
+    s.p16 = 1u << 16; s.p12 = 1u << 12; s.p8 = 1u << 8; s.p7 = 1u << 7;
+    s.pad[0] = s.pad[1] = s.pad[2] = 0u;
     return s;
 }
 static unsigned grid_for(size_t work_items, unsigned per_block, unsigned cap) {
@@ -298,11 +299,11 @@ static int d_commit_inner(lab_ctx *ctx, const LabSeed &seed, const uint32_t *Wha
     const int IC = R > 32 ? 16 : (R > 16 ? 8 : (R > 8 ? 4 : (R > 4 ? 2 : 1)));
     for (uint64_t ib = 0; ib < R; ib += (uint64_t)KA_CONS * IC) {
         switch (IC) {
-            case 16: LAUNCH(k_commit_inner<16>, grid, KA_THREADS, seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
-            case 8: LAUNCH(k_commit_inner<8>, grid, KA_THREADS, seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
-            case 4: LAUNCH(k_commit_inner<4>, grid, KA_THREADS, seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
-            case 2: LAUNCH(k_commit_inner<2>, grid, KA_THREADS, seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
-            default: LAUNCH(k_commit_inner<1>, grid, KA_THREADS, seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
+            case 16: LAUNCH((k_commit_inner<16, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
+            case 8: LAUNCH((k_commit_inner<8, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
+            case 4: LAUNCH((k_commit_inner<4, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
+            case 2: LAUNCH((k_commit_inner<2, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
+            default: LAUNCH((k_commit_inner<1, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
         }
     }
     return LAB_OK;
@@ -552,7 +553,7 @@ extern "C" int lab_sigma_inv(lab_ctx *ctx, const uint32_t *in, size_t n_polys, u
 extern "C" int lab_crs_expand_dev(lab_ctx *ctx, const uint8_t seed[32], uint64_t start_lo, uint64_t start_hi, size_t n_polys, uint32_t *out) {
     if (!n_polys) return LAB_OK;
     const size_t nc = n_polys * 64;
-    LAUNCH(k_crs_expand, grid_for(nc, 512, ctx->sms * 16), 256, make_seed(seed), start_lo, start_hi, nc, out);
+    LAUNCH(k_crs_expand<LAB_RM_EXPAND>, grid_for(nc, 512, ctx->sms * 16), 256, make_seed(seed), start_lo, start_hi, nc, out);
     return LAB_OK;
 }
 extern "C" int lab_crs_expand(lab_ctx *ctx, const uint8_t seed[32], uint64_t start_lo, uint64_t start_hi, size_t n_polys, uint32_t *out) {

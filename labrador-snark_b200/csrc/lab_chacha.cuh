@@ -5,20 +5,83 @@
 // (4 little-endian u32 words, low first), (hi, lo) = v * Q as 256 bits, accept iff lo <= (Q << 115) - 1,
 // i.e. iff the top 13 bits of lo are not all ones; return hi.  Rejected draws (probability 2^-13)
 // continue with the next 128 keystream bits.
+//
+// One ChaCha20 block per 13-bit coefficient makes every CRS-regenerating kernel INT32-bound, so the block function is
+// trimmed to what the result depends on:
+//   * only key word 7 (the byte-swapped low 32 bits of seed + counter) differs between neighbouring coefficients, so the
+//     part of the first double round that does not depend on it is computed once per 2^32 counters (LabHoist);
+//   * only keystream words 0..3 of block 0 are consumed, so the last diagonal round stops at the second `a` update;
+//   * xor and rotate exist only on the ALU pipe; the additions are written b * one + a (IMAD, FMA pipe) and a
+//     compile-time mask moves selected rotations to the FMA pipe as rotl(x, n) = hi32(x * 2^n) + lo32(x * 2^n)
+//     (IMAD + IMAD.HI) until both pipes carry the same load.
 #pragma once
 #include "lab_field.cuh"
 
 struct LabSeed {
     uint64_t limb[4];   // the 256-bit big-endian base seed as an integer, limb[0] least significant
     uint32_t one;       // always 1, but only known at run time (kernel parameter / constant bank): a + b is written
-                        // b * one + a so that ChaCha20's 320 additions per block issue as IMAD on the FMA pipe instead of
+                        // b * one + a so that ChaCha20's additions issue as IMAD on the FMA pipe instead of
                         // IADD3 on the ALU pipe, which the xors and rotates already saturate
-    uint32_t pad;
+    uint32_t p16, p12, p8, p7;   // 2^16, 2^12, 2^8, 2^7, run-time for the same reason (FMA-pipe rotations)
+    uint32_t pad[3];
 };
 
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t lab_bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
 __device__ __forceinline__ uint32_t lab_rotl(uint32_t x, int n) { return __funnelshift_l(x, x, n); }
+// x + y on the FMA pipe
+#ifdef LAB_NATIVE_ADD
+__device__ __forceinline__ uint32_t lab_addf(uint32_t x, uint32_t y, uint32_t) { return x + y; }
+#else
+__device__ __forceinline__ uint32_t lab_addf(uint32_t x, uint32_t y, uint32_t one) { return y * one + x; }
+#endif
+// rotl on the FMA pipe: pw == 2^n at run time
+__device__ __forceinline__ uint32_t lab_rotl_fma(uint32_t x, uint32_t pw) {
+    uint32_t lo = x * pw, r;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(pw), "r"(lo));
+    return r;
+}
+template <int N, bool FMA>
+__device__ __forceinline__ uint32_t lab_rot(uint32_t x, const LabSeed &s) {
+    if (FMA) return lab_rotl_fma(x, N == 16 ? s.p16 : (N == 12 ? s.p12 : (N == 8 ? s.p8 : s.p7)));
+    return lab_rotl(x, N);
+}
+
+// quarter round; M = 4-bit mask, bit j set -> rotation j (16, 12, 8, 7) runs on the FMA pipe
+template <uint32_t M>
+__device__ __forceinline__ void lab_qr(uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d, const LabSeed &s) {
+    a = lab_addf(a, b, s.one); d = lab_rot<16, (M & 1u) != 0>(d ^ a, s);
+    c = lab_addf(c, d, s.one); b = lab_rot<12, (M & 2u) != 0>(b ^ c, s);
+    a = lab_addf(a, b, s.one); d = lab_rot<8, (M & 4u) != 0>(d ^ a, s);
+    c = lab_addf(c, d, s.one); b = lab_rot<7, (M & 8u) != 0>(b ^ c, s);
+}
+// the same, stopping once `a` is final (last diagonal round: only x0..x3 are consumed)
+template <uint32_t M>
+__device__ __forceinline__ void lab_qr_a_only(uint32_t &a, uint32_t b, uint32_t c, uint32_t d, const LabSeed &s) {
+    a = lab_addf(a, b, s.one); d = lab_rot<16, (M & 1u) != 0>(d ^ a, s);
+    c = lab_addf(c, d, s.one); b = lab_rot<12, (M & 2u) != 0>(b ^ c, s);
+    a = lab_addf(a, b, s.one);
+}
+
+// one double round on NB interleaved states; RM = 32-bit mask, nibble q = lab_qr mask of quarter round q
+// (0..3 column, 4..7 diagonal)
+template <int NB, uint32_t RM>
+__device__ __forceinline__ void lab_double_round(uint32_t (&x)[NB][16], const LabSeed &s) {
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        lab_qr<(RM >> 0) & 15u>(x[b][0], x[b][4], x[b][8], x[b][12], s);
+        lab_qr<(RM >> 4) & 15u>(x[b][1], x[b][5], x[b][9], x[b][13], s);
+        lab_qr<(RM >> 8) & 15u>(x[b][2], x[b][6], x[b][10], x[b][14], s);
+        lab_qr<(RM >> 12) & 15u>(x[b][3], x[b][7], x[b][11], x[b][15], s);
+    }
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        lab_qr<(RM >> 16) & 15u>(x[b][0], x[b][5], x[b][10], x[b][15], s);
+        lab_qr<(RM >> 20) & 15u>(x[b][1], x[b][6], x[b][11], x[b][12], s);
+        lab_qr<(RM >> 24) & 15u>(x[b][2], x[b][7], x[b][8], x[b][13], s);
+        lab_qr<(RM >> 28) & 15u>(x[b][3], x[b][4], x[b][9], x[b][14], s);
+    }
+}
 
 // key words of ChaCha20Rng::from_seed(be_bytes(base + (chi:clo))) -- the counter's low 32 bits land
 // byte-swapped in key word 7 (structs.rs:59-68,155-165; rand_chacha reads the seed as LE u32s)
@@ -42,34 +105,125 @@ __device__ __forceinline__ void lab_key_from_counter(const LabSeed &s, uint64_t 
     key[7] = lab_bswap32((uint32_t)s0);
 }
 
-#define LAB_QR(a, b, c, d)                                                                       \
-    a = b * one + a; d ^= a; d = lab_rotl(d, 16); c = d * one + c; b ^= c; b = lab_rotl(b, 12);  \
-    a = b * one + a; d ^= a; d = lab_rotl(d, 8);  c = d * one + c; b ^= c; b = lab_rotl(b, 7);
+constexpr uint32_t LAB_CC0 = 0x61707865u, LAB_CC1 = 0x3320646eu, LAB_CC2 = 0x79622d32u, LAB_CC3 = 0x6b206574u;
 
-// the 10 double rounds on NB independent states (interleaved for ILP); `one` == 1 (see LabSeed)
-template <int NB>
-__device__ __forceinline__ void lab_chacha_rounds(uint32_t (&x)[NB][16], const uint32_t one) {
+// The part of the first double round that is the same for all counters sharing everything but the low 32 bits of
+// seed + counter (i.e. key words 0..6).  State after the first column round: columns 0..2 complete (A*), column 3 =
+// QR(c3, k3, k7, 0) starts with P0 = c3 + k3 and P1 = rotl(P0, 16); the diagonal round then starts from
+// Q0 = A0 + A5, Q1 = A1 + A6, Q2 = rotl(A12 ^ Q1, 16).
+struct LabHoist {
+    uint64_t tag_lo, tag_hi;   // (carry out of the low limb : high 32 bits of the low limb), counter high limb
+    uint32_t k3, P0, P1;
+    uint32_t Q0, A5, A10;
+    uint32_t Q1, Q2, A6;
+    uint32_t A2, A8, A13;
+    uint32_t A4, A9, A14;
+};
+__device__ __forceinline__ void lab_hoist_invalidate(LabHoist &h) { h.tag_lo = ~0ull; h.tag_hi = ~0ull; }
+
+// recompute for the 256-bit sum seed + (chi:clo): runs once per 2^32 counters
+__device__ __forceinline__ void lab_hoist_compute(const LabSeed &seed, uint64_t clo, uint64_t chi, LabHoist &h) {
+    uint32_t key[8];
+    lab_key_from_counter(seed, clo, chi, key);
+    const uint64_t s0 = seed.limb[0] + clo;
+    h.tag_lo = ((uint64_t)(s0 < clo) << 32) | (s0 >> 32);
+    h.tag_hi = chi;
+    uint32_t a0 = LAB_CC0, a4 = key[0], a8 = key[4], a12 = 0u;
+    uint32_t a1 = LAB_CC1, a5 = key[1], a9 = key[5], a13 = 0u;
+    uint32_t a2 = LAB_CC2, a6 = key[2], a10 = key[6], a14 = 0u;
+    lab_qr<0>(a0, a4, a8, a12, seed);
+    lab_qr<0>(a1, a5, a9, a13, seed);
+    lab_qr<0>(a2, a6, a10, a14, seed);
+    h.k3 = key[3];
+    h.P0 = LAB_CC3 + key[3];
+    h.P1 = lab_rotl(h.P0, 16);
+    h.Q0 = a0 + a5; h.A5 = a5; h.A10 = a10;
+    h.Q1 = a1 + a6; h.Q2 = lab_rotl(a12 ^ h.Q1, 16); h.A6 = a6;
+    h.A2 = a2; h.A8 = a8; h.A13 = a13;
+    h.A4 = a4; h.A9 = a9; h.A14 = a14;
+}
+// make h valid for counters (chi:clo) + [0, 2^32 - low32(seed + clo))
+__device__ __forceinline__ void lab_hoist_update(const LabSeed &seed, uint64_t clo, uint64_t chi, LabHoist &h) {
+    const uint64_t s0 = seed.limb[0] + clo;
+    const uint64_t tag = ((uint64_t)(s0 < clo) << 32) | (s0 >> 32);
+    if (tag != h.tag_lo || chi != h.tag_hi) lab_hoist_compute(seed, clo, chi, h);
+}
+
+// keystream words 0..3 of block 0 for NB keys that share h and differ in key word 7
+template <int NB, uint32_t RM>
+__device__ __forceinline__ void lab_chacha_w03(const LabSeed &s, const LabHoist &h, const uint32_t (&k7)[NB], uint32_t (&w)[NB][4]) {
+    uint32_t x[NB][16];
+    const uint32_t one = s.one;
+    // ---- first double round, hoisted ----
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        // column 3: QR(c3, k3, k7, 0) from its third operation on
+        uint32_t c = lab_addf(k7[b], h.P1, one);
+        uint32_t bb = lab_rot<12, ((RM >> 12) & 2u) != 0>(h.k3 ^ c, s);
+        uint32_t a = lab_addf(h.P0, bb, one);
+        uint32_t d = lab_rot<8, ((RM >> 12) & 4u) != 0>(h.P1 ^ a, s);
+        c = lab_addf(c, d, one);
+        bb = lab_rot<7, ((RM >> 12) & 8u) != 0>(bb ^ c, s);
+        x[b][3] = a; x[b][7] = bb; x[b][11] = c; x[b][15] = d;
+    }
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        {   // diagonal 0: (A0, A5, A10, x15), a + b = Q0 known
+            uint32_t d = lab_rot<16, ((RM >> 16) & 1u) != 0>(x[b][15] ^ h.Q0, s);
+            uint32_t c = lab_addf(h.A10, d, one);
+            uint32_t bb = lab_rot<12, ((RM >> 16) & 2u) != 0>(h.A5 ^ c, s);
+            uint32_t a = lab_addf(h.Q0, bb, one);
+            d = lab_rot<8, ((RM >> 16) & 4u) != 0>(d ^ a, s);
+            c = lab_addf(c, d, one);
+            bb = lab_rot<7, ((RM >> 16) & 8u) != 0>(bb ^ c, s);
+            x[b][0] = a; x[b][5] = bb; x[b][10] = c; x[b][15] = d;
+        }
+        {   // diagonal 1: (A1, A6, x11, A12), a = Q1 and d = Q2 known
+            uint32_t c = lab_addf(x[b][11], h.Q2, one);
+            uint32_t bb = lab_rot<12, ((RM >> 20) & 2u) != 0>(h.A6 ^ c, s);
+            uint32_t a = lab_addf(h.Q1, bb, one);
+            uint32_t d = lab_rot<8, ((RM >> 20) & 4u) != 0>(h.Q2 ^ a, s);
+            c = lab_addf(c, d, one);
+            bb = lab_rot<7, ((RM >> 20) & 8u) != 0>(bb ^ c, s);
+            x[b][1] = a; x[b][6] = bb; x[b][11] = c; x[b][12] = d;
+        }
+        x[b][2] = h.A2; x[b][8] = h.A8; x[b][13] = h.A13;
+        lab_qr<(RM >> 24) & 15u>(x[b][2], x[b][7], x[b][8], x[b][13], s);
+        x[b][4] = h.A4; x[b][9] = h.A9; x[b][14] = h.A14;
+        lab_qr<(RM >> 28) & 15u>(x[b][3], x[b][4], x[b][9], x[b][14], s);
+    }
+    // ---- double rounds 2..9 ----
 #pragma unroll 1
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < 8; r++) lab_double_round<NB, RM>(x, s);
+    // ---- double round 10: full column round, diagonal round only as far as x0..x3 need ----
 #pragma unroll
-        for (int b = 0; b < NB; b++) {
-            LAB_QR(x[b][0], x[b][4], x[b][8], x[b][12])
-            LAB_QR(x[b][1], x[b][5], x[b][9], x[b][13])
-            LAB_QR(x[b][2], x[b][6], x[b][10], x[b][14])
-            LAB_QR(x[b][3], x[b][7], x[b][11], x[b][15])
-        }
+    for (int b = 0; b < NB; b++) {
+        lab_qr<(RM >> 0) & 15u>(x[b][0], x[b][4], x[b][8], x[b][12], s);
+        lab_qr<(RM >> 4) & 15u>(x[b][1], x[b][5], x[b][9], x[b][13], s);
+        lab_qr<(RM >> 8) & 15u>(x[b][2], x[b][6], x[b][10], x[b][14], s);
+        lab_qr<(RM >> 12) & 15u>(x[b][3], x[b][7], x[b][11], x[b][15], s);
+    }
 #pragma unroll
-        for (int b = 0; b < NB; b++) {
-            LAB_QR(x[b][0], x[b][5], x[b][10], x[b][15])
-            LAB_QR(x[b][1], x[b][6], x[b][11], x[b][12])
-            LAB_QR(x[b][2], x[b][7], x[b][8], x[b][13])
-            LAB_QR(x[b][3], x[b][4], x[b][9], x[b][14])
-        }
+    for (int b = 0; b < NB; b++) {
+        lab_qr_a_only<(RM >> 16) & 15u>(x[b][0], x[b][5], x[b][10], x[b][15], s);
+        lab_qr_a_only<(RM >> 20) & 15u>(x[b][1], x[b][6], x[b][11], x[b][12], s);
+        lab_qr_a_only<(RM >> 24) & 15u>(x[b][2], x[b][7], x[b][8], x[b][13], s);
+        lab_qr_a_only<(RM >> 28) & 15u>(x[b][3], x[b][4], x[b][9], x[b][14], s);
+        w[b][0] = lab_addf(x[b][0], LAB_CC0, one);
+        w[b][1] = lab_addf(x[b][1], LAB_CC1, one);
+        w[b][2] = lab_addf(x[b][2], LAB_CC2, one);
+        w[b][3] = lab_addf(x[b][3], LAB_CC3, one);
     }
 }
 
+// the 10 double rounds on one full state (generic path: any block index, all 16 words)
+__device__ __forceinline__ void lab_chacha_rounds1(uint32_t (&x)[1][16], const LabSeed &s) {
+#pragma unroll 1
+    for (int r = 0; r < 10; r++) lab_double_round<1, 0u>(x, s);
+}
+
 __device__ __forceinline__ void lab_chacha_init(uint32_t (&x)[16], const uint32_t (&key)[8], uint64_t block) {
-    x[0] = 0x61707865u; x[1] = 0x3320646eu; x[2] = 0x79622d32u; x[3] = 0x6b206574u;
+    x[0] = LAB_CC0; x[1] = LAB_CC1; x[2] = LAB_CC2; x[3] = LAB_CC3;
 #pragma unroll
     for (int i = 0; i < 8; i++) x[4 + i] = key[i];
     x[12] = (uint32_t)block; x[13] = (uint32_t)(block >> 32);
@@ -83,11 +237,12 @@ __device__ __forceinline__ bool lab_sample_u128(uint32_t w0, uint32_t w1, uint32
     t = (uint64_t)w2 * LABQ + (t >> 32);
     t = (uint64_t)w3 * LABQ + (t >> 32);
     out = (uint32_t)(t >> 32);
-    return (((uint32_t)t) >> 19) != 0x1FFFu;
+    return ((uint32_t)t) < 0xFFF80000u;      // top 13 bits of the low half not all ones
 }
 
-// slow path after `first_attempt` rejected draws: full blocks, any number of further attempts
-__device__ __noinline__ uint32_t lab_crs_coeff_slow(const LabSeed &seed, uint64_t clo, uint64_t chi, uint32_t first_attempt) {
+// generic path: any counter, any number of rejected draws (`first_attempt` of them already known to be rejected).
+// Also the independent cross-check of the trimmed fast path: tests compare both on the same counters.
+__device__ __forceinline__ uint32_t lab_crs_coeff_generic(const LabSeed &seed, uint64_t clo, uint64_t chi, uint32_t first_attempt) {
     uint32_t key[8];
     lab_key_from_counter(seed, clo, chi, key);
     for (uint32_t a = first_attempt;; a++) {
@@ -95,7 +250,7 @@ __device__ __noinline__ uint32_t lab_crs_coeff_slow(const LabSeed &seed, uint64_
         lab_chacha_init(x[0], key, (uint64_t)(a >> 2));
 #pragma unroll
         for (int i = 0; i < 16; i++) init[i] = x[0][i];
-        lab_chacha_rounds<1>(x, seed.one);
+        lab_chacha_rounds1(x, seed);
         uint32_t w[4];
 #pragma unroll
         for (int i = 0; i < 16; i++) {
@@ -107,52 +262,33 @@ __device__ __noinline__ uint32_t lab_crs_coeff_slow(const LabSeed &seed, uint64_
     }
 }
 
-// NB coefficients at counters (chi:clo) + off[b]; only keystream words 0..3 of block 0 are finished
-// on the fast path (the compiler drops the dead tail of the last round).
-// Key setup: the 256-bit sum seed + (chi:clo) and the byte swaps of its upper six key words are done once for all NB
-// blocks; a block only adds its small offset to the low 64-bit limb and swaps two words.  If that addition carries out
-// of the low limb (possible only for seeds whose low limb is within `off` of 2^64) the block is recomputed by the
-// generic slow path, which also handles rejected draws.
-template <int NB>
-__device__ __forceinline__ void lab_crs_coeffs(const LabSeed &seed, uint64_t clo, uint64_t chi, const uint32_t (&off)[NB], uint32_t (&out)[NB]) {
-    const uint64_t s0 = seed.limb[0] + clo;
-    const uint64_t c0 = s0 < clo;
-    uint64_t s1 = seed.limb[1] + chi;
-    uint64_t c1 = s1 < chi;
-    s1 += c0;
-    c1 += (s1 < c0);
-    const uint64_t s2 = seed.limb[2] + c1;
-    const uint64_t c2 = s2 < c1;
-    const uint64_t s3 = seed.limb[3] + c2;
-    uint32_t khi[6];
-    khi[0] = lab_bswap32((uint32_t)(s3 >> 32));
-    khi[1] = lab_bswap32((uint32_t)s3);
-    khi[2] = lab_bswap32((uint32_t)(s2 >> 32));
-    khi[3] = lab_bswap32((uint32_t)s2);
-    khi[4] = lab_bswap32((uint32_t)(s1 >> 32));
-    khi[5] = lab_bswap32((uint32_t)s1);
-    uint32_t x[NB][16];
-    bool carry[NB];
+__device__ __noinline__ uint32_t lab_crs_coeff_slow(const LabSeed &seed, uint64_t clo, uint64_t chi, uint32_t first_attempt) {
+    return lab_crs_coeff_generic(seed, clo, chi, first_attempt);
+}
+
+// NB coefficients at counters (chi:clo) + off[b].  h is the caller's hoist cache (lab_hoist_invalidate once, then reuse
+// across calls: it is refreshed here when the high part of seed + counter changes).  A block whose offset carries out
+// of the low 32 bits of seed + clo, or whose first draw is rejected, is recomputed by the generic path.
+template <int NB, uint32_t RM>
+__device__ __forceinline__ void lab_crs_coeffs(const LabSeed &seed, LabHoist &h, uint64_t clo, uint64_t chi, const uint32_t (&off)[NB], uint32_t (&out)[NB]) {
+    lab_hoist_update(seed, clo, chi, h);
+    const uint32_t lo32 = (uint32_t)seed.limb[0] + (uint32_t)clo;
+    uint32_t k7[NB], w[NB][4];
+    bool slow[NB];
 #pragma unroll
     for (int b = 0; b < NB; b++) {
-        const uint64_t t = s0 + off[b];
-        carry[b] = t < s0;
-        x[b][0] = 0x61707865u; x[b][1] = 0x3320646eu; x[b][2] = 0x79622d32u; x[b][3] = 0x6b206574u;
-#pragma unroll
-        for (int i = 0; i < 6; i++) x[b][4 + i] = khi[i];
-        x[b][10] = lab_bswap32((uint32_t)(t >> 32));
-        x[b][11] = lab_bswap32((uint32_t)t);
-        x[b][12] = 0u; x[b][13] = 0u; x[b][14] = 0u; x[b][15] = 0u;
+        const uint32_t t = lo32 + off[b];
+        slow[b] = t < off[b];
+        k7[b] = lab_bswap32(t);
     }
-    lab_chacha_rounds<NB>(x, seed.one);
+    lab_chacha_w03<NB, RM>(seed, h, k7, w);
 #pragma unroll
     for (int b = 0; b < NB; b++) {
-        uint32_t w0 = x[b][0] + 0x61707865u, w1 = x[b][1] + 0x3320646eu, w2 = x[b][2] + 0x79622d32u, w3 = x[b][3] + 0x6b206574u;
-        const bool ok = lab_sample_u128(w0, w1, w2, w3, out[b]);
-        if (carry[b] || !ok) {
+        const bool ok = lab_sample_u128(w[b][0], w[b][1], w[b][2], w[b][3], out[b]);
+        if (slow[b] || !ok) {
             uint64_t lo = clo + off[b];
             uint64_t hi = chi + (lo < clo);
-            out[b] = lab_crs_coeff_slow(seed, lo, hi, carry[b] ? 0u : 1u);
+            out[b] = lab_crs_coeff_slow(seed, lo, hi, slow[b] ? 0u : 1u);
         }
     }
 }

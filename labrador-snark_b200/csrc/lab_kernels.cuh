@@ -413,46 +413,70 @@ __global__ void __launch_bounds__(256) k_digit_norm_sq(const uint32_t *__restric
 // ------------------------------------------------------------------------------------------------
 // CRS expansion (structs.rs:35-45,147-171): thread per coefficient, coalesced stores.  INT32-ALU bound.
 // ------------------------------------------------------------------------------------------------
+// FMA-pipe rotation masks (lab_chacha.cuh), one per kernel: chosen on a B200 so that the ALU and FMA pipes carry the
+// same load next to whatever else the kernel issues (tools/kbench.cu sweeps them; profiles/ holds the results)
+#ifndef LAB_RM_EXPAND
+#define LAB_RM_EXPAND 0x00000000u
+#endif
+#ifndef LAB_RM_COMMIT
+#define LAB_RM_COMMIT 0x00000000u
+#endif
+#ifndef LAB_RM_MATVEC
+#define LAB_RM_MATVEC 0x00000000u
+#endif
+
+template <uint32_t RM>
 __global__ void __launch_bounds__(256) k_crs_expand(LabSeed seed, uint64_t start_lo, uint64_t start_hi, size_t n_coeffs, uint32_t *__restrict__ out) {
     size_t idx = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
     const size_t stride = (size_t)gridDim.x * blockDim.x * 2;
+    LabHoist h;
+    lab_hoist_invalidate(h);
     for (; idx < n_coeffs; idx += stride) {
         uint64_t lo = start_lo + idx;
         uint64_t hi = start_hi + (lo < start_lo);
         const uint32_t off[2] = {0u, 1u};
         uint32_t c[2];
-        lab_crs_coeffs<2>(seed, lo, hi, off, c);
+        lab_crs_coeffs<2, RM>(seed, h, lo, hi, off, c);
         if (idx + 1 < n_coeffs) *reinterpret_cast<uint2 *>(out + idx) = make_uint2(c[0], c[1]);
         else out[idx] = c[0];
     }
 }
 
 // one CRS polynomial per warp, in the transform domain: lane j produces coefficients j and j+32
-__device__ __forceinline__ void crs_poly_hat(const LabSeed &seed, uint64_t lo, uint64_t hi, const LabWarpTw &tw, int lane, uint32_t &re, uint32_t &im) {
+template <uint32_t RM>
+__device__ __forceinline__ void crs_poly_hat(const LabSeed &seed, LabHoist &h, uint64_t lo, uint64_t hi, const LabWarpTw &tw, int lane, uint32_t &re, uint32_t &im) {
     const uint32_t off[2] = {(uint32_t)lane, (uint32_t)lane + 32u};
     uint32_t c[2];
-    lab_crs_coeffs<2>(seed, lo, hi, off, c);
+    lab_crs_coeffs<2, RM>(seed, h, lo, hi, off, c);
     re = c[0]; im = c[1];
     lab_ntt32_fwd_warp(re, im, tw, lane, seed.one);
 }
 
 // ------------------------------------------------------------------------------------------------
 // K_A: inner Ajtai commitments t_i[row] = sum_n A[row][n] * s_i[n]   (proofgen.rs:41-49)
-// CTA = 8 warps, RT = 4 rows.  Per step two columns n are processed: warp w generates and transforms
-// A[row0 + (w & 3)][n0 + (w >> 2)] (64 ChaCha blocks), parks it in shared memory, then every thread
-// (lane = slot, warp = group of IC witness vectors) does RT*IC complex multiply-accumulates per column
-// against the n-major transformed witness (128 B coalesced per (n, i), L2 resident).
-// ChaCha runs on the ALU pipe, the MACs on the FMA pipe.  A is generated exactly once.
+// One CTA owns KA_RT = 4 rows of A and walks all N columns in tiles of `cols` columns.  A is generated exactly once.
+//
+// Warp-specialised: the "producer" warps (registers trimmed with setmaxnreg) do nothing but ChaCha20 + the warp
+// transform, PP polynomials of A per tile each, and park them (re, im, Q - im) in a 4-deep shared-memory ring; the four
+// "consumer" warps (one warpgroup with a raised register budget) hold the accumulators (4 rows x IC witness vectors per
+// thread, lane = slot) and multiply-accumulate every tile against the n-major transformed witness (128 B coalesced per
+// (n, i), L2 resident), fetched one column ahead.  Producers never wait for the MACs (ring + FULL named barriers /
+// EMPTY mbarriers), so the ALU pipe sees an uninterrupted ChaCha20 stream while the consumers' IMADs use the FMA pipe.
+//   PP = 1: 12 producer warps x 1 polynomial (2 interleaved ChaCha20 states per lane), tile = 4 rows x 3 columns
+//   PP = 2:  8 producer warps x 2 polynomials (4 interleaved states per lane),          tile = 4 rows x 4 columns
 // ------------------------------------------------------------------------------------------------
 constexpr int KA_RT = 4;        // rows of A per CTA
-constexpr int KA_COLS = 3;      // columns of A per tile: 4 x 3 = 12 polynomials = one per producer warp
-constexpr int KA_PROD = 12;     // producer warps (three warpgroups)
 constexpr int KA_CONS = 4;      // consumer warps (one warpgroup)
 constexpr int KA_DEPTH = 4;     // ring slots between producer and consumer warps
-constexpr int KA_THREADS = 32 * (KA_PROD + KA_CONS);
-// hats of padding the transformed witness needs after its N*R entries: the consumers read up to KA_COLS columns past
+__host__ __device__ constexpr int ka_prod(int pp) { return pp == 1 ? 12 : 8; }            // producer warps
+__host__ __device__ constexpr int ka_cols(int pp) { return ka_prod(pp) * pp / KA_RT; }    // columns of A per tile
+__host__ __device__ constexpr int ka_threads(int pp) { return 32 * (ka_prod(pp) + KA_CONS); }
+#ifndef LAB_KA_PP
+#define LAB_KA_PP 1
+#endif
+// hats of padding the transformed witness needs after its N*R entries: the consumers read up to `cols` columns past
 // the end (ring tail + one-column prefetch) and up to KA_CONS*16 vectors past R without predicates
-constexpr size_t KA_PAD_COLS = KA_COLS + 1;
+constexpr size_t KA_PAD_COLS = 4 + 1;
 constexpr size_t KA_PAD_VECS = KA_CONS * 16;
 
 __device__ __forceinline__ void bar_sync_named(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -475,51 +499,97 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
 
-// Warp-specialised: warps 0-11 ("producers", three warpgroups, registers trimmed with setmaxnreg) do nothing but
-// ChaCha20 + the warp transform, one polynomial of A per tile each (tile = 4 rows x 3 columns), and park it in a
-// 4-deep shared-memory ring; warps 12-15 ("consumers", one warpgroup with a raised register budget) hold the
-// accumulators (4 rows x IC witness vectors per thread, lane = slot) and multiply-accumulate every tile against the
-// n-major transformed witness, fetched from L2 one column ahead.  Producers never wait for the MACs (ring + named
-// barriers FULL/EMPTY), so the ALU pipe sees an uninterrupted ChaCha20 stream from three warps per scheduler while
-// the consumers' IMADs use the FMA pipe.
-template <int IC>
-__global__ void __launch_bounds__(KA_THREADS, 1) k_commit_inner(LabSeed seed, const uint32_t *__restrict__ What, uint32_t N, uint32_t R,
-                                                                 uint64_t row0, uint64_t nrows, uint32_t i_base, uint32_t *__restrict__ T) {
-    __shared__ uint32_t Are[KA_DEPTH][KA_PROD][32], Aim[KA_DEPTH][KA_PROD][32], Anim[KA_DEPTH][KA_PROD][32];   // re, im, Q - im
+template <int IC, uint32_t RM, int PP>
+__global__ void __launch_bounds__(ka_threads(PP), 1) k_commit_inner(LabSeed seed, const uint32_t *__restrict__ What, uint32_t N, uint32_t R,
+                                                                     uint64_t row0, uint64_t nrows, uint32_t i_base, uint32_t *__restrict__ T) {
+    constexpr int PROD = ka_prod(PP), COLS = ka_cols(PP), TP = PROD * PP, THREADS = ka_threads(PP), NB = 2 * PP;
+    __shared__ uint32_t Are[KA_DEPTH][TP][32], Aim[KA_DEPTH][TP][32], Anim[KA_DEPTH][TP][32];   // re, im, Q - im; polynomial col * 4 + row
     __shared__ uint64_t empty_bar[KA_DEPTH];                     // consumers -> producers: slot may be overwritten
+    __shared__ uint32_t tws[LAB_TWS_ROWS][32];                   // forward transform constants of the 32 lanes
+    __shared__ uint32_t hoist[PROD][16];                         // per producer warp: LabHoist of its current counter range
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < KA_DEPTH; s++) mbar_init(&empty_bar[s], 32 * KA_CONS);
     }
+    if (w == 0) lab_warp_tw_to_smem(tws, lane);
     __syncthreads();
     const uint64_t rblk = (uint64_t)blockIdx.x * KA_RT;          // first row of this CTA, relative to row0
-    const uint32_t ntiles = (N + KA_COLS - 1) / KA_COLS;
+    const uint32_t ntiles = (N + COLS - 1) / COLS;
     // FULL[s] is named barrier 1 + s (producers arrive, consumers sync); EMPTY[s] is an mbarrier only the consumers
     // arrive on, so producer warps never wait for each other
-    if (w < KA_PROD) {
+    if (w < PROD) {
         // ---------------- producer ----------------
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
-        const LabWarpTw tw = lab_warp_tw(lane);
-        const int grow = w & 3, gcol = w >> 2;
+        if constexpr (PP == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
+        const int grow = w & 3, gcol = w >> 2;                  // polynomial p of this warp is column gcol + p * (PROD / 4) of the tile
         const bool row_ok = rblk + grow < nrows;
         // counter of coefficient 0 of A[row][n]: (row * N + n) * 64 (structs.rs:55-72); < 2^64 for every supported shape
         uint64_t ctr = ((row0 + rblk + grow) * (uint64_t)N + gcol) * 64ull;
+        uint64_t tag = ~0ull;                                    // which counter range hoist[w] is valid for
+        constexpr uint32_t PSTEP = 64u * (PROD / 4);             // counter distance between the warp's polynomials
         for (uint32_t t = 0; t < ntiles; t++) {
             const int s = t % KA_DEPTH;
-            uint32_t re = 0, im = 0;
-            if (row_ok && KA_COLS * t + gcol < N) crs_poly_hat(seed, ctr, 0ull, tw, lane, re, im);
-            ctr += 64ull * KA_COLS;
+            uint32_t c[NB];
+#pragma unroll
+            for (int b = 0; b < NB; b++) c[b] = 0;
+            if (row_ok && COLS * t + gcol < N) {
+                const uint64_t s0 = seed.limb[0] + ctr;
+                const uint64_t ntag = ((uint64_t)(s0 < ctr) << 32) | (s0 >> 32);
+                if (ntag != tag) {                               // warp-uniform, once per 2^32 counters
+                    LabHoist hh;
+                    lab_hoist_compute(seed, ctr, 0ull, hh);
+                    __syncwarp();
+                    if (lane == 0) {
+                        uint32_t *q = hoist[w];
+                        q[0] = hh.k3; q[1] = hh.P0; q[2] = hh.P1; q[3] = hh.Q0; q[4] = hh.A5; q[5] = hh.A10; q[6] = hh.Q1; q[7] = hh.Q2;
+                        q[8] = hh.A6; q[9] = hh.A2; q[10] = hh.A8; q[11] = hh.A13; q[12] = hh.A4; q[13] = hh.A9; q[14] = hh.A14;
+                    }
+                    __syncwarp();
+                    tag = ntag;
+                }
+                const uint32_t lo32 = (uint32_t)s0;
+                // a tile slice that straddles a 2^32 boundary of seed + counter (key word 6 differs from the hoisted one for
+                // some lanes; once per 2^26 polynomials) takes the generic path, and so do coefficients whose first draw is rejected
+                const bool straddle = lo32 > 0xFFFFFFFFu - (PSTEP * (PP - 1) + 63u);
+                LabHoist h;
+                const uint32_t *q = hoist[w];
+                h.k3 = q[0]; h.P0 = q[1]; h.P1 = q[2]; h.Q0 = q[3]; h.A5 = q[4]; h.A10 = q[5]; h.Q1 = q[6]; h.Q2 = q[7];
+                h.A6 = q[8]; h.A2 = q[9]; h.A8 = q[10]; h.A13 = q[11]; h.A4 = q[12]; h.A9 = q[13]; h.A14 = q[14];
+                uint32_t k7[NB], wd[NB][4];
+#pragma unroll
+                for (int b = 0; b < NB; b++) k7[b] = lab_bswap32(lo32 + (uint32_t)lane + 32u * (b & 1) + PSTEP * (b >> 1));
+                lab_chacha_w03<NB, RM>(seed, h, k7, wd);
+                uint32_t slow = straddle ? (1u << NB) - 1u : 0u;
+#pragma unroll
+                for (int b = 0; b < NB; b++) slow |= lab_sample_u128(wd[b][0], wd[b][1], wd[b][2], wd[b][3], c[b]) ? 0u : 1u << b;
+                if (slow) {      // inlined: a call here would pin the ChaCha state to the ABI's registers
+#pragma unroll
+                    for (int b = 0; b < NB; b++)
+                        if (slow >> b & 1u) c[b] = lab_crs_coeff_generic(seed, ctr + lane + 32u * (b & 1) + PSTEP * (b >> 1), 0ull, straddle ? 0u : 1u);
+                }
+#pragma unroll
+                for (int p = 0; p < PP; p++) {
+                    if (PP > 1 && !(COLS * t + gcol + p * (PROD / 4) < N)) { c[2 * p] = 0; c[2 * p + 1] = 0; }   // column past N: zero polynomial
+                    else lab_ntt32_fwd_warp_smem(c[2 * p], c[2 * p + 1], tws, lane, seed.one);
+                }
+            }
+            ctr += 64ull * COLS;
             if (t >= KA_DEPTH) mbar_wait(&empty_bar[s], (t / KA_DEPTH - 1) & 1);  // slot free again?
-            Are[s][w][lane] = re;
-            Aim[s][w][lane] = im;
-            Anim[s][w][lane] = LABQ - im;
-            bar_arrive_named(1 + s, KA_THREADS);                                 // slot full
+#pragma unroll
+            for (int p = 0; p < PP; p++) {
+                const int slot = (gcol + p * (PROD / 4)) * 4 + grow;
+                Are[s][slot][lane] = c[2 * p];
+                Aim[s][slot][lane] = c[2 * p + 1];
+                Anim[s][slot][lane] = LABQ - c[2 * p + 1];
+            }
+            bar_arrive_named(1 + s, THREADS);                                    // slot full
         }
     } else {
         // ---------------- consumer ----------------
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-        const int cw = w - KA_PROD;
+        if constexpr (PP == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+        const int cw = w - PROD;
         const uint32_t i0 = i_base + (uint32_t)cw * IC;
         uint32_t accr[KA_RT][IC], acci[KA_RT][IC];
 #pragma unroll
@@ -527,9 +597,9 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_commit_inner(LabSeed seed, co
 #pragma unroll
             for (int ii = 0; ii < IC; ii++) { accr[r][ii] = 0; acci[r][ii] = 0; }
         // The transformed witness is read as two 16-bit halves per slot (re at +0, im at +2 bytes of the packed word):
-        // no ALU-pipe unpacking.  No bounds predicates either: What is padded (see KA_PAD_HATS) so that columns n >= N
-        // and vectors i >= R are readable; the producers emit zero polynomials for n >= N and results for i >= R are
-        // never stored, so whatever is read there cannot reach the output.
+        // no ALU-pipe unpacking.  No bounds predicates either: What is padded (KA_PAD_COLS, KA_PAD_VECS) so that columns
+        // n >= N and vectors i >= R are readable; the producers emit zero polynomials for n >= N and results for i >= R
+        // are never stored, so whatever is read there cannot reach the output.
         const uint16_t *sp = reinterpret_cast<const uint16_t *>(What + (size_t)i0 * 32 + lane);
         const size_t col_stride = (size_t)R * 64;                 // 16-bit units per column n
         uint32_t nsr[IC], nsm[IC];                                // next column, already split
@@ -538,14 +608,15 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_commit_inner(LabSeed seed, co
             for (int ii = 0; ii < IC; ii++) { nsr[ii] = __ldg(sp + ii * 64); nsm[ii] = __ldg(sp + ii * 64 + 1); }
             sp += col_stride;
         };
+        constexpr int FOLD_EVERY = 30 / (2 * COLS);               // tiles between folds: 2 * COLS products < 2^26 each per tile
         int pending = 0;
         fetch();
         for (uint32_t t = 0; t < ntiles; t++) {
             const int s = t % KA_DEPTH;
             const uint32_t *a_re = &Are[s][0][lane], *a_im = &Aim[s][0][lane], *a_nim = &Anim[s][0][lane];
-            bar_sync_named(1 + s, KA_THREADS);                    // wait for the producers
+            bar_sync_named(1 + s, THREADS);                       // wait for the producers
 #pragma unroll
-            for (int nn = 0; nn < KA_COLS; nn++) {
+            for (int nn = 0; nn < COLS; nn++) {
                 uint32_t sr[IC], sm_[IC];
 #pragma unroll
                 for (int ii = 0; ii < IC; ii++) { sr[ii] = nsr[ii]; sm_[ii] = nsm[ii]; }
@@ -566,7 +637,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_commit_inner(LabSeed seed, co
                     }
             }
             mbar_arrive(&empty_bar[s]);                          // slot may be overwritten
-            if (++pending == 5) {                                 // 5 tiles * 3 columns * 2 products < 2^5 * 2^26
+            if (++pending == FOLD_EVERY) {
                 pending = 0;
 #pragma unroll
                 for (int r = 0; r < KA_RT; r++)
@@ -626,12 +697,14 @@ __global__ void __launch_bounds__(256) k_crs_matvec(LabSeed seed, const MvItem *
     }
     uint32_t accr = 0, acci = 0;
     int pending = 0;
+    LabHoist h;
+    lab_hoist_invalidate(h);
     for (uint32_t y = it.y0; y < it.y0 + it.cnt; y++) {
         const uint64_t add = (uint64_t)(y / it.nk) * it.sp + (uint64_t)(y % it.nk) * it.sk;
         const uint64_t plo = lo + add;
         const uint64_t phi = hi + (plo < lo);
         uint32_t re, im;
-        crs_poly_hat(seed, plo, phi, tw, lane, re, im);
+        crs_poly_hat<LAB_RM_MATVEC>(seed, h, plo, phi, tw, lane, re, im);
         const uint32_t v = __ldg(V + ((size_t)it.vec_off + y) * 32 + lane);
         accr += re * lab_re(v) + (LABQ - im) * lab_im(v);
         acci += re * lab_im(v) + im * lab_re(v);

@@ -67,6 +67,37 @@ __device__ __forceinline__ void lab_ntt32_fwd_warp(uint32_t &re, uint32_t &im, c
     im = lab_csub(im);
 }
 
+// The forward constants of all 32 lanes as a table in shared memory (row 5 * kind + stage; kind = fr, fi, nfi, sgn, off):
+// the CRS producer warps of K_A read them with LDS per stage instead of holding 25 registers across the ChaCha20 rounds.
+constexpr int LAB_TWS_ROWS = 25;
+__device__ __forceinline__ void lab_warp_tw_to_smem(uint32_t (*tws)[32], int lane) {
+    const LabWarpTw t = lab_warp_tw(lane);
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        tws[s][lane] = t.fr[s];
+        tws[5 + s][lane] = t.fi[s];
+        tws[10 + s][lane] = t.nfi[s];
+        tws[15 + s][lane] = t.sgn[s];
+        tws[20 + s][lane] = t.off[s];
+    }
+}
+__device__ __forceinline__ void lab_ntt32_fwd_warp_smem(uint32_t &re, uint32_t &im, const uint32_t (*tws)[32], int lane, uint32_t one) {
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        const int len = 16 >> s;
+        const uint32_t fr = tws[s][lane], fi = tws[5 + s][lane], nfi = tws[10 + s][lane], sgn = tws[15 + s][lane], off = tws[20 + s][lane];
+        uint32_t pr = re * fr + im * nfi;
+        uint32_t pi = re * fi + im * fr;
+        pr = lab_fold(lab_fold(pr));
+        pi = lab_fold(lab_fold(pi));
+        const uint32_t recv = __shfl_xor_sync(0xffffffffu, pi * 65536u + pr, len);
+        re = lab_fold(pr * sgn + (lab_re(recv) * one + off));
+        im = lab_fold(pi * sgn + (lab_im(recv) * one + off));
+    }
+    re = lab_csub(re);
+    im = lab_csub(im);
+}
+
 // lane j holds slot j (residues < 2Q); returns g_j = f_j + i f_{j+32}, canonical, scaled by 1/32.
 __device__ __forceinline__ void lab_ntt32_inv_warp(uint32_t &re, uint32_t &im, const LabWarpTw &tw, int lane) {
 #pragma unroll
