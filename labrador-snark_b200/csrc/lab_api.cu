@@ -73,6 +73,19 @@ struct lab_ctx {
         CK(cudaGetLastError());                                                                      \
     } while (0)
 
+#define LAUNCH_SMEM(kern, grid, block, smem, ...)                                                   \
+    do {                                                                                             \
+        /* per call site (= per instantiation) and device; idempotent, so racing threads are harmless */ \
+        static bool attr_set_[64] = {};                                                              \
+        if (!attr_set_[ctx->device & 63]) {                                                          \
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); \
+            attr_set_[ctx->device & 63] = true;                                                      \
+        }                                                                                            \
+        kern<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);                                 \
+        ctx->launches++;                                                                             \
+        CK(cudaGetLastError());                                                                      \
+    } while (0)
+
 // ---------------------------------------------------------------------------------------------
 // arena
 // ---------------------------------------------------------------------------------------------
@@ -299,11 +312,11 @@ static int d_commit_inner(lab_ctx *ctx, const LabSeed &seed, const uint32_t *Wha
     const int IC = R > 32 ? 16 : (R > 16 ? 8 : (R > 8 ? 4 : (R > 4 ? 2 : 1)));
     for (uint64_t ib = 0; ib < R; ib += (uint64_t)KA_CONS * IC) {
         switch (IC) {
-            case 16: LAUNCH((k_commit_inner<16, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
-            case 8: LAUNCH((k_commit_inner<8, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
-            case 4: LAUNCH((k_commit_inner<4, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
-            case 2: LAUNCH((k_commit_inner<2, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
-            default: LAUNCH((k_commit_inner<1, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
+            case 16: LAUNCH_SMEM((k_commit_inner<16, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, 16), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
+            case 8: LAUNCH_SMEM((k_commit_inner<8, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, 8), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
+            case 4: LAUNCH_SMEM((k_commit_inner<4, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, 4), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
+            case 2: LAUNCH_SMEM((k_commit_inner<2, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, 2), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
+            default: LAUNCH_SMEM((k_commit_inner<1, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, 1), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
         }
     }
     return LAB_OK;

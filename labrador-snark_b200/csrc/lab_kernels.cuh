@@ -471,6 +471,7 @@ constexpr int KA_DEPTH = 4;     // ring slots between producer and consumer warp
 __host__ __device__ constexpr int ka_prod(int pp) { return pp == 1 ? 12 : 8; }            // producer warps
 __host__ __device__ constexpr int ka_cols(int pp) { return ka_prod(pp) * pp / KA_RT; }    // columns of A per tile
 __host__ __device__ constexpr int ka_threads(int pp) { return 32 * (ka_prod(pp) + KA_CONS); }
+__host__ __device__ constexpr size_t ka_dyn_smem(int pp, int ic) { return (size_t)KA_DEPTH * ka_cols(pp) * KA_CONS * ic * 128; }   // witness ring
 #ifndef LAB_KA_PP
 #define LAB_KA_PP 1
 #endif
@@ -499,6 +500,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
 
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (cp.async.bulk, sm_90+)
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+// 16-bit shared load zero-extended into a 32-bit register (no ALU-pipe unpacking)
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
+    uint32_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
 template <int IC, uint32_t RM, int PP>
 __global__ void __launch_bounds__(ka_threads(PP), 1) k_commit_inner(LabSeed seed, const uint32_t *__restrict__ What, uint32_t N, uint32_t R,
                                                                      uint64_t row0, uint64_t nrows, uint32_t i_base, uint32_t *__restrict__ T) {
@@ -507,10 +524,13 @@ __global__ void __launch_bounds__(ka_threads(PP), 1) k_commit_inner(LabSeed seed
     __shared__ uint64_t empty_bar[KA_DEPTH];                     // consumers -> producers: slot may be overwritten
     __shared__ uint32_t tws[LAB_TWS_ROWS][32];                   // forward transform constants of the 32 lanes
     __shared__ uint32_t hoist[PROD][16];                         // per producer warp: LabHoist of its current counter range
+    __shared__ uint64_t wfull_bar[KA_DEPTH];                     // TMA -> consumers: witness columns of the tile have landed
+    extern __shared__ __align__(128) uint32_t Sw[];              // [KA_DEPTH][COLS][KA_CONS * IC][32] witness hats of the tile
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < KA_DEPTH; s++) mbar_init(&empty_bar[s], 32 * KA_CONS);
+        for (int s = 0; s < KA_DEPTH; s++) { mbar_init(&empty_bar[s], 32 * KA_CONS); mbar_init(&wfull_bar[s], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (w == 0) lab_warp_tw_to_smem(tws, lane);
     __syncthreads();
@@ -596,31 +616,40 @@ __global__ void __launch_bounds__(ka_threads(PP), 1) k_commit_inner(LabSeed seed
         for (int r = 0; r < KA_RT; r++)
 #pragma unroll
             for (int ii = 0; ii < IC; ii++) { accr[r][ii] = 0; acci[r][ii] = 0; }
-        // The transformed witness is read as two 16-bit halves per slot (re at +0, im at +2 bytes of the packed word):
-        // no ALU-pipe unpacking.  No bounds predicates either: What is padded (KA_PAD_COLS, KA_PAD_VECS) so that columns
+        // The transformed witness of the tile (COLS columns x 4 * IC vectors, 128 B each) is brought into a shared-memory ring
+        // by TMA bulk copies that one consumer thread issues KA_DEPTH - 1 tiles ahead; the MAC loop reads it as two 16-bit
+        // halves per slot (re at +0, im at +2 bytes of the packed word): no address arithmetic, no ALU-pipe unpacking, no
+        // prefetch registers.  No bounds predicates either: What is padded (KA_PAD_COLS, KA_PAD_VECS) so that columns
         // n >= N and vectors i >= R are readable; the producers emit zero polynomials for n >= N and results for i >= R
         // are never stored, so whatever is read there cannot reach the output.
-        const uint16_t *sp = reinterpret_cast<const uint16_t *>(What + (size_t)i0 * 32 + lane);
-        const size_t col_stride = (size_t)R * 64;                 // 16-bit units per column n
-        uint32_t nsr[IC], nsm[IC];                                // next column, already split
-        auto fetch = [&]() {
+        constexpr uint32_t CHUNK = KA_CONS * IC * 128u;           // bytes of one column's slice
+        constexpr uint32_t SLOT_WORDS = COLS * KA_CONS * IC * 32;
+        const bool loader = (cw == 0 && lane == 0);
+        auto load_tile = [&](uint32_t u) {                        // tile u -> ring slot u % KA_DEPTH
+            const int su = u % KA_DEPTH;
+            mbar_expect_tx(&wfull_bar[su], COLS * CHUNK);
 #pragma unroll
-            for (int ii = 0; ii < IC; ii++) { nsr[ii] = __ldg(sp + ii * 64); nsm[ii] = __ldg(sp + ii * 64 + 1); }
-            sp += col_stride;
+            for (int nn = 0; nn < COLS; nn++)
+                bulk_g2s(Sw + su * SLOT_WORDS + nn * (KA_CONS * IC * 32), What + ((size_t)(u * COLS + nn) * R + i_base) * 32, CHUNK, &wfull_bar[su]);
         };
+        if (loader)
+            for (uint32_t u = 0; u < ntiles && u < KA_DEPTH - 1; u++) load_tile(u);
         constexpr int FOLD_EVERY = 30 / (2 * COLS);               // tiles between folds: 2 * COLS products < 2^26 each per tile
         int pending = 0;
-        fetch();
+        const uint32_t sw_lane = (uint32_t)__cvta_generic_to_shared(Sw) + (uint32_t)(cw * IC * 32 + lane) * 4u;
         for (uint32_t t = 0; t < ntiles; t++) {
             const int s = t % KA_DEPTH;
+            if (loader && t + KA_DEPTH - 1 < ntiles) {            // slot of tile t - 1 is free once every consumer has passed it
+                if (t >= 1) mbar_wait(&empty_bar[(t - 1) % KA_DEPTH], ((t - 1) / KA_DEPTH) & 1);
+                load_tile(t + KA_DEPTH - 1);
+            }
+            __syncwarp();
             const uint32_t *a_re = &Are[s][0][lane], *a_im = &Aim[s][0][lane], *a_nim = &Anim[s][0][lane];
+            mbar_wait(&wfull_bar[s], (t / KA_DEPTH) & 1);         // witness slice landed
             bar_sync_named(1 + s, THREADS);                       // wait for the producers
+            const uint32_t sw_slot = sw_lane + (uint32_t)s * (SLOT_WORDS * 4u);
 #pragma unroll
             for (int nn = 0; nn < COLS; nn++) {
-                uint32_t sr[IC], sm_[IC];
-#pragma unroll
-                for (int ii = 0; ii < IC; ii++) { sr[ii] = nsr[ii]; sm_[ii] = nsm[ii]; }
-                fetch();                                          // next column's witness slots land during these MACs
                 uint32_t ar[KA_RT], am[KA_RT], nam[KA_RT];
 #pragma unroll
                 for (int r = 0; r < KA_RT; r++) {
@@ -629,12 +658,17 @@ __global__ void __launch_bounds__(ka_threads(PP), 1) k_commit_inner(LabSeed seed
                     nam[r] = a_nim[(nn * 4 + r) * 32];
                 }
 #pragma unroll
-                for (int ii = 0; ii < IC; ii++)
+                for (int ii = 0; ii < IC; ii++) {
+                    const uint32_t sr = lds_u16(sw_slot + (uint32_t)(nn * KA_CONS * IC + ii) * 128u);
+                    const uint32_t sm_ = lds_u16(sw_slot + (uint32_t)(nn * KA_CONS * IC + ii) * 128u + 2u);
 #pragma unroll
-                    for (int r = 0; r < KA_RT; r++) {
-                        accr[r][ii] += ar[r] * sr[ii] + nam[r] * sm_[ii];
-                        acci[r][ii] += ar[r] * sm_[ii] + am[r] * sr[ii];
+                    for (int r = 0; r < KA_RT; r++) {         // four chained IMADs, nothing else
+                        accr[r][ii] = ar[r] * sr + accr[r][ii];
+                        accr[r][ii] = nam[r] * sm_ + accr[r][ii];
+                        acci[r][ii] = ar[r] * sm_ + acci[r][ii];
+                        acci[r][ii] = am[r] * sr + acci[r][ii];
                     }
+                }
             }
             mbar_arrive(&empty_bar[s]);                          // slot may be overwritten
             if (++pending == FOLD_EVERY) {

@@ -145,8 +145,9 @@ static void bench_expand(Timer &tm, const LabSeed &seed, uint32_t *out, size_t n
 template <uint32_t RM, int PP>
 static void bench_commit(Timer &tm, const LabSeed &seed, const uint32_t *What, uint32_t N, uint32_t R, uint64_t rows, uint32_t *T, unsigned long long *ref) {
     const unsigned grid = (unsigned)((rows + KA_RT - 1) / KA_RT);
+    CK(cudaFuncSetAttribute(k_commit_inner<16, RM, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ka_dyn_smem(PP, 16)));
     auto launch = [&] {
-        for (uint32_t ib = 0; ib < R; ib += KA_CONS * 16) k_commit_inner<16, RM, PP><<<grid, ka_threads(PP)>>>(seed, What, N, R, 0ull, rows, ib, T);
+        for (uint32_t ib = 0; ib < R; ib += KA_CONS * 16) k_commit_inner<16, RM, PP><<<grid, ka_threads(PP), ka_dyn_smem(PP, 16)>>>(seed, What, N, R, 0ull, rows, ib, T);
     };
     float ms = tm.run(launch, 2);
     CK(cudaGetLastError());
