@@ -16,7 +16,7 @@ all-reduce followed by mod q; g tiles are all-gathered; T stays row-sharded.
   value        inputs resident in HBM, CUDA-event timed on the library's stream, max over ranks
   e2e          same step through the host-buffer C ABI (pinned host buffers, H2D/D2H inside the timed region)
   roofline     dominant kernel k_commit_inner against the MEASURED ALU-pipe ceiling (ChaCha20 xor+rotate
-               cannot leave the ALU pipe: 640 ALU-pipe lane-ops per CRS coefficient); roofline_ntt is the
+               cannot leave the ALU pipe: 596 ALU-pipe lane-ops per CRS coefficient); roofline_ntt is the
                HBM roofline of the batched NTT kernel (512 algorithmic bytes per polynomial)
   cpu_baseline the oracle (restatement of the reference algorithm, NTT multiplication path) on the host
                cores, on a bounded sample of commitment rows, extrapolated to the whole step
@@ -37,7 +37,10 @@ sys.path.insert(0, os.path.join(ROOT, "labrador-snark_b200"))
 SEED32 = bytes(range(32))
 PRG_SEED = 0x4C61425241444F52
 D, Q, JL = 64, 8191, 256
-ALU_OPS_PER_BLOCK = 640      # 20 rounds x 4 quarter-rounds x 4 steps x (xor + rotate)
+# ALU-pipe lane-ops (xor + rotate) one CRS coefficient needs: 20 rounds x 4 quarter-rounds x 4 steps x 2 = 640 for a full
+# ChaCha20 block, minus 28 in the first double round (the part that does not depend on key word 7 is computed once per
+# 2^32 counters) minus 16 in the last diagonal round (only keystream words 0..3 are consumed) = 596 (lab_chacha.cuh)
+ALU_OPS_PER_BLOCK = 596
 
 
 def workload_shape(name):
@@ -250,6 +253,18 @@ def main():
 
     # ---- per-kernel numbers for the roofline (rank 0, kernel timed alone, same shard) ----
     roof = roof_ntt = extra = None
+    # DRAM bytes per launch from the committed ncu capture of this very command (profiles/ncu_traffic_r1.json);
+    # only quoted when the launch shape is the captured one
+    try:
+        traffic_db = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
+    except Exception:
+        traffic_db = {}
+
+    def traffic_of(kernel, ok):
+        d = traffic_db.get(kernel)
+        if not d or not ok:
+            return None
+        return d["dram_bytes_read_per_launch"] + d["dram_bytes_write_per_launch"]
     if rank == 0:
         reps = []
         for _ in range(2):
@@ -261,9 +276,13 @@ def main():
         alu_peak = ctx.alu_peak()                                            # lane-ops/s, LOP3 + SHF
         achieved = blocks * ALU_OPS_PER_BLOCK / (k_ms * 1e-3)
         roof = {"kernel": "k_commit_inner", "bound": "int32_alu", "achieved": achieved / 1e9, "peak": alu_peak / 1e9, "unit": "Gop/s",
-                "frac": achieved / alu_peak, "traffic": None, "share_of_step": k_ms / ms_step,
+                "frac": achieved / alu_peak, "traffic": traffic_of("k_commit_inner", args.workload == "cfg3" and world == 1),
+                "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum); algorithmic bytes per launch = "
+                                f"{R * N * 128 + R * nrows * 256} (transformed witness once + T once)",
+                "share_of_step": k_ms / ms_step,
                 "chacha_blocks_per_s": blocks / (k_ms * 1e-3), "kernel_ms": k_ms,
-                "note": "algorithmic ops = 640 ALU-pipe lane-ops (xor + rotate) per ChaCha20 block, one block per CRS coefficient; "
+                "note": "algorithmic ops = 596 ALU-pipe lane-ops (xor + rotate) per CRS coefficient = one ChaCha20 block minus the hoisted part "
+                        "of its first double round and the dead tail of its last; "
                         "peak = LOP3+SHF microbenchmark measured in this run (no driver-measured INT32 peak exists); HBM is idle here"}
         # batched R_q NTT (BASELINE config 2): 2^22 polys, 512 algorithmic bytes per poly
         peaks = {}
@@ -291,7 +310,7 @@ def main():
             t = sorted(tt)[len(tt) // 2]
             res[name] = {"polys_per_s": npoly / (t * 1e-3), "GBps": npoly * bpp / (t * 1e-3) / 1e9, "ms": t}
         roof_ntt = {"kernel": "k_ntt_fwd_regs", "bound": "hbm", "achieved": res["ntt_fwd"]["GBps"], "peak": hbm, "unit": "GB/s",
-                    "frac": res["ntt_fwd"]["GBps"] / hbm, "traffic": None,
+                    "frac": res["ntt_fwd"]["GBps"] / hbm, "traffic": traffic_of("k_ntt_fwd_regs", True),
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                     "log2_polys": 22, "operands_exceed_L2": True}
         extra = {"ntt": res}
