@@ -22,6 +22,12 @@ all-reduce followed by mod q; g tiles are all-gathered; T stays row-sharded.
                cores, on a bounded sample of commitment rows, extrapolated to the whole step
 
 --impl reference times that CPU restatement alone (the reference is Rust and cannot be built here).
+
+Other BASELINE configs are selected with --workload; each prints one JSON line with the same keys:
+  cfg1   labrador_perf sweep (N,R) = (2,2)..(32,32): full prove() and verify() timed separately; value = prove ms at (2,2)
+  cfg2   batched R_q NTT / INTT / fused polymul, 2^10..2^24 polynomials; value = forward-NTT polys/s at 2^24
+  cfg5   1024 independent default-size statements, per-statement CRS seeds (and the shared-seed variant); value = proofs/s
+Under torchrun every rank runs cfg1/cfg2 as an independent replica (these paths do not shard); cfg5 shards statements.
 """
 import argparse
 import json
@@ -145,6 +151,268 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def _finish_line(line, rank, world):
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def _clock_wrap(local_rank, fn):
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    out = fn()
+    return out, sampler.stop()
+
+
+def run_cfg2(args, rank, world, local_rank):
+    """BASELINE config 2: batched negacyclic transform sweep on one GPU (replicas under torchrun)."""
+    import numpy as np
+    import torch
+    import labrador_b200 as lb
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = lb.Context(local_rank)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    big = 1 << 24
+    a = torch.empty((big, D), dtype=torch.int32, device=dev)
+    b = torch.empty((big, D), dtype=torch.int32, device=dev)
+    o = torch.empty((big, D), dtype=torch.int32, device=dev)
+    ctx.synth_zq_dev(PRG_SEED, 20, 0, big * D, a.data_ptr())
+    ctx.synth_zq_dev(PRG_SEED, 21, 0, big * D, b.data_ptr())
+    ctx.sync()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    def timed(fn, small):
+        ts = []
+        for i in range(args.warmup + args.steps):
+            if small:
+                flush.fill_(i & 255)                                     # small batches would otherwise be L2-resident
+                torch.cuda.synchronize()
+            ctx.timer_start(); fn(); t = ctx.timer_stop()
+            if i >= args.warmup:
+                ts.append(t)
+        return sorted(ts)[len(ts) // 2]
+
+    def sweep():
+        tab = []
+        for lg in range(10, 25, 2):
+            n = 1 << lg
+            small = n * 512 < (256 << 20)
+            row = {"log2_polys": lg, "l2": "flushed between iterations" if small else "operands exceed L2"}
+            for name, fn, bpp in (("ntt_fwd", lambda: ctx.ntt_fwd_batch_dev(a.data_ptr(), o.data_ptr(), n), 512),
+                                  ("ntt_inv", lambda: ctx.ntt_inv_batch_dev(a.data_ptr(), o.data_ptr(), n), 512),
+                                  ("ntt_fwd_inplace", lambda: ctx.ntt_fwd_batch_dev(o.data_ptr(), o.data_ptr(), n), 512),
+                                  ("polymul", lambda: ctx.polymul_batch_dev(a.data_ptr(), b.data_ptr(), o.data_ptr(), n), 768)):
+                t = timed(fn, small)
+                row[name] = {"ms": t, "polys_per_s": n / (t * 1e-3), "GBps": n * bpp / (t * 1e-3) / 1e9}
+            tab.append(row)
+        return tab
+    tab, clocks = _clock_wrap(local_rank, sweep)
+    top = tab[-1]
+    # end to end: host buffers through lab_ntt_fwd_batch (H2D + kernel + D2H inside the call)
+    n_e = 1 << 20
+    h_in = torch.empty((n_e, D), dtype=torch.int32, pin_memory=True); h_in.copy_(a[:n_e].cpu())
+    x = h_in.numpy().view(np.uint32)
+    ctx.ntt_fwd_batch(x)
+    t0 = time.perf_counter(); y = ctx.ntt_fwd_batch(x); te = time.perf_counter() - t0
+    # parity spot check against the oracle (the checker, not the product)
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle
+        m = 1 << 16
+        A_, B_ = a[:m].cpu().numpy().view(np.uint32), b[:m].cpu().numpy().view(np.uint32)
+        t0 = time.perf_counter(); ref = oracle.rq_mul_batch(A_, B_, ntt=True); tc = time.perf_counter() - t0
+        ctx.polymul_batch_dev(a.data_ptr(), b.data_ptr(), o.data_ptr(), m); ctx.sync()
+        if not np.array_equal(ref, o[:m].cpu().numpy().view(np.uint32)):
+            raise SystemExit("GPU polymul differs from the oracle")
+        cpu = {"value": m / tc, "unit": "products/s", "cores": 1, "kind": "port",
+               "sample": f"{m} negacyclic products (transform + slot product + inverse) by the oracle, one thread; compare with extra.sweep[-1].polymul"}
+    line = {"metric": "ntt_polys_per_s", "value": top["ntt_fwd"]["polys_per_s"] * world, "unit": "polys/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": top["ntt_fwd"]["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 (F_q^2 slots, exact)", "data": "synthetic",
+            "config": {"workload": "cfg2", "log2_polys": 24, "op": "forward transform, out of place", "parallelism": "replicas only" if world > 1 else "1 GPU",
+                       "l2": "operands exceed L2 at >= 2^20 polys; smaller batches flushed with a 256 MB write"},
+            "e2e": {"value": n_e / te, "unit": "polys/s", "h2d_bytes_per_step": n_e * 256, "d2h_bytes_per_step": n_e * 128, "note": "lab_ntt_fwd_batch on 2^20 host polys"},
+            "gpu_launches": args.steps, "clocks": clocks,
+            "roofline": {"kernel": "k_ntt_fwd_regs", "bound": "hbm", "achieved": top["ntt_fwd"]["GBps"], "peak": hbm, "unit": "GB/s", "frac": top["ntt_fwd"]["GBps"] / hbm,
+                         "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
+            "cpu_baseline": cpu, "extra": {"sweep": tab}}
+    _finish_line(line, rank, world)
+    ctx.close()
+
+
+def run_cfg1(args, rank, world, local_rank):
+    """BASELINE config 1: labrador_perf sweep, prove() and verify() timed separately (the reference's bench times their sum)."""
+    import numpy as np
+    import torch
+    import labrador_b200 as lb
+    from labrador_b200 import synth
+    torch.cuda.set_device(local_rank)
+    ctx = lb.Context(local_rank)
+    sizes = [(2, 2), (4, 4), (8, 8), (16, 16), (32, 32)]
+    cpu_sizes = {(2, 2), (4, 4)}
+    oracle = None
+    if rank == 0 and not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle
+
+    def sweep():
+        tab = []
+        for (N, R) in sizes:
+            try:
+                c = lb.RuntimeConstants.new(N, R)
+            except Exception as e:
+                tab.append({"N": N, "R": R, "skipped": repr(e)})
+                continue
+            S = synth.generate_witness(N, R, c.BETA_BOUND, PRG_SEED)
+            st = lb.State.new(S, c, PRG_SEED, ctx)
+            ver = lb.Verifier.new(st.b_prime_k, c, seed=PRG_SEED, n_attempts=6)
+            prover = lb.Prover.new(S, ver, c, ctx)
+            crs = lb.CRS.from_seed(c, SEED32, ctx)
+            reps = args.steps if N <= 8 else 1
+            for _ in range(2):       # the scratch arena is sized after the first call of a shape
+                tr = prover.proof_gen(st, crs)
+            l0 = ctx.kernel_launches
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                tr = prover.proof_gen(st, crs)
+            tp = (time.perf_counter() - t0) / reps
+            launches = (ctx.kernel_launches - l0) // reps
+            d = tr.as_oracle_dict()
+            ctx.verify(c, SEED32, st.phi_k[0], st.a_k[0], st.b_k[0], ver.challenges, d)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                okv = ctx.verify(c, SEED32, st.phi_k[0], st.a_k[0], st.b_k[0], ver.challenges, d)
+            tv = (time.perf_counter() - t0) / reps
+            npairs = R * (R + 1) // 2
+            blocks = (c.R * c.T_1 * c.KAPPA_1 * c.KAPPA + c.KAPPA * c.N + npairs * (c.T_1 + c.T_2) * c.KAPPA_2) * 64
+            row = {"N": N, "R": R, "kappa": c.KAPPA, "T_1": c.T_1, "T_2": c.T_2, "prove_ms": tp * 1e3, "verify_ms": tv * 1e3, "verify_accepts": bool(okv[0]),
+                   "launches_per_proof": launches, "crs_coefficients_per_proof": blocks, "chacha_blocks_per_s_prove": blocks / tp,
+                   "witness_coeffs_per_s": N * R * D / tp, "jl_attempt": tr.jl_attempt}
+            if oracle is not None and (N, R) in cpu_sizes:
+                co, _ = oracle.constants(N, R)
+                nth = oracle.num_threads()
+                t0 = time.perf_counter()
+                rc, ref = oracle.prove(co, SEED32, S, st.phi_k[0], st.a_k[0], st.b_k[0], ver.challenges, ntt=True, nthreads=nth)
+                tcp = time.perf_counter() - t0
+                t0 = time.perf_counter()
+                okc = oracle.verify(co, SEED32, st.phi_k[0], st.a_k[0], st.b_k[0], ver.challenges, d, ntt=True, nthreads=nth)
+                tcv = time.perf_counter() - t0
+                same = all(np.array_equal(d[k], ref[k]) for k in ("t", "g", "u_1", "projection_int", "b_prime_prime", "h", "u_2", "z"))
+                if rc != 0 or not same or not okc[0]:
+                    raise SystemExit(f"GPU transcript differs from the oracle at (N,R)=({N},{R})")
+                row.update({"cpu_prove_ms": tcp * 1e3, "cpu_verify_ms": tcv * 1e3, "cpu_threads": nth, "bit_exact_vs_oracle": True})
+            tab.append(row)
+        return tab
+    tab, clocks = _clock_wrap(local_rank, sweep)
+    first = tab[0]
+    cpu = None
+    if "cpu_prove_ms" in first:
+        cpu = {"value": first["cpu_prove_ms"], "unit": "ms", "cores": first["cpu_threads"], "kind": "port",
+               "sample": "one full prove() of the same (2,2) statement by the oracle (restatement of the reference algorithm), all host threads"}
+    line = {"metric": "prove_ms", "value": first["prove_ms"], "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": first["prove_ms"], "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 (exact integer arithmetic mod 8191; int64 JL accumulation)", "data": "synthetic",
+            "config": {"workload": "cfg1", "N": 2, "R": 2, "note": "constants.rs default shape; host buffers in, transcript out (this IS the end-to-end path); sweep in extra",
+                       "parallelism": "replicas only" if world > 1 else "1 GPU", "l2": "whole proof is L2/launch-latency bound; CRS regenerated every proof"},
+            "e2e": {"value": first["prove_ms"], "unit": "ms", "h2d_bytes_per_step": 2 * 2 * 2 * 256 * 2 + 2 * 2 * 256 + 2 * 256 * 128 + 5 * 256,
+                    "d2h_bytes_per_step": (128 * 2 + 128 * 2 + 2 * 2 * 2 + 2 + 2 * 2) * 256, "note": "lab_prove with host pointers"},
+            "gpu_launches": first["launches_per_proof"] * args.steps, "clocks": clocks,
+            "roofline": {"kernel": "k_crs_matvec", "bound": "int32_alu", "achieved": first["chacha_blocks_per_s_prove"] * ALU_OPS_PER_BLOCK / 1e9, "peak": ctx.alu_peak() / 1e9,
+                         "unit": "Gop/s", "frac": first["chacha_blocks_per_s_prove"] * ALU_OPS_PER_BLOCK / ctx.alu_peak(), "traffic": None,
+                         "note": "whole-proof CRS coefficients x 596 ALU ops over the whole prove() wall time (launch latency included)"},
+            "cpu_baseline": cpu, "extra": {"sweep": tab}}
+    _finish_line(line, rank, world)
+    ctx.close()
+
+
+def run_cfg5(args, rank, world, local_rank):
+    """BASELINE config 5: 1024 independent default-size statements, sharded over ranks (no collective on the data path)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import labrador_b200 as lb
+    from labrador_b200 import synth
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = lb.Context(local_rank)
+    total = 1024
+    lo, nb = lb.shard.split(total, world, rank)
+    c = lb.RuntimeConstants.new(2, 2)
+    # a handful of distinct statements, cycled (generating 1024 witnesses on the host is input work, not prover work)
+    base = []
+    for k in range(4):
+        S = synth.generate_witness(2, 2, c.BETA_BOUND, PRG_SEED + k)
+        st = lb.State.new(S, c, PRG_SEED + k, ctx)
+        ch = synth.sample_challenges(2, 2, PRG_SEED + k, 6)
+        base.append((S, st, ch))
+    pick = [base[(lo + i) % 4] for i in range(nb)]
+    Sb = np.stack([p[0] for p in pick]); phib = np.stack([p[1].phi_k[0] for p in pick])
+    ab = np.stack([p[1].a_k[0] for p in pick]); bb = np.stack([p[1].b_k[0] for p in pick])
+    chs = [p[2] for p in pick]
+    seeds = [bytes([(lo + i) & 255, (lo + i) >> 8]) + bytes(30) for i in range(nb)]
+    res = {}
+
+    def run():
+        for shared in (False, True):
+            for _ in range(max(1, args.warmup // 2)):
+                ctx.prove_batch(c, seeds, shared, Sb[:8], phib[:8], ab[:8], bb[:8], chs[:8])
+            ts = []
+            for _ in range(args.steps):
+                if world > 1:
+                    dist.barrier(); torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                out = ctx.prove_batch(c, seeds, shared, Sb, phib, ab, bb, chs)
+                ts.append(time.perf_counter() - t0)
+            t = torch.tensor([sum(ts) / len(ts)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res["shared" if shared else "per_statement"] = {"s_per_batch": float(t.item()), "proofs_per_s": total / float(t.item())}
+            res["out_shared" if shared else "out_per_statement"] = out
+    _, clocks = _clock_wrap(local_rank, run)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle
+        co, _ = oracle.constants(2, 2)
+        nth = oracle.num_threads()
+        k = 4
+        t0 = time.perf_counter()
+        for i in range(k):
+            S, st, ch = base[i % 4]
+            rc, ref = oracle.prove(co, seeds[i], S, st.phi_k[0], st.a_k[0], st.b_k[0], ch, ntt=True, nthreads=nth)
+            got = res["out_per_statement"][i]
+            if rc != 0 or not all(np.array_equal(got[f], ref[f]) for f in ("t", "g", "u_1", "h", "u_2", "z")):
+                raise SystemExit("batched GPU proof differs from the oracle")
+            if i == 0:      # the shared-seed variant uses the first statement's seed for every statement
+                got = res["out_shared"][0]
+                if not all(np.array_equal(got[f], ref[f]) for f in ("t", "g", "u_1", "h", "u_2", "z")):
+                    raise SystemExit("batched GPU proof (shared seed) differs from the oracle")
+        tc = (time.perf_counter() - t0) / k
+        cpu = {"value": 1.0 / tc, "unit": "proofs/s", "cores": nth, "kind": "port", "sample": f"{k} of the 1024 statements proved by the oracle, all host threads per proof"}
+    per = res["per_statement"]
+    line = {"metric": "proofs_per_s", "value": per["proofs_per_s"], "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": per["s_per_batch"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32 (exact integer arithmetic mod 8191; int64 JL accumulation)", "data": "synthetic",
+            "config": {"workload": "cfg5", "statements": total, "N": 2, "R": 2, "crs": "one seed per statement (reference semantics: CRS::new per proof)",
+                       "parallelism": f"statements sharded over {world} rank(s), no collective", "l2": "CRS regenerated per proof; working set per proof < L2"},
+            "e2e": {"value": per["proofs_per_s"], "unit": "proofs/s", "h2d_bytes_per_step": int(Sb.nbytes + phib.nbytes + ab.nbytes + bb.nbytes),
+                    "d2h_bytes_per_step": nb * (128 * 2 + 128 * 2 + 16) * 256, "note": "lab_prove_batch takes host buffers: this is the end-to-end number"},
+            "gpu_launches": None, "clocks": clocks, "roofline": None, "cpu_baseline": cpu,
+            "extra": {"shared_crs_seed_variant": res["shared"], "per_statement_seed_variant": per}}
+    _finish_line(line, rank, world)
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -160,6 +428,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload in ("cfg1", "cfg2", "cfg5"):
+        {"cfg1": run_cfg1, "cfg2": run_cfg2, "cfg5": run_cfg5}[args.workload](args, rank, world, local_rank)
         return
 
     import numpy as np
