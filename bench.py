@@ -26,6 +26,8 @@ all-reduce followed by mod q; g tiles are all-gathered; T stays row-sharded.
 Other BASELINE configs are selected with --workload; each prints one JSON line with the same keys:
   cfg1   labrador_perf sweep (N,R) = (2,2)..(32,32): full prove() and verify() timed separately; value = prove ms at (2,2)
   cfg2   batched R_q NTT / INTT / fused polymul, 2^10..2^24 polynomials; value = forward-NTT polys/s at 2^24
+  prove  one full prove() + verify() of the largest shape of that sweep, (N,R) = (32,32), ROW-SHARDED over the ranks by
+         the library's own NCCL communicator (lab_comm_*): prove() ms at 1/2/4/8 GPUs; value = witness-coeffs/s
   cfg5   1024 independent default-size statements, per-statement CRS seeds (and the shared-seed variant); value = proofs/s
 Under torchrun every rank runs cfg1/cfg2 as an independent replica (these paths do not shard); cfg5 shards statements.
 """
@@ -331,6 +333,94 @@ def run_cfg1(args, rank, world, local_rank):
     ctx.close()
 
 
+def run_prove(args, rank, world, local_rank):
+    """Full Prover::proof_gen + Verifier::verify of one (32,32) statement, CRS-regenerating stages row-sharded over the
+    ranks inside the library (NCCL all-gathers on the library's stream).  Strong scaling; every rank gets the transcript."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import labrador_b200 as lb
+    from labrador_b200 import synth
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    N = R = int(os.environ.get("LAB_BENCH_PROVE_N", "32"))
+    ctx = lb.Context(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.tensor(list(lb.Context.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        ctx.comm_init(bytes(uid.cpu().tolist()), rank, world)
+    c = lb.RuntimeConstants.new(N, R)
+    S = synth.generate_witness(N, R, c.BETA_BOUND, PRG_SEED)
+    st = lb.State.new(S, c, PRG_SEED, ctx)
+    ver = lb.Verifier.new(st.b_prime_k, c, seed=PRG_SEED, n_attempts=6)
+    prover = lb.Prover.new(S, ver, c, ctx)
+    crs = lb.CRS.from_seed(c, SEED32, ctx)
+
+    def barrier():
+        ctx.sync(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+    for _ in range(max(2, min(args.warmup, 2))):
+        tr = prover.proof_gen(st, crs)
+    d = tr.as_oracle_dict()
+    ctx.verify(c, SEED32, st.phi_k[0], st.a_k[0], st.b_k[0], ver.challenges, d)
+    barrier()
+
+    def timed():
+        tp, tv = [], []
+        for _ in range(args.steps):
+            barrier()
+            t0 = time.perf_counter(); trx = prover.proof_gen(st, crs); tp.append(time.perf_counter() - t0)
+            barrier()
+            t0 = time.perf_counter(); ok = ctx.verify(c, SEED32, st.phi_k[0], st.a_k[0], st.b_k[0], ver.challenges, d); tv.append(time.perf_counter() - t0)
+        return trx, ok, sum(tp) / len(tp), sum(tv) / len(tv)
+    l0 = ctx.kernel_launches
+    (trx, ok, tp, tv), clocks = _clock_wrap(local_rank, timed)
+    launches = ctx.kernel_launches - l0
+    t = torch.tensor([tp, tv], dtype=torch.float64, device=dev)
+    import hashlib
+    dig = hashlib.sha256(b"".join(np.ascontiguousarray(trx.as_oracle_dict()[k]).tobytes() for k in ("t", "g", "u_1", "h", "u_2", "z"))).digest()
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # every rank must hold the same transcript: compare digests
+        dt = torch.tensor(list(dig), dtype=torch.uint8, device=dev)
+        d0 = dt.clone(); dist.broadcast(d0, 0)
+        same = torch.tensor([int(torch.equal(dt, d0))], device=dev); dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        if int(same.item()) != 1:
+            raise SystemExit("ranks disagree on the transcript")
+    tp, tv = float(t[0].item()), float(t[1].item())
+    if not ok[0]:
+        raise SystemExit(f"verifier rejected at check {ok[1]}")
+    npairs = R * (R + 1) // 2
+    blocks = (c.R * c.T_1 * c.KAPPA_1 * c.KAPPA + c.KAPPA * c.N + npairs * (c.T_1 + c.T_2) * c.KAPPA_2) * 64
+    alu = ctx.alu_peak()
+    line = {"metric": "witness_coeffs_per_s", "value": N * R * D / tp, "unit": "coeffs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": tp * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32 (exact integer arithmetic mod 8191; int64 JL accumulation)", "data": "synthetic",
+            "config": {"workload": "prove", "N": N, "R": R, "kappa": c.KAPPA, "T_1": c.T_1, "T_2": c.T_2,
+                       "stages": "whole Prover::proof_gen (S1-S10) through lab_prove with host buffers; verify timed separately",
+                       "parallelism": f"rows of A, u_1, u_2 sharded over {world} rank(s); in-place NCCL all-gathers inside the library",
+                       "l2": "CRS regenerated every proof (2^35.6 ChaCha20 blocks); nothing to cache"},
+            "e2e": {"value": N * R * D / tp, "unit": "coeffs/s", "h2d_bytes_per_step": int(2 * S.nbytes + ver.challenges["pi"].nbytes // max(1, ver.challenges["pi"].shape[0])),
+                    "d2h_bytes_per_step": int(R * c.KAPPA * 256 + 2 * c.KAPPA * 256), "note": "lab_prove takes host buffers: the timed call IS the end-to-end path"},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"kernel": "k_crs_matvec", "bound": "int32_alu", "achieved": blocks / world * ALU_OPS_PER_BLOCK / tp / 1e9, "peak": alu / 1e9, "unit": "Gop/s",
+                         "frac": blocks / world * ALU_OPS_PER_BLOCK / tp / alu, "traffic": None,
+                         "note": "per-GPU share of the proof's CRS coefficients x 596 ALU ops over the whole prove() wall time"},
+            "cpu_baseline": None,
+            "extra": {"prove_ms": tp * 1e3, "verify_ms": tv * 1e3, "verify_accepts": bool(ok[0]), "crs_coefficients_per_proof": blocks,
+                      "chacha_blocks_per_s_whole_job": blocks / tp,
+                      "transcript_sha256": dig.hex() + " (t, g, u_1, h, u_2, z; equal on all ranks and for every number of GPUs)"}}
+    _finish_line(line, rank, world)
+    if world > 1:
+        ctx.comm_destroy()
+        dist.destroy_process_group()
+    ctx.close()
+
+
 def run_cfg5(args, rank, world, local_rank):
     """BASELINE config 5: 1024 independent default-size statements, sharded over ranks (no collective on the data path)."""
     import numpy as np
@@ -429,8 +519,8 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
-    if args.workload in ("cfg1", "cfg2", "cfg5"):
-        {"cfg1": run_cfg1, "cfg2": run_cfg2, "cfg5": run_cfg5}[args.workload](args, rank, world, local_rank)
+    if args.workload in ("cfg1", "cfg2", "cfg5", "prove"):
+        {"cfg1": run_cfg1, "cfg2": run_cfg2, "cfg5": run_cfg5, "prove": run_prove}[args.workload](args, rank, world, local_rank)
         return
 
     import numpy as np

@@ -77,6 +77,19 @@ int lab_version(void);
 int lab_timer_start(lab_ctx *ctx);
 int lab_timer_stop(lab_ctx *ctx, double *elapsed_ms);     /* synchronises on the stop event */
 
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink (the reference's only parallelism is rayon, proofgen.rs:101-124) ----
+ * Rank 0 calls lab_comm_unique_id and the HOST distributes the 128 bytes by its own means (MPI, a socket,
+ * torch.distributed ...); every rank then attaches its ctx with lab_comm_init (collective).  From then on lab_prove and
+ * lab_verify, called by all ranks with identical arguments, shard the CRS-regenerating stages by output rows --
+ * rows of A for the inner commitments t_i (proofgen.rs:41-49) and for A z (verification.rs:274-279), rows of u_1
+ * (proofgen.rs:101-153) and u_2 (proofgen.rs:364-378) -- and complete them with in-place all-gathers on the ctx stream;
+ * every rank returns the same transcript.  Row counts the communicator size does not divide are computed unsharded.
+ * libnccl.so.2 is resolved at run time; without it these three calls fail and everything else works. */
+#define LAB_COMM_ID_BYTES 128
+int lab_comm_unique_id(uint8_t id[LAB_COMM_ID_BYTES]);
+int lab_comm_init(lab_ctx *ctx, const uint8_t id[LAB_COMM_ID_BYTES], int rank, int world);
+int lab_comm_destroy(lab_ctx *ctx);
+
 /* RuntimeConstants::new(N, R)  (constants.rs:234-264). Returns LAB_ERR_PARAMS (and fills out,
  * degenerate = 1) where the reference's formulas leave the range in which it terminates. */
 int lab_runtime_constants(uint64_t N, uint64_t R, lab_constants *out);

@@ -11,6 +11,8 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <dlfcn.h>
+#include <nccl.h>      // types and prototypes only: libnccl.so.2 is opened lazily (lab_comm_*), never linked
 
 using namespace lab;
 typedef unsigned __int128 u128;
@@ -46,6 +48,10 @@ struct lab_ctx {
     // worker contexts (own stream + arena each) for lab_prove_batch: independent statements overlap host-side
     // enqueueing of one proof with the GPU work of the others
     std::vector<lab_ctx *> workers;
+    // multi-GPU (one process per GPU): NCCL communicator attached with lab_comm_init; lab_prove / lab_verify then
+    // shard the CRS-regenerating stages by output rows and complete them with in-place all-gathers on the ctx stream
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
 };
 
 #define CK(call)                                                                                     \
@@ -188,6 +194,7 @@ extern "C" void lab_ctx_destroy(lab_ctx *ctx) {
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
     for (auto &p : ctx->mv_plans) cudaFree(p.dev);
     for (lab_ctx *w : ctx->workers) lab_ctx_destroy(w);
+    lab_comm_destroy(ctx);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -223,6 +230,110 @@ extern "C" int lab_timer_stop(lab_ctx *ctx, double *elapsed_ms) {
 }
 extern "C" void *lab_stream(lab_ctx *ctx) { return (void *)ctx->stream; }
 extern "C" uint64_t lab_kernel_launches(const lab_ctx *ctx) { return ctx->launches; }
+
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU communicator: NCCL over NVLink, one process per GPU.  libnccl.so.2 is resolved at run time (the copy
+// the host process already has loaded, e.g. PyTorch's, or the system one), so the library has no link-time dependency.
+// ---------------------------------------------------------------------------------------------
+struct LabNccl {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static LabNccl *nccl_api(std::string &err) {
+    static LabNccl api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) {
+            api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+            api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+            api.GroupStart = (decltype(api.GroupStart))dlsym(h, "ncclGroupStart");
+            api.GroupEnd = (decltype(api.GroupEnd))dlsym(h, "ncclGroupEnd");
+            api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+            if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.GroupStart && api.GroupEnd && api.GetErrorString) api.h = h;
+        }
+    }
+    if (!api.h) { err = "libnccl.so.2 not found or incomplete (needed only for lab_comm_*)"; return nullptr; }
+    return &api;
+}
+#define NCCLCK(call)                                                                                 \
+    do {                                                                                             \
+        ncclResult_t r_ = (call);                                                                    \
+        if (r_ != ncclSuccess) {                                                                     \
+            ctx->err = std::string(#call) + ": " + nc->GetErrorString(r_);                           \
+            return LAB_ERR_CUDA;                                                                     \
+        }                                                                                            \
+    } while (0)
+
+extern "C" int lab_comm_unique_id(uint8_t id[LAB_COMM_ID_BYTES]) {
+    std::string err;
+    LabNccl *nc = nccl_api(err);
+    if (!nc) { g_create_err = err; return LAB_ERR_CUDA; }
+    ncclUniqueId u;
+    static_assert(sizeof(ncclUniqueId) == LAB_COMM_ID_BYTES, "ncclUniqueId size");
+    if (nc->GetUniqueId(&u) != ncclSuccess) { g_create_err = "ncclGetUniqueId failed"; return LAB_ERR_CUDA; }
+    std::memcpy(id, &u, sizeof u);
+    return LAB_OK;
+}
+extern "C" int lab_comm_init(lab_ctx *ctx, const uint8_t id[LAB_COMM_ID_BYTES], int rank, int world) {
+    if (!ctx || !id || world < 1 || rank < 0 || rank >= world) { if (ctx) ctx->err = "lab_comm_init: bad arguments"; return LAB_ERR_PARAMS; }
+    if (ctx->comm) FAIL(LAB_ERR_PARAMS, "a communicator is already attached");
+    LabNccl *nc = nccl_api(ctx->err);
+    if (!nc) return LAB_ERR_CUDA;
+    cudaSetDevice(ctx->device);
+    ncclUniqueId u;
+    std::memcpy(&u, id, sizeof u);
+    NCCLCK(nc->CommInitRank(&ctx->comm, world, u, rank));
+    ctx->rank = rank;
+    ctx->world = world;
+    return LAB_OK;
+}
+extern "C" int lab_comm_destroy(lab_ctx *ctx) {
+    if (!ctx || !ctx->comm) return LAB_OK;
+    LabNccl *nc = nccl_api(ctx->err);
+    if (!nc) return LAB_ERR_CUDA;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    NCCLCK(nc->CommDestroy(ctx->comm));
+    ctx->comm = nullptr; ctx->rank = 0; ctx->world = 1;
+    return LAB_OK;
+}
+// this rank's share [x0, x0 + nx) of `total` output rows: an equal slice when the communicator's size divides it,
+// otherwise (and without a communicator) everything -- then every rank computes all rows and nothing is exchanged
+static bool shard_rows(const lab_ctx *ctx, uint64_t total, uint64_t *x0, uint64_t *nx) {
+    if (ctx->comm && ctx->world > 1 && total % (uint64_t)ctx->world == 0) {
+        *nx = total / (uint64_t)ctx->world;
+        *x0 = *nx * (uint64_t)ctx->rank;
+        return true;
+    }
+    *x0 = 0; *nx = total;
+    return false;
+}
+// in-place all-gather of row slices: `blocks` arrays of `total_rows` rows each (block b at buf + b * block_stride words),
+// every rank having filled rows [rank * total_rows / world, ...) of every block
+static int allgather_rows(lab_ctx *ctx, uint32_t *buf, uint64_t blocks, uint64_t block_stride_words, uint64_t total_rows, uint64_t words_per_row) {
+    LabNccl *nc = nccl_api(ctx->err);
+    if (!nc) return LAB_ERR_CUDA;
+    const uint64_t nx = total_rows / (uint64_t)ctx->world, cnt = nx * words_per_row;
+    NCCLCK(nc->GroupStart());
+    for (uint64_t b = 0; b < blocks; b++) {
+        uint32_t *base = buf + b * block_stride_words;
+        NCCLCK(nc->AllGather(base + (uint64_t)ctx->rank * cnt, base, cnt, ncclUint32, ctx->comm, ctx->stream));
+    }
+    NCCLCK(nc->GroupEnd());
+    return LAB_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // RuntimeConstants::new (constants.rs:234-264): same f64 operation order, `as i128` saturating casts
@@ -300,7 +411,9 @@ static int d_inv_hat(lab_ctx *ctx, const uint32_t *in, uint32_t *out, size_t n) 
     LAUNCH(k_inv_hat, grid_for(n, 8, ctx->sms * 16), 256, in, out, n);
     return LAB_OK;
 }
-static int d_commit_inner(lab_ctx *ctx, const LabSeed &seed, const uint32_t *What, uint64_t N, uint64_t R, uint64_t row0, uint64_t nrows, uint32_t *T) {
+static int d_commit_inner(lab_ctx *ctx, const LabSeed &seed, const uint32_t *What, uint64_t N, uint64_t R, uint64_t row0, uint64_t nrows, uint32_t *T,
+                          uint64_t t_stride = 0, uint64_t t_row_off = 0) {
+    if (!t_stride) t_stride = nrows;            // default: T is exactly [R][nrows][64]
     if (!nrows) return LAB_OK;
     if (N >= (1ull << 32) || R >= (1ull << 32)) FAIL(LAB_ERR_PARAMS, "N, R must be < 2^32");
     {   // counters of A stay below 2^64 (structs.rs:62): (row * N + n) * 64
@@ -312,11 +425,11 @@ static int d_commit_inner(lab_ctx *ctx, const LabSeed &seed, const uint32_t *Wha
     const int IC = R > 32 ? 16 : (R > 16 ? 8 : (R > 8 ? 4 : (R > 4 ? 2 : 1)));
     for (uint64_t ib = 0; ib < R; ib += (uint64_t)KA_CONS * IC) {
         switch (IC) {
-            case 16: LAUNCH_SMEM((k_commit_inner<16, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, 16), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
-            case 8: LAUNCH_SMEM((k_commit_inner<8, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, 8), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
-            case 4: LAUNCH_SMEM((k_commit_inner<4, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, 4), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
-            case 2: LAUNCH_SMEM((k_commit_inner<2, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, 2), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
-            default: LAUNCH_SMEM((k_commit_inner<1, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, 1), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T); break;
+            case 16: LAUNCH_SMEM((k_commit_inner<16, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, 16), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T, t_stride, t_row_off); break;
+            case 8: LAUNCH_SMEM((k_commit_inner<8, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, 8), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T, t_stride, t_row_off); break;
+            case 4: LAUNCH_SMEM((k_commit_inner<4, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, 4), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T, t_stride, t_row_off); break;
+            case 2: LAUNCH_SMEM((k_commit_inner<2, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, 2), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T, t_stride, t_row_off); break;
+            default: LAUNCH_SMEM((k_commit_inner<1, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, 1), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T, t_stride, t_row_off); break;
         }
     }
     return LAB_OK;
@@ -385,7 +498,9 @@ __global__ void k_gather_pairs(const uint32_t *__restrict__ M, uint32_t R, uint3
 }
 
 // u_1 (proofgen.rs:101-153) from device T [R][KAPPA][64] and G [R][R][64]
-static int d_outer_u1(lab_ctx *ctx, const lab_constants *c, const LabSeed &seed, const uint32_t *dT, const uint32_t *dG, uint32_t *du1) {
+// rows [x0, x0 + nx) only; du1 points at row 0 of the full u_1
+static int d_outer_u1(lab_ctx *ctx, const lab_constants *c, const LabSeed &seed, const uint32_t *dT, const uint32_t *dG, uint32_t *du1,
+                      uint64_t x0 = 0, uint64_t nx = ~0ull) {
     const uint64_t R = c->R, K = c->KAPPA, K1 = c->KAPPA_1, K2 = c->KAPPA_2, T1 = (uint64_t)c->T_1, T2 = (uint64_t)c->T_2;
     const uint64_t npairs = R * (R + 1) / 2;
     if (R * T1 * K + npairs * T2 >= (1ull << 32)) FAIL(LAB_ERR_PARAMS, "u_1 vector too long for 32-bit indexing");
@@ -400,10 +515,12 @@ static int d_outer_u1(lab_ctx *ctx, const lab_constants *c, const LabSeed &seed,
         for (uint64_t k = 0; k < T1; k++)
             segs.push_back(MvSeg{off_B(c, i, k, 0), K * LAB_D, LAB_D, 0, 1u, (uint32_t)K, (uint32_t)((i * T1 + k) * K)});
     segs.push_back(MvSeg{off_C(c, 0, 0, 0), LAB_D, T1 * K2 * LAB_D, K2 * LAB_D, (uint32_t)T2, (uint32_t)(npairs * T2), (uint32_t)(R * T1 * K)});
-    return d_crs_matvec(ctx, seed, segs, 0, K1, V, du1);
+    if (nx == ~0ull) nx = K1;
+    return d_crs_matvec(ctx, seed, segs, x0, nx, V, du1 + x0 * 64);
 }
 // u_2 (proofgen.rs:364-378) from device H [R][R][64]
-static int d_outer_u2(lab_ctx *ctx, const lab_constants *c, const LabSeed &seed, const uint32_t *dH, uint32_t *du2) {
+static int d_outer_u2(lab_ctx *ctx, const lab_constants *c, const LabSeed &seed, const uint32_t *dH, uint32_t *du2,
+                      uint64_t x0 = 0, uint64_t nx = ~0ull) {
     const uint64_t R = c->R, K2 = c->KAPPA_2, T1 = (uint64_t)c->T_1;
     const uint64_t npairs = R * (R + 1) / 2;
     uint32_t *V, *Hp;
@@ -413,7 +530,8 @@ static int d_outer_u2(lab_ctx *ctx, const lab_constants *c, const LabSeed &seed,
     LAUNCH(k_decomp_fwd, grid_for(npairs, 8, ctx->sms * 16), 256, Hp, V, (size_t)npairs, (size_t)1, (uint32_t)c->B_1, (int)T1);
     std::vector<MvSeg> segs;
     segs.push_back(MvSeg{off_D(c, 0, 0, 0), LAB_D, T1 * K2 * LAB_D, K2 * LAB_D, (uint32_t)T1, (uint32_t)(npairs * T1), 0u});
-    return d_crs_matvec(ctx, seed, segs, 0, K2, V, du2);
+    if (nx == ~0ull) nx = K2;
+    return d_crs_matvec(ctx, seed, segs, x0, nx, V, du2 + x0 * 64);
 }
 // rows i in [i0, i0+ni) of g: dG is [ni][R][64]
 static int d_gram(lab_ctx *ctx, const uint32_t *What, uint64_t N, uint64_t R, uint64_t i0, uint64_t ni, uint32_t *Ghat /* scratch ni*R*32 */, uint32_t *dG) {
@@ -786,7 +904,12 @@ static int prove_one(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_by
     TRACE("jl accepted");
     // S1: inner commitments (proofgen.rs:35-49)
     TRY(arena_alloc(ctx, R * K * 64, &dT));
-    TRY(d_commit_inner(ctx, seed, What, N, R, 0, K, dT));
+    {   // with a communicator: this rank regenerates only its rows of A; T is completed in place by R grouped all-gathers
+        uint64_t x0, nx;
+        const bool sharded = shard_rows(ctx, K, &x0, &nx);
+        TRY(d_commit_inner(ctx, seed, What, N, R, x0, nx, dT, K, x0));
+        if (sharded) TRY(allgather_rows(ctx, dT, R, K * 64, K, 64));
+    }
     // S2: g (proofgen.rs:59-70)
     uint32_t *Ghat, *dG;
     TRY(arena_alloc(ctx, R * R * 32, &Ghat));
@@ -795,7 +918,12 @@ static int prove_one(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_by
     // S3: u_1 (proofgen.rs:101-153)
     uint32_t *du1;
     TRY(arena_alloc(ctx, K1 * 64, &du1));
-    TRY(d_outer_u1(ctx, c, seed, dT, dG, du1));
+    {
+        uint64_t x0, nx;
+        const bool sharded = shard_rows(ctx, K1, &x0, &nx);
+        TRY(d_outer_u1(ctx, c, seed, dT, dG, du1, x0, nx));
+        if (sharded) TRY(allgather_rows(ctx, du1, 1, 0, K1, 64));
+    }
     TRACE("u1 enqueued");
     // S9: z (proofgen.rs:380-399) -- independent of the JL outcome, enqueued first
     uint32_t *Chat, *zhat, *dz;
@@ -847,7 +975,12 @@ static int prove_one(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_by
         // S7: h (proofgen.rs:320-358)
         TRY(d_h_gram(ctx, PFhat, What, N, R, Hhat, dH));
         // S8: u_2 (proofgen.rs:364-378)
-        TRY(d_outer_u2(ctx, c, seed, dH, du2));
+        {
+            uint64_t x0, nx;
+            const bool sharded = shard_rows(ctx, K2, &x0, &nx);
+            TRY(d_outer_u2(ctx, c, seed, dH, du2, x0, nx));
+            if (sharded) TRY(allgather_rows(ctx, du2, 1, 0, K2, 64));
+        }
         // exact integer of Check 14 (verification.rs:185-267): digits of z (B, 2), t (B_1, T_1), all g (B_2, T_2), all h (B_1, T_1)
         CK(cudaMemsetAsync(dnorm, 0, sizeof *dnorm, ctx->stream));
         LAUNCH(k_digit_norm_sq, grid_for(N * 64, 2048, ctx->sms * 8), 256, dz, (size_t)(N * 64), (uint32_t)c->B, 2, dnorm);
@@ -992,7 +1125,12 @@ extern "C" int lab_verify(lab_ctx *ctx, const lab_constants *c, const uint8_t se
         TRY(arena_alloc(ctx, K * 64, &lhs));
         TRY(arena_alloc(ctx, K * 32, &rhs_h));
         TRY(arena_alloc(ctx, K * 64, &rhs));
-        TRY(d_commit_inner(ctx, seed, zhat, N, 1, 0, K, lhs));
+        {
+            uint64_t x0, nx;
+            const bool sharded = shard_rows(ctx, K, &x0, &nx);
+            TRY(d_commit_inner(ctx, seed, zhat, N, 1, x0, nx, lhs, K, x0));
+            if (sharded) TRY(allgather_rows(ctx, lhs, 1, 0, K, 64));
+        }
         TRY(d_amortize(ctx, Chat, That, K, R, 0, R, rhs_h, rhs));
         TRY(dev_equal(ctx, lhs, rhs, K * 64, dcnt, &eq));
         if (!eq) fc = 15;
@@ -1053,14 +1191,24 @@ extern "C" int lab_verify(lab_ctx *ctx, const lab_constants *c, const uint8_t se
     if (!fc) {   // check 19: u_1 (verification.rs:372-415)
         uint32_t *cand;
         TRY(arena_alloc(ctx, K1 * 64, &cand));
-        TRY(d_outer_u1(ctx, c, seed, dT, dG, cand));
+        {
+            uint64_t x0, nx;
+            const bool sharded = shard_rows(ctx, K1, &x0, &nx);
+            TRY(d_outer_u1(ctx, c, seed, dT, dG, cand, x0, nx));
+            if (sharded) TRY(allgather_rows(ctx, cand, 1, 0, K1, 64));
+        }
         TRY(dev_equal(ctx, cand, du1, K1 * 64, dcnt, &eq));
         if (!eq) fc = 19;
     }
     if (!fc) {   // check 20: u_2 (verification.rs:421-435)
         uint32_t *cand;
         TRY(arena_alloc(ctx, K2 * 64, &cand));
-        TRY(d_outer_u2(ctx, c, seed, dH, cand));
+        {
+            uint64_t x0, nx;
+            const bool sharded = shard_rows(ctx, K2, &x0, &nx);
+            TRY(d_outer_u2(ctx, c, seed, dH, cand, x0, nx));
+            if (sharded) TRY(allgather_rows(ctx, cand, 1, 0, K2, 64));
+        }
         TRY(dev_equal(ctx, cand, du2, K2 * 64, dcnt, &eq));
         if (!eq) fc = 20;
     }

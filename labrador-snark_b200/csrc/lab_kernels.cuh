@@ -518,7 +518,8 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
 
 template <int IC, uint32_t RM, int PP>
 __global__ void __launch_bounds__(ka_threads(PP), 1) k_commit_inner(LabSeed seed, const uint32_t *__restrict__ What, uint32_t N, uint32_t R,
-                                                                     uint64_t row0, uint64_t nrows, uint32_t i_base, uint32_t *__restrict__ T) {
+                                                                     uint64_t row0, uint64_t nrows, uint32_t i_base, uint32_t *__restrict__ T,
+                                                                     uint64_t t_stride, uint64_t t_row_off) {
     constexpr int PROD = ka_prod(PP), COLS = ka_cols(PP), TP = PROD * PP, THREADS = ka_threads(PP), NB = 2 * PP;
     __shared__ uint32_t Are[KA_DEPTH][TP][32], Aim[KA_DEPTH][TP][32], Anim[KA_DEPTH][TP][32];   // re, im, Q - im; polynomial col * 4 + row
     __shared__ uint64_t empty_bar[KA_DEPTH];                     // consumers -> producers: slot may be overwritten
@@ -679,7 +680,8 @@ __global__ void __launch_bounds__(ka_threads(PP), 1) k_commit_inner(LabSeed seed
                     for (int ii = 0; ii < IC; ii++) { accr[r][ii] = lab_fold(accr[r][ii]); acci[r][ii] = lab_fold(acci[r][ii]); }
             }
         }
-        // inverse transform and store T[i][row][.]  (T is [R][nrows][64])
+        // inverse transform and store T[i][t_row_off + row][.]  (T is [R][t_stride][64]; a row shard of a multi-GPU proof
+        // writes its rows straight into the full T that the all-gather completes in place)
         const LabWarpTw tw = lab_warp_tw(lane);
 #pragma unroll
         for (int ii = 0; ii < IC; ii++)
@@ -689,7 +691,7 @@ __global__ void __launch_bounds__(ka_threads(PP), 1) k_commit_inner(LabSeed seed
                 lab_ntt32_inv_warp(re, im, tw, lane);
                 const uint32_t i = i0 + ii;
                 if (rblk + r < nrows && i < R) {
-                    uint32_t *dst = T + ((size_t)i * nrows + rblk + r) * 64;
+                    uint32_t *dst = T + ((size_t)i * t_stride + t_row_off + rblk + r) * 64;
                     dst[lane] = re;
                     dst[lane + 32] = im;
                 }

@@ -87,6 +87,27 @@ class Context:
         self._ck(self.L.lab_timer_stop(self._h, C.byref(ms)))
         return ms.value
 
+    # ---- multi-GPU: NCCL communicator inside the library (lab_comm_*) ----
+    @staticmethod
+    def comm_unique_id():
+        """128 bytes that rank 0 generates and the host distributes to all ranks (any transport)."""
+        buf = (C.c_uint8 * 128)()
+        L = _lib.lib()
+        rc = L.lab_comm_unique_id(buf)
+        if rc != 0:
+            raise LabError(rc, L.lab_last_error(None).decode())
+        return bytes(buf)
+
+    def comm_init(self, uid, rank, world):
+        """Collective.  Afterwards proof_gen / verify called by all ranks with the same arguments shard the
+        CRS-regenerating stages by rows and all-gather them over NVLink; every rank gets the same transcript."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(uid))
+        self._ck(self.L.lab_comm_init(self._h, buf, C.c_int(rank), C.c_int(world)))
+        self.rank, self.world = rank, world
+
+    def comm_destroy(self):
+        self._ck(self.L.lab_comm_destroy(self._h))
+
     # ---- device-pointer entry points (inputs resident in HBM) ----
     def ntt_fwd_batch_dev(self, din, dout, n):
         self._ck(self.L.lab_ntt_fwd_batch_dev(self._h, C.c_void_p(din), C.c_void_p(dout), C.c_size_t(n)))

@@ -147,7 +147,7 @@ static void bench_commit(Timer &tm, const LabSeed &seed, const uint32_t *What, u
     const unsigned grid = (unsigned)((rows + KA_RT - 1) / KA_RT);
     CK(cudaFuncSetAttribute(k_commit_inner<16, RM, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ka_dyn_smem(PP, 16)));
     auto launch = [&] {
-        for (uint32_t ib = 0; ib < R; ib += KA_CONS * 16) k_commit_inner<16, RM, PP><<<grid, ka_threads(PP), ka_dyn_smem(PP, 16)>>>(seed, What, N, R, 0ull, rows, ib, T);
+        for (uint32_t ib = 0; ib < R; ib += KA_CONS * 16) k_commit_inner<16, RM, PP><<<grid, ka_threads(PP), ka_dyn_smem(PP, 16)>>>(seed, What, N, R, 0ull, rows, ib, T, rows, 0ull);
     };
     float ms = tm.run(launch, 2);
     CK(cudaGetLastError());

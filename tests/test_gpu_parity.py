@@ -138,6 +138,45 @@ def test_crs_fetch_offsets(ctx, orc):
     assert np.array_equal(crs.fetch_D_ijk(0, 2, 3), orc.fetch_D_ijk(co, SEED32, 0, 2, 3))
 
 
+def test_crs_32bit_boundary_of_seed_plus_counter(ctx, orc):
+    """The trimmed ChaCha20 path hoists everything that depends only on key words 0..6; key word 6 changes when the low
+    32 bits of seed + counter wrap.  Seeds chosen so that this happens (without a 64-bit carry) inside polynomial 5 of A,
+    inside a B_ik row and inside a plain expansion: lanes before the wrap use the hoisted state, lanes after it the
+    generic path, the next polynomial a recomputed hoist."""
+    N, R = 4, 2
+    low = (5 << 32) + (1 << 32) - 64 * 5 - 20
+    seed = bytes(range(7, 31)) + low.to_bytes(8, "big")
+    c = lb.RuntimeConstants.new(N, R)
+    co, _ = orc.constants(N, R)
+    S = synth.uniform_witness(N, R, seed=9)
+    assert np.array_equal(ctx.commit_inner(c, seed, S, 0, 8), orc.commit_inner_rows(co, seed, S, 0, 8))
+    assert np.array_equal(ctx.crs_expand(seed, 64 * 3, 6), orc.crs_polys(seed, 64 * 3, 6))
+    # u_1 walks B_ik / C_ijk far away from counter 0: put the wrap inside row 0 of B_00
+    crs = lb.CRS.from_seed(c, seed, ctx)
+    assert np.array_equal(crs.fetch_B_ik_row(0, 0, 0), orc.fetch_B_ik_row(co, seed, 0, 0, 0))
+    # u_1 for a seed whose wrap falls into the B region: low32(seed) + kappa*N*64 + 700 == 2^32
+    startB = c.KAPPA * N * 64
+    low2 = (9 << 32) + (1 << 32) - (startB % (1 << 32)) - 700
+    seed2 = bytes(range(3, 27)) + low2.to_bytes(8, "big")
+    Sw = orc.generate_witness(co, 9)
+    st_phi, st_a, st_b = orc.generate_state(co, Sw, 3)
+    ch = orc.sample_challenges(co, 11, 3)
+    rc, ref = orc.prove(co, seed2, Sw, st_phi, st_a, st_b, ch, ntt=True, nthreads=8)
+    assert rc == 0
+    assert np.array_equal(ctx.commit_outer_u1(c, seed2, ref["t"], ref["g"]), ref["u_1"])
+
+
+def test_crs_expand_hoist_cache_across_grid_stride_iterations(ctx, orc):
+    """2.6 M coefficients = more than one grid-stride sweep of k_crs_expand, starting 1.5 M before a 2^32 boundary of
+    seed + counter: threads refresh their hoisted state between iterations."""
+    low = (3 << 32) + (1 << 32) - 1_500_000
+    seed = bytes(range(11, 35)) + low.to_bytes(8, "big")
+    n = 40_000
+    got = ctx.crs_expand(seed, 0, n)
+    ref = orc.crs_polys(seed, 0, n)
+    assert np.array_equal(got, ref)
+
+
 # ---- stages ----
 @pytest.mark.parametrize("N,R", [(1, 1), (2, 2), (3, 5), (2, 9), (5, 17), (2, 40)])
 def test_commit_inner(ctx, orc, N, R):
@@ -322,3 +361,34 @@ def test_large_shape_sampled_rows(ctx, orc):
         assert np.array_equal(T, ref), row
     assert ctx.norm_sq_dev(dS, R * N * 64) == int((S.astype(np.uint64) ** 2).sum())
     ctx.free(dS); ctx.free(dT)
+
+
+def test_comm_single_rank_and_sharded_entry_points(ctx, orc):
+    """lab_comm_* with a one-rank NCCL communicator (the multi-rank row sharding itself is exercised by
+    `bench.py --workload prove` under torchrun, which checks that all ranks hold the same transcript digest as a
+    single-GPU run), and the row-range forms the sharding is built from."""
+    uid = lb.Context.comm_unique_id()
+    assert len(uid) == 128
+    c2 = lb.Context(0)
+    try:
+        c2.comm_init(uid, 0, 1)
+        N, R = 2, 2
+        c = lb.RuntimeConstants.new(N, R)
+        co, _ = orc.constants(N, R)
+        S = orc.generate_witness(co, 3)
+        phi, a, b = orc.generate_state(co, S, 3)
+        ch = orc.sample_challenges(co, 3, 2)
+        rc, ref = orc.prove(co, SEED32, S, phi, a, b, ch, ntt=True, nthreads=4)
+        assert rc == 0
+        st = lb.State(phi, a, b)
+        ver = lb.Verifier.new(st.b_prime_k, c, challenges=ch)
+        tr = lb.Prover.new(S, ver, c, c2).proof_gen(st, lb.CRS.from_seed(c, SEED32, c2)).as_oracle_dict()
+        for k in ("t", "g", "u_1", "h", "u_2", "z"):
+            assert np.array_equal(tr[k], ref[k]), k
+        c2.comm_destroy()
+    finally:
+        c2.close()
+    # row shards of T written with the destination stride of the full T, as the multi-GPU path does
+    Tfull = ctx.commit_inner(c, SEED32, S)
+    parts = [ctx.commit_inner(c, SEED32, S, row0=r0, nrows=32) for r0 in range(0, c.KAPPA, 32)]
+    assert np.array_equal(np.concatenate(parts, axis=1), Tfull)
