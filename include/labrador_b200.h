@@ -203,6 +203,16 @@ int lab_prove_batch(lab_ctx *ctx, const lab_constants *c, size_t n_statements, c
 int lab_verify(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], const lab_state *st, const lab_challenges *ch,
                const lab_transcript *tr, int *accepted, int *failed_check, uint64_t *norm_sum);
 
+/* ---- transcript wire format (structs.rs:192-221) ----
+ * The bytes `bincode::serialize(&Transcript)` produces in the reference (bincode 1.3.3 defaults: fixed-width little-endian
+ * integers, u64 sequence lengths): the 14 fields in declaration order; Rq = Vec<Zq> of the TRIMMED coefficients
+ * (algebraic.rs:422-429), Zq = i128 (16 bytes); Array2<T> (ndarray 0.15 serde) = u8 version 1, two u64 dims, then the
+ * elements as a row-major sequence; pi_i_all = the accepted JL attempt lifted to Z_q (-1 -> q-1, proofgen.rs:445-453);
+ * t_i_all = Vec<Vec<Rq>> [R][KAPPA]; psi/omega = one inner vector each (K = L = 1).  Pure host code, no ctx.
+ * Call with out == NULL to get the size.  Returns LAB_ERR_SHAPE when cap is too small. */
+int lab_transcript_bincode(const lab_constants *c, const lab_transcript *tr, const lab_challenges *ch,
+                           uint8_t *out, size_t cap, size_t *size);
+
 /* ---- device-resident stage API (inputs already in HBM; used for sharded / pipelined proving) ---- */
 /* S_dev: uint32_t[R][N][64] on device.  Prepares the transformed witness inside ctx. */
 int lab_witness_load_dev(lab_ctx *ctx, const lab_constants *c, const uint32_t *S_dev);

@@ -1250,6 +1250,70 @@ extern "C" int lab_prove_batch(lab_ctx *ctx, const lab_constants *c, size_t n_st
 }
 
 // ---------------------------------------------------------------------------------------------
+// transcript wire format: what bincode::serialize(&Transcript) emits in the reference (structs.rs:192-221)
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct BinWriter {
+    uint8_t *out;
+    size_t cap, pos = 0;
+    void raw(const void *p, size_t n) {
+        if (out && pos + n <= cap) std::memcpy(out + pos, p, n);
+        pos += n;
+    }
+    void u8(uint8_t v) { raw(&v, 1); }
+    void u64(uint64_t v) { raw(&v, 8); }                         // little-endian host assumed (x86-64 / aarch64)
+    void zq(uint32_t v) { uint64_t w[2] = {(uint64_t)(v % LAB_Q), 0}; raw(w, 16); }   // i128 of a canonical residue
+    void rq(const uint32_t *poly) {                               // Rq -> Vec<Zq> of the trimmed coefficients
+        int len = LAB_D;
+        while (len > 0 && poly[len - 1] % LAB_Q == 0) len--;
+        u64((uint64_t)len);
+        for (int d = 0; d < len; d++) zq(poly[d]);
+    }
+    void vec_rq(const uint32_t *polys, uint64_t n) {
+        u64(n);
+        for (uint64_t i = 0; i < n; i++) rq(polys + i * LAB_D);
+    }
+    void array2_header(uint64_t rows, uint64_t cols) { u8(1); u64(rows); u64(cols); u64(rows * cols); }
+};
+}  // namespace
+extern "C" int lab_transcript_bincode(const lab_constants *c, const lab_transcript *tr, const lab_challenges *ch, uint8_t *out, size_t cap, size_t *size) {
+    if (!c || !tr || !ch || !size) return LAB_ERR_PARAMS;
+    if (!tr->u_1 || !tr->projection || !tr->b_prime_prime || !tr->u_2 || !tr->z || !tr->t || !tr->g || !tr->h || !ch->pi || !ch->omega || !ch->alpha ||
+        !ch->beta || !ch->c || tr->jl_attempt < 0 || tr->jl_attempt >= ch->n_attempts)
+        return LAB_ERR_PARAMS;
+    const uint64_t R = c->R, N = c->N, K = c->KAPPA, ND = N * LAB_D;
+    BinWriter w{out, out ? cap : 0};
+    w.vec_rq(tr->u_1, c->KAPPA_1);                                                   // u_1: Vec<Rq>
+    w.u64(R);                                                                        // pi_i_all: Vec<Array2<Zq>>
+    const int8_t *pi = ch->pi + (size_t)tr->jl_attempt * R * LAB_JL_ROWS * ND;
+    for (uint64_t i = 0; i < R; i++) {
+        w.array2_header(LAB_JL_ROWS, ND);
+        const int8_t *p = pi + i * LAB_JL_ROWS * ND;
+        for (uint64_t e = 0; e < LAB_JL_ROWS * ND; e++) w.zq(p[e] < 0 ? LAB_Q - 1 : (uint32_t)p[e]);
+    }
+    w.u64(LAB_JL_ROWS);                                                              // projection: Vec<Zq>
+    for (int j = 0; j < LAB_JL_ROWS; j++) w.zq(tr->projection[j]);
+    w.u64(1); w.u64(1); w.zq(ch->psi);                                               // psi: Vec<Vec<Zq>> [1][L = 1]
+    w.u64(1); w.u64(LAB_JL_ROWS);                                                    // omega: [1][256]
+    for (int j = 0; j < LAB_JL_ROWS; j++) w.zq(ch->omega[j]);
+    w.vec_rq(tr->b_prime_prime, 1);                                                  // b_prime_prime, alpha, beta: Vec<Rq> of one
+    w.vec_rq(ch->alpha, 1);
+    w.vec_rq(ch->beta, 1);
+    w.vec_rq(tr->u_2, c->KAPPA_2);
+    w.vec_rq(ch->c, R);
+    w.vec_rq(tr->z, N);
+    w.u64(R);                                                                        // t_i_all: Vec<Vec<Rq>>
+    for (uint64_t i = 0; i < R; i++) w.vec_rq(tr->t + i * K * LAB_D, K);
+    w.array2_header(R, R);                                                           // g_mat, h_mat: Array2<Rq>
+    for (uint64_t e = 0; e < R * R; e++) w.rq(tr->g + e * LAB_D);
+    w.array2_header(R, R);
+    for (uint64_t e = 0; e < R * R; e++) w.rq(tr->h + e * LAB_D);
+    *size = w.pos;
+    if (out && w.pos > cap) return LAB_ERR_SHAPE;
+    return LAB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // device-resident stage API
 // ---------------------------------------------------------------------------------------------
 extern "C" int lab_witness_load_dev(lab_ctx *ctx, const lab_constants *c, const uint32_t *S_dev) {

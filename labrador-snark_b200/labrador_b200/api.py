@@ -340,6 +340,29 @@ class Context:
         return outs
 
 
+def transcript_bincode(c, tr, ch, jl_attempt=None):
+    """tr: oracle-layout transcript dict; ch: challenges dict (pi [attempts][R][256][N*64]).  Host-only: needs no GPU."""
+    L = _lib.lib()
+    pi = np.ascontiguousarray(ch["pi"], dtype=np.int8)
+    if pi.ndim == 3:
+        pi = pi[None]
+    omega, alpha, beta, cc = _u32(ch["omega"]), _u32(ch["alpha"]), _u32(ch["beta"]), _u32(ch["c"])
+    keep = {k: _u32(tr[k]) for k in ("u_1", "projection", "b_prime_prime", "u_2", "z", "t", "g", "h")}
+    att = int(tr.get("jl_attempt", 0)) if jl_attempt is None else jl_attempt
+    cch = _lib.CChallenges(_p(pi), pi.shape[0], int(ch["psi"]), _p(omega), _p(alpha), _p(beta), _p(cc))
+    ctr = _lib.CTranscript(_p(keep["u_1"]), att, None, _p(keep["projection"]), _p(keep["b_prime_prime"]),
+                           _p(keep["u_2"]), _p(keep["z"]), _p(keep["t"]), _p(keep["g"]), _p(keep["h"]), None, 0)
+    size = C.c_size_t(0)
+    rc = L.lab_transcript_bincode(C.byref(c), C.byref(ctr), C.byref(cch), None, C.c_size_t(0), C.byref(size))
+    if rc != 0:
+        raise LabError(rc, "lab_transcript_bincode: bad arguments")
+    buf = np.empty(size.value, np.uint8)
+    rc = L.lab_transcript_bincode(C.byref(c), C.byref(ctr), C.byref(cch), _p(buf), C.c_size_t(buf.size), C.byref(size))
+    if rc != 0:
+        raise LabError(rc, "lab_transcript_bincode failed")
+    return buf.tobytes()
+
+
 _default_ctx = None
 
 
@@ -459,6 +482,12 @@ class Transcript:
     def pi_i_all(self):
         pi = self.pi_accepted.astype(np.int32)
         return np.where(pi < 0, pi + Q, pi).astype(np.uint32)
+
+    def to_bincode(self, constants):
+        """bincode::serialize(&Transcript) of the reference (structs.rs:192-221), byte for byte (lab_transcript_bincode)."""
+        return transcript_bincode(constants, self.as_oracle_dict(),
+                                  {"pi": self.pi_accepted[None], "psi": self.psi[0][0], "omega": self.omega[0], "alpha": self.alpha[0],
+                                   "beta": self.beta[0], "c": self.c}, jl_attempt=0)
 
     def as_oracle_dict(self):
         return {"u_1": self.u_1, "projection_int": self.projection_int, "projection": self.projection,

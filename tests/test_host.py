@@ -160,3 +160,80 @@ def test_shard_plan_covers_everything():
             assert parts[0][0] == 0 and sum(n for _, n in parts) == total
             for (s0, n0), (s1, _) in zip(parts, parts[1:]):
                 assert s0 + n0 == s1
+
+
+# ---- transcript wire format (structs.rs:192-221) ----
+def _bincode_reference(c, tr, ch, att):
+    """Independent restatement with struct.pack of what serde + bincode 1.3.3 (fixint, little endian) emit for the
+    reference's #[derive(Serialize)] Transcript: fields in declaration order, Vec = u64 length + items, Zq = i128,
+    Rq = Vec<Zq> of the trimmed coefficients (algebraic.rs:422-429), ndarray Array2 = {v: u8 = 1, dim: (u64, u64), data: seq}."""
+    import struct
+    out = bytearray()
+
+    def u64(v): out.extend(struct.pack("<Q", v))
+    def zq(v): out.extend(struct.pack("<QQ", int(v) % Q, 0))
+
+    def rq(p):
+        p = [int(x) % Q for x in p]
+        while p and p[-1] == 0:
+            p.pop()
+        u64(len(p))
+        for x in p:
+            zq(x)
+
+    def vec_rq(ps):
+        u64(len(ps))
+        for p in ps:
+            rq(p)
+
+    def arr2_hdr(r, cc):
+        out.append(1); u64(r); u64(cc); u64(r * cc)
+    R, N, K = c.R, c.N, c.KAPPA
+    vec_rq(tr["u_1"])
+    u64(R)
+    for i in range(R):
+        arr2_hdr(256, N * 64)
+        for v in np.asarray(ch["pi"][att][i]).reshape(-1):
+            zq(Q - 1 if v < 0 else v)
+    u64(256)
+    for v in tr["projection"]:
+        zq(v)
+    u64(1); u64(1); zq(ch["psi"])
+    u64(1); u64(256)
+    for v in ch["omega"]:
+        zq(v)
+    vec_rq([tr["b_prime_prime"]]); vec_rq([ch["alpha"]]); vec_rq([ch["beta"]])
+    vec_rq(tr["u_2"]); vec_rq(ch["c"]); vec_rq(tr["z"])
+    u64(R)
+    for i in range(R):
+        vec_rq(tr["t"][i])
+    for M in (tr["g"], tr["h"]):
+        arr2_hdr(R, R)
+        for i in range(R):
+            for j in range(R):
+                rq(M[i][j])
+    return bytes(out)
+
+
+def test_transcript_bincode_matches_independent_packer(orc):
+    from labrador_b200.api import transcript_bincode
+    N, R = 1, 2
+    c = lb.RuntimeConstants.new(N, R)
+    co, _ = orc.constants(N, R)
+    S = orc.generate_witness(co, 5)
+    phi, a, b = orc.generate_state(co, S, 5)
+    ch = orc.sample_challenges(co, 5, 2)
+    rc, tr = orc.prove(co, bytes(range(32)), S, phi, a, b, ch, ntt=True, nthreads=4)
+    assert rc == 0
+    tr = dict(tr)
+    tr["z"] = np.array(tr["z"], copy=True)
+    tr["z"][0, 40:] = 0                      # a polynomial with trailing zeros: must be trimmed to 40 coefficients
+    tr["u_2"] = np.array(tr["u_2"], copy=True)
+    tr["u_2"][3] = 0                         # the zero polynomial serialises as an empty Vec (algebraic.rs:431-439)
+    att = int(tr.get("jl_attempt", 0))
+    got = transcript_bincode(c, tr, ch)
+    ref = _bincode_reference(c, tr, ch, att)
+    assert len(got) == len(ref)
+    assert got == ref
+    # size: every Zq is 16 bytes; Pi dominates (R * 256 * N*64 entries)
+    assert len(got) > R * 256 * N * 64 * 16
