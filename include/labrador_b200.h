@@ -234,6 +234,18 @@ int lab_amortize_z_dev(lab_ctx *ctx, const uint32_t *ch_dev, uint64_t i0, uint64
  * entry from stream 5 + (attempt << 8), row-major fill order. */
 int lab_synth_zq_dev(lab_ctx *ctx, uint64_t seed, uint64_t stream, uint64_t start, size_t n, uint32_t *out_dev);
 int lab_synth_pi_dev(lab_ctx *ctx, uint64_t seed, uint64_t attempt, uint64_t first_entry /* multiple of 32 */, size_t total, int8_t *out_dev);
+/* Verifier::fetch_challenge (verification.rs:460-489) on the device, seeded: challenge polynomials first_idx ..
+ * first_idx + count - 1 into c_dev [count][64]; streams 10 / 11 + (idx << 8) for the draws without replacement from
+ * {0 x23, 1 x31, 2 x10} with random signs (util.rs:83-104) and for the 1000 operator-norm samples (util.rs:227-246,
+ * threshold T = 15, the reference's f64 ratio).  candidates_dev (nullable): uint32[count], candidates tried. */
+int lab_sample_challenge_polys_dev(lab_ctx *ctx, uint64_t seed, uint32_t first_idx, uint32_t count, uint32_t *c_dev, uint32_t *candidates_dev);
+/* generate_witness (proofgen.rs:460-518) on the device, seeded: uniform coefficients (stream 1), then floor-halving of
+ * polynomials picked from stream 2 until the squared norm is <= BETA_BOUND^2.  S_dev: [R][N][64].  info (nullable, host):
+ * final squared norm, number of PRG draws; passing it synchronises. */
+int lab_generate_witness_dev(lab_ctx *ctx, const lab_constants *c, uint64_t seed, uint32_t *S_dev, uint64_t info[2]);
+/* State::gen_f (structs.rs:289-350) on the device, seeded: symmetric uniform a (stream 3), uniform phi (stream 4),
+ * b = sum a_ij <s_i,s_j> + sum <phi_i,s_i>.  phi_dev [R][N][64], a_dev [R][R][64], b_dev [64]. */
+int lab_generate_state_dev(lab_ctx *ctx, const lab_constants *c, uint64_t seed, const uint32_t *S_dev, uint32_t *phi_dev, uint32_t *a_dev, uint32_t *b_dev);
 /* measured ALU-pipe (LOP3 + SHF) ceiling in lane-operations per second: the roofline denominator of the
  * ChaCha20-bound kernels (BASELINE.md section 2 asks for a measured INT32 figure) */
 int lab_bench_alu_peak(lab_ctx *ctx, double *lane_ops_per_s);

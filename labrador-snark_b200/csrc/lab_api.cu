@@ -3,6 +3,7 @@
 // There is NO CPU fallback: every entry point needs a CUDA device and fails with LAB_ERR_CUDA otherwise.
 #include "../../include/labrador_b200.h"
 #include "lab_kernels.cuh"
+#include "lab_gen.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -1359,6 +1360,65 @@ extern "C" int lab_synth_pi_dev(lab_ctx *ctx, uint64_t seed, uint64_t attempt, u
     LAUNCH(k_synth_pi, grid_for((total + 31) / 32, 256, ctx->sms * 16), 256, base, total, out_dev);
     return LAB_OK;
 }
+// ---- device-side generation of challenges, witness and statement (f2, f4) ----
+extern "C" int lab_sample_challenge_polys_dev(lab_ctx *ctx, uint64_t seed, uint32_t first_idx, uint32_t count, uint32_t *c_dev, uint32_t *candidates_dev) {
+    if (!count) return LAB_OK;
+    if (!c_dev) FAIL(LAB_ERR_PARAMS, "null output");
+    LAUNCH(k_challenge_polys, count, 32 * CH_WARPS, seed, first_idx, c_dev, candidates_dev);
+    return LAB_OK;
+}
+extern "C" int lab_generate_witness_dev(lab_ctx *ctx, const lab_constants *c, uint64_t seed, uint32_t *S_dev, uint64_t info[2]) {
+    cudaSetDevice(ctx->device);
+    TRY(check_consts(ctx, c, false));
+    const uint64_t np = c->N * c->R;
+    arena_reset(ctx);
+    unsigned long long *normtab, *dinfo;
+    uint32_t *halv;
+    TRY(arena_alloc(ctx, np * WIT_LEVELS, &normtab));
+    TRY(arena_alloc(ctx, (size_t)2, &dinfo));
+    TRY(arena_alloc(ctx, np, &halv));
+    CK(cudaMemsetAsync(halv, 0, np * sizeof(uint32_t), ctx->stream));
+    LAUNCH(k_witness_uniform, (unsigned)((np + 7) / 8), 256, seed, (size_t)np, S_dev, normtab);
+    const unsigned long long bound = (unsigned long long)c->BETA_BOUND * (unsigned long long)c->BETA_BOUND;
+    LAUNCH(k_witness_pick, 1, 32, seed, c->N, c->R, bound, normtab, halv, dinfo);
+    LAUNCH(k_witness_apply, grid_for(np * 64, 1024, ctx->sms * 16), 256, halv, (size_t)(np * 64), S_dev);
+    if (info) {
+        CK(cudaMemcpyAsync(info, dinfo, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        TRY(lab_sync(ctx));
+    }
+    return LAB_OK;
+}
+extern "C" int lab_generate_state_dev(lab_ctx *ctx, const lab_constants *c, uint64_t seed, const uint32_t *S_dev, uint32_t *phi_dev, uint32_t *a_dev, uint32_t *b_dev) {
+    cudaSetDevice(ctx->device);
+    TRY(check_consts(ctx, c, false));
+    if (!S_dev || !phi_dev || !a_dev || !b_dev) FAIL(LAB_ERR_PARAMS, "null argument");
+    const uint64_t R = c->R, N = c->N;
+    arena_reset(ctx);
+    uint32_t *What, *Phihat, *Ahat, *Ghat, *AG, *diag, *sums, *bhat;
+    TRY(arena_alloc(ctx, R * N * 32, &What));
+    TRY(arena_alloc(ctx, R * N * 32, &Phihat));
+    TRY(arena_alloc(ctx, R * R * 32, &Ahat));
+    TRY(arena_alloc(ctx, R * R * 32, &Ghat));
+    TRY(arena_alloc(ctx, R * R * 32, &AG));
+    TRY(arena_alloc(ctx, R * 32, &diag));
+    TRY(arena_alloc(ctx, (size_t)2 * 32, &sums));
+    TRY(arena_alloc(ctx, (size_t)32, &bhat));
+    LAUNCH(k_synth_zq, grid_for(R * N * 64, 1024, ctx->sms * 16), 256, prg_base(seed, 4), (uint64_t)0, (size_t)(R * N * 64), phi_dev);   // phi: structs.rs:306-318
+    LAUNCH(k_statement_a, dim3((unsigned)R, (unsigned)R), 64, seed, (uint32_t)R, a_dev);                                                   // a symmetric: structs.rs:289-305
+    TRY(d_fwd_hat(ctx, S_dev, What, R * N, N, R));
+    TRY(d_fwd_hat(ctx, phi_dev, Phihat, R * N, N, R));
+    TRY(d_fwd_hat(ctx, a_dev, Ahat, R * R, 0, 0));
+    // b = sum_ij a_ij <s_i, s_j> + sum_i <phi_i, s_i>   (structs.rs:320-350)
+    LAUNCH(k_ip_hat, (unsigned)(R * R), 256, What, (size_t)R, (size_t)1, What, (size_t)R, (size_t)1, (size_t)N, (size_t)R, 1u, 0, Ghat);
+    LAUNCH(k_pointwise, grid_for(R * R * 32, 256, ctx->sms * 16), 256, Ahat, (size_t)1, (size_t)(R * R), Ghat, (const uint32_t *)nullptr, (size_t)1, (size_t)0,
+           (const uint32_t *)nullptr, AG, (size_t)(R * R));
+    LAUNCH(k_sum_hats, 1, 32, AG, (size_t)(R * R), (size_t)1, sums, (size_t)1);
+    LAUNCH(k_ip_hat, (unsigned)R, 256, Phihat, (size_t)R, (size_t)1, What, (size_t)R, (size_t)1, (size_t)N, (size_t)0, 1u, 2, diag);
+    LAUNCH(k_sum_hats, 1, 32, diag, (size_t)R, (size_t)1, sums + 32, (size_t)1);
+    LAUNCH(k_sum_hats, 1, 32, sums, (size_t)2, (size_t)1, bhat, (size_t)1);
+    return d_inv_hat(ctx, bhat, b_dev, 1);
+}
+
 // measured ALU-pipe ceiling in lane-ops/s (roofline denominator of the ChaCha-bound kernels)
 extern "C" int lab_bench_alu_peak(lab_ctx *ctx, double *lane_ops_per_s) {
     CallScope cs(ctx);

@@ -137,6 +137,49 @@ class Context:
     def synth_pi_dev(self, seed, attempt, first_entry, total, dout):
         self._ck(self.L.lab_synth_pi_dev(self._h, C.c_uint64(seed), C.c_uint64(attempt), C.c_uint64(first_entry), C.c_size_t(total), C.c_void_p(dout)))
 
+    # ---- device-side generation (f2 challenges, f4 witness / statement) ----
+    def sample_challenge_polys(self, seed, first_idx, count):
+        """Verifier::fetch_challenge on the device -> ([count][64] canonical, candidates tried per polynomial)."""
+        dc, dn = self.malloc(count * D * 4), self.malloc(count * 4)
+        try:
+            self._ck(self.L.lab_sample_challenge_polys_dev(self._h, C.c_uint64(seed), C.c_uint32(first_idx), C.c_uint32(count), C.c_void_p(dc), C.c_void_p(dn)))
+            out, tries = np.empty((count, D), np.uint32), np.empty(count, np.uint32)
+            self.d2h(out, dc); self.d2h(tries, dn); self.sync()
+        finally:
+            self.free(dc); self.free(dn)
+        return out, tries
+
+    def generate_witness_dev(self, c, seed, dS):
+        info = (C.c_uint64 * 2)()
+        self._ck(self.L.lab_generate_witness_dev(self._h, C.byref(c), C.c_uint64(seed), C.c_void_p(dS), info))
+        return int(info[0]), int(info[1])
+
+    def generate_witness(self, c, seed):
+        """generate_witness (proofgen.rs:460-518), seeded, computed on the device -> [R][N][64]."""
+        n = c.R * c.N * D
+        dS = self.malloc(n * 4)
+        try:
+            norm, draws = self.generate_witness_dev(c, seed, dS)
+            S = np.empty((c.R, c.N, D), np.uint32)
+            self.d2h(S, dS); self.sync()
+        finally:
+            self.free(dS)
+        return S, norm, draws
+
+    def generate_state(self, c, seed, S):
+        """State::gen_f (structs.rs:289-350), seeded, computed on the device -> (phi, a, b)."""
+        S = _u32(S)
+        dS, dphi, da, db = self.malloc(S.nbytes), self.malloc(S.nbytes), self.malloc(c.R * c.R * D * 4), self.malloc(D * 4)
+        try:
+            self.h2d(dS, S)
+            self._ck(self.L.lab_generate_state_dev(self._h, C.byref(c), C.c_uint64(seed), C.c_void_p(dS), C.c_void_p(dphi), C.c_void_p(da), C.c_void_p(db)))
+            phi, a, b = np.empty((c.R, c.N, D), np.uint32), np.empty((c.R, c.R, D), np.uint32), np.empty(D, np.uint32)
+            self.d2h(phi, dphi); self.d2h(a, da); self.d2h(b, db); self.sync()
+        finally:
+            for d in (dS, dphi, da, db):
+                self.free(d)
+        return phi, a, b
+
     def alu_peak(self):
         v = C.c_double(0)
         self._ck(self.L.lab_bench_alu_peak(self._h, C.byref(v)))

@@ -392,3 +392,35 @@ def test_comm_single_rank_and_sharded_entry_points(ctx, orc):
     Tfull = ctx.commit_inner(c, SEED32, S)
     parts = [ctx.commit_inner(c, SEED32, S, row0=r0, nrows=32) for r0 in range(0, c.KAPPA, 32)]
     assert np.array_equal(np.concatenate(parts, axis=1), Tfull)
+
+
+# ---- device-side generation (f2 challenge polys, f4 witness / statement) ----
+def test_challenge_polys_on_device_match_oracle(ctx, orc):
+    """Verifier::fetch_challenge (verification.rs:460-489) with the 1000-sample operator-norm rejection
+    (util.rs:227-246): same draws, same f64 accept/reject decisions as the oracle and the host generator."""
+    got, tries = ctx.sample_challenge_polys(synth.SEED, 0, 6)
+    for i in range(6):
+        assert np.array_equal(got[i], orc.sample_challenge_poly(synth.SEED, i)), i
+    assert np.array_equal(got[2], synth.sample_challenge_poly(synth.SEED, 2))
+    assert (tries >= 1).all()
+    # shape of the challenge space: 23 zeros, 31 coefficients +-1, 10 coefficients +-2
+    for p in got:
+        v = np.where(p > Q // 2, Q - p.astype(np.int64), p.astype(np.int64))
+        assert sorted(np.bincount(v, minlength=3).tolist()) == [10, 23, 31]
+    other, _ = ctx.sample_challenge_polys(12345, 7, 3)
+    for k in range(3):
+        assert np.array_equal(other[k], orc.sample_challenge_poly(12345, 7 + k))
+
+
+@pytest.mark.parametrize("N,R", [(1, 1), (2, 2), (3, 5), (8, 8)])
+def test_generate_witness_and_state_on_device(ctx, orc, N, R):
+    c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
+    co, _ = orc.constants(N, R)
+    S, norm, draws = ctx.generate_witness(c, 77 + N)
+    ref = orc.generate_witness(co, 77 + N)
+    assert np.array_equal(S, ref)
+    assert norm == int((ref.astype(np.uint64) ** 2).sum()) <= c.BETA_BOUND ** 2
+    assert draws % 2 == 0 and draws > 0
+    phi, a, b = ctx.generate_state(c, 5, S)
+    rphi, ra, rb = orc.generate_state(co, S, 5)
+    assert np.array_equal(phi, rphi) and np.array_equal(a, ra) and np.array_equal(b, rb)
