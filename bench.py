@@ -293,7 +293,24 @@ def run_cfg1(args, rank, world, local_rank):
             tv = (time.perf_counter() - t0) / reps
             npairs = R * (R + 1) // 2
             blocks = (c.R * c.T_1 * c.KAPPA_1 * c.KAPPA + c.KAPPA * c.N + npairs * (c.T_1 + c.T_2) * c.KAPPA_2) * 64
+            # the same with the CRS cache (lab_crs_cache_configure): the proof writes the transformed CRS polynomials of the
+            # outer commitments through to HBM; verify right after it, and a second proof under the same CRS, read them back
+            cached = {}
+            try:
+                ctx.crs_cache_configure(150 << 30)
+                t0 = time.perf_counter(); trc = prover.proof_gen(st, crs); cached["prove_filling_cache_ms"] = (time.perf_counter() - t0) * 1e3
+                t0 = time.perf_counter(); okc = ctx.verify(c, SEED32, st.phi_k[0], st.a_k[0], st.b_k[0], ver.challenges, d); cached["verify_after_prove_ms"] = (time.perf_counter() - t0) * 1e3
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    trc = prover.proof_gen(st, crs)
+                cached["prove_again_same_crs_ms"] = (time.perf_counter() - t0) / reps * 1e3
+                cached["cache"] = ctx.crs_cache_stats()
+                dc = trc.as_oracle_dict()
+                cached["bit_identical_to_uncached"] = bool(okc[0]) and all(np.array_equal(dc[k], d[k]) for k in ("t", "g", "u_1", "h", "u_2", "z"))
+            finally:
+                ctx.crs_cache_configure(0)
             row = {"N": N, "R": R, "kappa": c.KAPPA, "T_1": c.T_1, "T_2": c.T_2, "prove_ms": tp * 1e3, "verify_ms": tv * 1e3, "verify_accepts": bool(okv[0]),
+                   "with_crs_cache": cached,
                    "launches_per_proof": launches, "crs_coefficients_per_proof": blocks, "chacha_blocks_per_s_prove": blocks / tp,
                    "witness_coeffs_per_s": N * R * D / tp, "jl_attempt": tr.jl_attempt}
             if oracle is not None and (N, R) in cpu_sizes:

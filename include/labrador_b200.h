@@ -203,6 +203,16 @@ int lab_prove_batch(lab_ctx *ctx, const lab_constants *c, size_t n_statements, c
 int lab_verify(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], const lab_state *st, const lab_challenges *ch,
                const lab_transcript *tr, int *accepted, int *failed_check, uint64_t *norm_sum);
 
+/* ---- CRS cache: B200 has 180 GB of HBM, the reference regenerates every CRS polynomial at every use (structs.rs:35-45) ----
+ * With max_bytes > 0 the outer-commitment kernel writes the transformed CRS polynomials it generates (B_ik rows, C_ijk,
+ * D_ijk) through to HBM, and any later call on this ctx with the same seed, shape and row range -- Verifier::verify
+ * recomputing u_1 / u_2 right after the proof (verification.rs:372-435), or further proofs under the same CRS object
+ * (CRS is borrowed &mut but never mutated, proofgen.rs:30) -- streams them back at HBM speed instead of running
+ * ChaCha20 (128 B per polynomial; (32,32) needs 103 GB).  Results are bit-identical.  Off by default (max_bytes = 0): a
+ * single proof then regenerates its CRS exactly like the reference.  Entries that do not fit stay uncached. */
+int lab_crs_cache_configure(lab_ctx *ctx, size_t max_bytes);
+int lab_crs_cache_stats(const lab_ctx *ctx, size_t *bytes_used, uint64_t *hits, uint64_t *misses);
+
 /* ---- transcript wire format (structs.rs:192-221) ----
  * The bytes `bincode::serialize(&Transcript)` produces in the reference (bincode 1.3.3 defaults: fixed-width little-endian
  * integers, u64 sequence lengths): the 14 fields in declaration order; Rq = Vec<Zq> of the TRIMMED coefficients

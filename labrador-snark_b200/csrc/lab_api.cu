@@ -46,6 +46,13 @@ struct lab_ctx {
     // (an H2D copy from pageable memory first synchronises the stream and would stall the enqueueing thread)
     struct MvPlan { std::vector<unsigned char> host; void *dev; };
     std::vector<MvPlan> mv_plans;
+    // CRS cache (lab_crs_cache_configure): hats of the CRS polynomials a K_MV call generated, kept in HBM and re-used by
+    // later calls with the same seed, item list and row range (the verifier right after the prover; further proofs under
+    // the same CRS).  Bit-identical results; off by default so that a proof regenerates its CRS like the reference does.
+    struct CrsEntry { std::vector<unsigned char> key; uint32_t *dev; size_t bytes; };
+    std::vector<CrsEntry> crs_cache;
+    size_t crs_cache_max = 0, crs_cache_used = 0;
+    uint64_t crs_cache_hits = 0, crs_cache_misses = 0;
     // worker contexts (own stream + arena each) for lab_prove_batch: independent statements overlap host-side
     // enqueueing of one proof with the GPU work of the others
     std::vector<lab_ctx *> workers;
@@ -194,6 +201,7 @@ extern "C" void lab_ctx_destroy(lab_ctx *ctx) {
     if (ctx->What) cudaFree(ctx->What);
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
     for (auto &p : ctx->mv_plans) cudaFree(p.dev);
+    for (auto &e : ctx->crs_cache) cudaFree(e.dev);
     for (lab_ctx *w : ctx->workers) lab_ctx_destroy(w);
     lab_comm_destroy(ctx);
     cudaStreamDestroy(ctx->stream);
@@ -464,6 +472,10 @@ static int d_crs_matvec(lab_ctx *ctx, const LabSeed &seed, const std::vector<MvS
             items.push_back(it);
         }
     const uint32_t ipr = (uint32_t)items.size();
+    {   // position of every item inside a row of the CRS cache
+        uint32_t off = 0;
+        for (MvItem &it : items) { it.poff = off; off += it.cnt; }
+    }
     MvItem *d_items = nullptr;
     uint32_t *partial;
     const size_t ibytes = items.size() * sizeof(MvItem);
@@ -485,7 +497,33 @@ static int d_crs_matvec(lab_ctx *ctx, const LabSeed &seed, const std::vector<MvS
     }
     TRY(arena_alloc(ctx, (size_t)n_rows * ipr * 32, &partial));
     const uint64_t warps = n_rows * ipr;
-    LAUNCH(k_crs_matvec, (unsigned)((warps + 7) / 8), 256, seed, d_items, ipr, n_rows, x0, V, partial);
+    // CRS cache: key = seed, row range, item list
+    uint32_t *cache_hit = nullptr, *cache_fill = nullptr;
+    if (ctx->crs_cache_max) {
+        std::vector<unsigned char> key(sizeof(seed.limb) + 2 * sizeof(uint64_t) + ibytes);
+        std::memcpy(key.data(), seed.limb, sizeof(seed.limb));
+        std::memcpy(key.data() + sizeof(seed.limb), &x0, 8);
+        std::memcpy(key.data() + sizeof(seed.limb) + 8, &n_rows, 8);
+        std::memcpy(key.data() + sizeof(seed.limb) + 16, items.data(), ibytes);
+        for (auto &e : ctx->crs_cache)
+            if (e.key == key) { cache_hit = e.dev; break; }
+        const size_t need = (size_t)n_rows * total_polys * 32 * sizeof(uint32_t);
+        if (cache_hit) ctx->crs_cache_hits++;
+        else {
+            ctx->crs_cache_misses++;
+            if (ctx->crs_cache_used + need <= ctx->crs_cache_max) {
+                void *dev = nullptr;
+                if (cudaMalloc(&dev, need) == cudaSuccess) {
+                    cache_fill = (uint32_t *)dev;
+                    ctx->crs_cache.push_back(lab_ctx::CrsEntry{std::move(key), cache_fill, need});
+                    ctx->crs_cache_used += need;
+                } else cudaGetLastError();         // no room: this call simply stays uncached
+            }
+        }
+    }
+    if (cache_hit) LAUNCH(k_cached_matvec, (unsigned)((warps + 7) / 8), 256, cache_hit, total_polys, d_items, ipr, n_rows, V, partial);
+    else if (cache_fill) LAUNCH(k_crs_matvec<true>, (unsigned)((warps + 7) / 8), 256, seed, d_items, ipr, n_rows, x0, V, partial, cache_fill, total_polys);
+    else LAUNCH(k_crs_matvec<false>, (unsigned)((warps + 7) / 8), 256, seed, d_items, ipr, n_rows, x0, V, partial, (uint32_t *)nullptr, total_polys);
     LAUNCH(k_finish_rows, (unsigned)((n_rows + 7) / 8), 256, partial, ipr, n_rows, out);
     return LAB_OK;
 }
@@ -1247,6 +1285,26 @@ extern "C" int lab_prove_batch(lab_ctx *ctx, const lab_constants *c, size_t n_st
         ctx->workers[t]->launches = 0;
         if (status[t] != LAB_OK) { ctx->err = "statement failed in batch worker: " + ctx->workers[t]->err; return status[t]; }
     }
+    return LAB_OK;
+}
+
+extern "C" int lab_crs_cache_configure(lab_ctx *ctx, size_t max_bytes) {
+    if (!ctx) return LAB_ERR_PARAMS;
+    cudaSetDevice(ctx->device);
+    if (max_bytes < ctx->crs_cache_used) {          // shrinking: drop everything (entries are regenerated on demand)
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (auto &e : ctx->crs_cache) cudaFree(e.dev);
+        ctx->crs_cache.clear();
+        ctx->crs_cache_used = 0;
+    }
+    ctx->crs_cache_max = max_bytes;
+    return LAB_OK;
+}
+extern "C" int lab_crs_cache_stats(const lab_ctx *ctx, size_t *bytes_used, uint64_t *hits, uint64_t *misses) {
+    if (!ctx) return LAB_ERR_PARAMS;
+    if (bytes_used) *bytes_used = ctx->crs_cache_used;
+    if (hits) *hits = ctx->crs_cache_hits;
+    if (misses) *misses = ctx->crs_cache_misses;
     return LAB_OK;
 }
 

@@ -712,10 +712,16 @@ struct MvItem {
     uint32_t nk;
     uint32_t y0, cnt;            // this item covers y in [y0, y0 + cnt)
     uint32_t vec_off;            // V index of y = 0
+    uint32_t poff;               // polynomials of this row that precede the item (index into a row of the CRS cache)
+    uint32_t pad;
 };
 
+// cache_out (nullable): the generated polynomials are also written, as packed hats, to cache_out[(xr * row_polys + poff + y - y0)]
+// -- the CRS cache that lets the verifier's recomputation and later proofs under the same CRS skip ChaCha20 altogether
+template <bool FILL_CACHE>
 __global__ void __launch_bounds__(256) k_crs_matvec(LabSeed seed, const MvItem *__restrict__ items, uint32_t items_per_row, uint64_t n_rows,
-                                                    uint64_t x0, const uint32_t *__restrict__ V, uint32_t *__restrict__ partial) {
+                                                    uint64_t x0, const uint32_t *__restrict__ V, uint32_t *__restrict__ partial,
+                                                    uint32_t *__restrict__ cache_out, uint64_t row_polys) {
     const int lane = threadIdx.x & 31;
     const LabWarpTw tw = lab_warp_tw(lane);
     uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -735,16 +741,50 @@ __global__ void __launch_bounds__(256) k_crs_matvec(LabSeed seed, const MvItem *
     int pending = 0;
     LabHoist h;
     lab_hoist_invalidate(h);
+    uint32_t *co = FILL_CACHE ? cache_out + (xr * row_polys + it.poff) * 32 + lane : nullptr;
     for (uint32_t y = it.y0; y < it.y0 + it.cnt; y++) {
         const uint64_t add = (uint64_t)(y / it.nk) * it.sp + (uint64_t)(y % it.nk) * it.sk;
         const uint64_t plo = lo + add;
         const uint64_t phi = hi + (plo < lo);
         uint32_t re, im;
         crs_poly_hat<LAB_RM_MATVEC>(seed, h, plo, phi, tw, lane, re, im);
+        if (FILL_CACHE) { *co = lab_pack(re, im); co += 32; }
         const uint32_t v = __ldg(V + ((size_t)it.vec_off + y) * 32 + lane);
         accr += re * lab_re(v) + (LABQ - im) * lab_im(v);
         acci += re * lab_im(v) + im * lab_re(v);
         if (++pending == 16) { accr = lab_fold(accr); acci = lab_fold(acci); pending = 0; }
+    }
+    partial[wid * 32 + lane] = lab_pack(lab_canon(accr), lab_canon(acci));
+}
+// the same mat-vec from cached hats: HBM-bound stream of 128 B per CRS polynomial, no ChaCha20
+__global__ void __launch_bounds__(256) k_cached_matvec(const uint32_t *__restrict__ cache, uint64_t row_polys, const MvItem *__restrict__ items,
+                                                       uint32_t items_per_row, uint64_t n_rows, const uint32_t *__restrict__ V, uint32_t *__restrict__ partial) {
+    const int lane = threadIdx.x & 31;
+    uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t total = n_rows * items_per_row;
+    if (wid >= total) return;
+    const uint64_t xr = wid / items_per_row;
+    const MvItem it = items[wid % items_per_row];
+    const uint32_t *ci = cache + (xr * row_polys + it.poff) * 32 + lane;
+    const uint32_t *vi = V + ((size_t)it.vec_off + it.y0) * 32 + lane;
+    uint32_t accr = 0, acci = 0;
+    uint32_t y = 0;
+    for (; y + 4 <= it.cnt; y += 4) {                       // four independent 128 B streams in flight per warp
+        uint32_t a[4], v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { a[u] = __ldcs(ci + (size_t)(y + u) * 32); v[u] = __ldg(vi + (size_t)(y + u) * 32); }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            accr += lab_re(a[u]) * lab_re(v[u]) + (LABQ - lab_im(a[u])) * lab_im(v[u]);
+            acci += lab_re(a[u]) * lab_im(v[u]) + lab_im(a[u]) * lab_re(v[u]);
+        }
+        if ((y & 12) == 12) { accr = lab_fold(accr); acci = lab_fold(acci); }     // every 16 terms: 16 * 2 * 2^26 < 2^32
+    }
+    accr = lab_fold(accr); acci = lab_fold(acci);
+    for (; y < it.cnt; y++) {
+        const uint32_t a = __ldcs(ci + (size_t)y * 32), v = __ldg(vi + (size_t)y * 32);
+        accr += lab_re(a) * lab_re(v) + (LABQ - lab_im(a)) * lab_im(v);
+        acci += lab_re(a) * lab_im(v) + lab_im(a) * lab_re(v);
     }
     partial[wid * 32 + lane] = lab_pack(lab_canon(accr), lab_canon(acci));
 }

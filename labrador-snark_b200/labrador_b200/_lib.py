@@ -61,7 +61,7 @@ SYMBOLS = [
     "lab_aggregate_phi", "lab_h_gram", "lab_amortize_z", "lab_prove", "lab_prove_batch", "lab_verify",
     "lab_witness_load_dev", "lab_commit_inner_dev", "lab_gram_dev", "lab_jl_project_dev", "lab_amortize_z_dev",
     "lab_synth_zq_dev", "lab_synth_pi_dev", "lab_bench_alu_peak",
-    "lab_comm_unique_id", "lab_comm_init", "lab_comm_destroy", "lab_transcript_bincode",
+    "lab_comm_unique_id", "lab_comm_init", "lab_comm_destroy", "lab_transcript_bincode", "lab_crs_cache_configure", "lab_crs_cache_stats",
     "lab_sample_challenge_polys_dev", "lab_generate_witness_dev", "lab_generate_state_dev",
 ]
 

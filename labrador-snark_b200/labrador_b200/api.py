@@ -137,6 +137,17 @@ class Context:
     def synth_pi_dev(self, seed, attempt, first_entry, total, dout):
         self._ck(self.L.lab_synth_pi_dev(self._h, C.c_uint64(seed), C.c_uint64(attempt), C.c_uint64(first_entry), C.c_size_t(total), C.c_void_p(dout)))
 
+    # ---- CRS cache (lab_crs_cache_*) ----
+    def crs_cache_configure(self, max_bytes):
+        """Keep the transformed CRS polynomials of the outer commitments in HBM (up to max_bytes) so that verify after
+        prove, and further proofs under the same CRS, skip ChaCha20.  0 disables and frees.  Bit-identical results."""
+        self._ck(self.L.lab_crs_cache_configure(self._h, C.c_size_t(max_bytes)))
+
+    def crs_cache_stats(self):
+        used, hits, misses = C.c_size_t(0), C.c_uint64(0), C.c_uint64(0)
+        self._ck(self.L.lab_crs_cache_stats(self._h, C.byref(used), C.byref(hits), C.byref(misses)))
+        return {"bytes": used.value, "hits": hits.value, "misses": misses.value}
+
     # ---- device-side generation (SURVEY 8f: f2 challenges, f4 witness / statement) ----
     def sample_challenge_polys(self, seed, first_idx, count):
         """Verifier::fetch_challenge on the device -> ([count][64] canonical, candidates tried per polynomial)."""

@@ -424,3 +424,48 @@ def test_generate_witness_and_state_on_device(ctx, orc, N, R):
     phi, a, b = ctx.generate_state(c, 5, S)
     rphi, ra, rb = orc.generate_state(co, S, 5)
     assert np.array_equal(phi, rphi) and np.array_equal(a, ra) and np.array_equal(b, rb)
+
+
+def test_crs_cache_is_transparent(ctx, orc):
+    """lab_crs_cache_configure: the first proof fills the cache (write-through in K_MV), verify and a second proof read
+    it back; every result stays bit-identical to the uncached run and to the oracle."""
+    N, R = 2, 3
+    c = lb.RuntimeConstants.new(N, R)
+    co, _ = orc.constants(N, R)
+    S = orc.generate_witness(co, 21)
+    phi, a, b = orc.generate_state(co, S, 21)
+    ch = orc.sample_challenges(co, 21, 3)
+    rc, ref = orc.prove(co, SEED32, S, phi, a, b, ch, ntt=True, nthreads=8)
+    assert rc == 0
+    st = lb.State(phi, a, b)
+    ver = lb.Verifier.new(st.b_prime_k, c, challenges=ch)
+    c2 = lb.Context(0)
+    try:
+        c2.crs_cache_configure(1 << 30)
+        prover = lb.Prover.new(S, ver, c, c2)
+        crs = lb.CRS.from_seed(c, SEED32, c2)
+        tr1 = prover.proof_gen(st, crs).as_oracle_dict()
+        s1 = c2.crs_cache_stats()
+        assert s1["misses"] == 2 and s1["hits"] == 0 and s1["bytes"] > 0          # u_1 and u_2 generated and stored
+        ok = c2.verify(c, SEED32, phi, a, b, ch, tr1)
+        s2 = c2.crs_cache_stats()
+        assert ok[0] and s2["hits"] == 2                                          # Checks 19, 20 from the cache
+        tr2 = prover.proof_gen(st, crs).as_oracle_dict()
+        assert c2.crs_cache_stats()["hits"] == 4
+        for k in ("t", "g", "u_1", "projection_int", "b_prime_prime", "h", "u_2", "z"):
+            assert np.array_equal(tr1[k], ref[k]), k
+            assert np.array_equal(tr2[k], ref[k]), k
+        # a different seed must not hit
+        other = bytes(range(1, 33))
+        rc, ref_o = orc.prove(co, other, S, phi, a, b, ch, ntt=True, nthreads=8)
+        tr3 = prover.proof_gen(st, lb.CRS.from_seed(c, other, c2)).as_oracle_dict()
+        assert np.array_equal(tr3["u_1"], ref_o["u_1"]) and np.array_equal(tr3["u_2"], ref_o["u_2"])
+        # a tampered transcript is still rejected at the same check when the verifier reads the cache
+        bad = dict(tr1); bad["u_1"] = np.array(tr1["u_1"], copy=True); bad["u_1"][0, 0] ^= 1
+        assert c2.verify(c, SEED32, phi, a, b, ch, bad)[:2] == (False, 19)
+        c2.crs_cache_configure(0)
+        assert c2.crs_cache_stats()["bytes"] == 0
+        tr4 = prover.proof_gen(st, crs).as_oracle_dict()
+        assert np.array_equal(tr4["u_1"], ref["u_1"])
+    finally:
+        c2.close()
