@@ -432,15 +432,49 @@ static int d_commit_inner(lab_ctx *ctx, const LabSeed &seed, const uint32_t *Wha
     const unsigned grid = (unsigned)((nrows + KA_RT - 1) / KA_RT);
     // four consumer warps x IC witness vectors per pass
     const int IC = R > 32 ? 16 : (R > 16 ? 8 : (R > 8 ? 4 : (R > 4 ? 2 : 1)));
-    for (uint64_t ib = 0; ib < R; ib += (uint64_t)KA_CONS * IC) {
-        switch (IC) {
-            case 16: LAUNCH_SMEM((k_commit_inner<16, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, 16), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T, t_stride, t_row_off); break;
-            case 8: LAUNCH_SMEM((k_commit_inner<8, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, 8), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T, t_stride, t_row_off); break;
-            case 4: LAUNCH_SMEM((k_commit_inner<4, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, 4), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T, t_stride, t_row_off); break;
-            case 2: LAUNCH_SMEM((k_commit_inner<2, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, 2), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T, t_stride, t_row_off); break;
-            default: LAUNCH_SMEM((k_commit_inner<1, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, 1), seed, What, (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T, t_stride, t_row_off); break;
+    // CRS cache (lab_crs_cache_configure): A as transformed polynomials [nrows][N], keyed by seed, N and the row range
+    uint32_t *acache = nullptr;
+    int mode = 0;
+    if (ctx->crs_cache_max && (IC == 16 || IC == 1)) {
+        std::vector<unsigned char> key(sizeof(seed.limb) + 4 * sizeof(uint64_t));
+        const uint64_t tag = 0x41ull /* 'A' */, kv[4] = {tag, N, row0, nrows};
+        std::memcpy(key.data(), seed.limb, sizeof(seed.limb));
+        std::memcpy(key.data() + sizeof(seed.limb), kv, sizeof kv);
+        for (auto &e : ctx->crs_cache)
+            if (e.key == key) { acache = e.dev; mode = 2; break; }
+        if (mode == 2) ctx->crs_cache_hits++;
+        else {
+            ctx->crs_cache_misses++;
+            const size_t need = (size_t)nrows * N * 32 * sizeof(uint32_t);
+            if (ctx->crs_cache_used + need <= ctx->crs_cache_max) {
+                void *dev = nullptr;
+                if (cudaMalloc(&dev, need) == cudaSuccess) {
+                    acache = (uint32_t *)dev;
+                    mode = 1;
+                    ctx->crs_cache.push_back(lab_ctx::CrsEntry{std::move(key), acache, need});
+                    ctx->crs_cache_used += need;
+                } else cudaGetLastError();
+            }
         }
     }
+#define KA_LAUNCH(ICV, MODEV)                                                                                                        \
+    LAUNCH_SMEM((k_commit_inner<ICV, LAB_RM_COMMIT, LAB_KA_PP, MODEV>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, ICV), seed, What, \
+                (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T, t_stride, t_row_off, acache)
+    for (uint64_t ib = 0; ib < R; ib += (uint64_t)KA_CONS * IC) {
+        switch (IC) {
+            case 16:
+                if (mode == 2) KA_LAUNCH(16, 2); else if (mode == 1) KA_LAUNCH(16, 1); else KA_LAUNCH(16, 0);
+                break;
+            case 8: KA_LAUNCH(8, 0); break;
+            case 4: KA_LAUNCH(4, 0); break;
+            case 2: KA_LAUNCH(2, 0); break;
+            default:
+                if (mode == 2) KA_LAUNCH(1, 2); else if (mode == 1) KA_LAUNCH(1, 1); else KA_LAUNCH(1, 0);
+                break;
+        }
+        if (mode == 1) mode = 2;          // later passes over more witness vectors (R > 64) already read the cache
+    }
+#undef KA_LAUNCH
     return LAB_OK;
 }
 

@@ -446,12 +446,12 @@ def test_crs_cache_is_transparent(ctx, orc):
         crs = lb.CRS.from_seed(c, SEED32, c2)
         tr1 = prover.proof_gen(st, crs).as_oracle_dict()
         s1 = c2.crs_cache_stats()
-        assert s1["misses"] == 2 and s1["hits"] == 0 and s1["bytes"] > 0          # u_1 and u_2 generated and stored
+        assert s1["misses"] == 3 and s1["hits"] == 0 and s1["bytes"] > 0          # A, u_1 and u_2 generated and stored
         ok = c2.verify(c, SEED32, phi, a, b, ch, tr1)
         s2 = c2.crs_cache_stats()
-        assert ok[0] and s2["hits"] == 2                                          # Checks 19, 20 from the cache
+        assert ok[0] and s2["hits"] == 3                                          # Checks 15 (A z), 19, 20 from the cache
         tr2 = prover.proof_gen(st, crs).as_oracle_dict()
-        assert c2.crs_cache_stats()["hits"] == 4
+        assert c2.crs_cache_stats()["hits"] == 6
         for k in ("t", "g", "u_1", "projection_int", "b_prime_prime", "h", "u_2", "z"):
             assert np.array_equal(tr1[k], ref[k]), k
             assert np.array_equal(tr2[k], ref[k]), k
@@ -463,6 +463,16 @@ def test_crs_cache_is_transparent(ctx, orc):
         # a tampered transcript is still rejected at the same check when the verifier reads the cache
         bad = dict(tr1); bad["u_1"] = np.array(tr1["u_1"], copy=True); bad["u_1"][0, 0] ^= 1
         assert c2.verify(c, SEED32, phi, a, b, ch, bad)[:2] == (False, 19)
+        # the inner commitment alone, 64-vector shape (IC = 16 kernel): fill, then read
+        Nw, Rw = 3, 40
+        cw = lb.RuntimeConstants.new(Nw, Rw, allow_degenerate=True)
+        cow, _ = orc.constants(Nw, Rw)
+        Sw = synth.uniform_witness(Nw, Rw, seed=4)
+        refT = orc.commit_inner_rows(cow, SEED32, Sw, 2, 21, nthreads=8)
+        h0 = c2.crs_cache_stats()["hits"]
+        assert np.array_equal(c2.commit_inner(cw, SEED32, Sw, row0=2, nrows=21), refT)
+        assert np.array_equal(c2.commit_inner(cw, SEED32, Sw, row0=2, nrows=21), refT)
+        assert c2.crs_cache_stats()["hits"] == h0 + 1
         c2.crs_cache_configure(0)
         assert c2.crs_cache_stats()["bytes"] == 0
         tr4 = prover.proof_gen(st, crs).as_oracle_dict()
