@@ -29,6 +29,16 @@ class Context {
     Context &operator=(const Context &) = delete;
     lab_ctx *get() const { return ctx_; }
     void check(int rc) const { if (rc != LAB_OK) throw Error(rc, lab_last_error(ctx_)); }
+    // one process per GPU: rank 0 makes the id, the host distributes it, every rank attaches (collective); proof_gen /
+    // verify then shard the CRS-regenerating stages by rows inside the library
+    static std::array<std::uint8_t, LAB_COMM_ID_BYTES> comm_unique_id() {
+        std::array<std::uint8_t, LAB_COMM_ID_BYTES> id{};
+        if (int rc = lab_comm_unique_id(id.data()); rc != LAB_OK) throw Error(rc, lab_last_error(nullptr));
+        return id;
+    }
+    void comm_init(const std::array<std::uint8_t, LAB_COMM_ID_BYTES> &id, int rank, int world) const { check(lab_comm_init(ctx_, id.data(), rank, world)); }
+    // keep transformed CRS polynomials in HBM between calls (verify after prove, proofs under one CRS); 0 = off
+    void crs_cache_configure(std::size_t max_bytes) const { check(lab_crs_cache_configure(ctx_, max_bytes)); }
   private:
     lab_ctx *ctx_ = nullptr;
 };
@@ -109,6 +119,29 @@ class Prover {
         tr.jl_attempt = out.jl_attempt;
         tr.norm_sum = out.norm_sum;
         return tr;
+    }
+
+    // Verifier::verify (verification.rs:25-438): returns the reference's check number that failed, 0 = accepted
+    int verify(const Context &ctx, const State &st, const CRS &crs, const Challenges &ch, Transcript &tr) const {
+        lab_state cst{st.phi.data(), st.a.data(), st.b.data()};
+        lab_challenges cch{ch.pi.data(), ch.n_attempts, ch.psi, ch.omega.data(), ch.alpha.data(), ch.beta.data(), ch.c.data()};
+        lab_transcript in{tr.u_1.data(), tr.jl_attempt, tr.projection_int.data(), tr.projection.data(), tr.b_prime_prime.data(), tr.u_2.data(),
+                          tr.z.data(), tr.t_i_all.data(), tr.g_mat.data(), tr.h_mat.data(), nullptr, 0};
+        int accepted = 0, failed = 0;
+        std::uint64_t norm = 0;
+        ctx.check(lab_verify(ctx.get(), &c_, crs.base_seed.data(), &cst, &cch, &in, &accepted, &failed, &norm));
+        return accepted ? 0 : failed;
+    }
+    // bincode::serialize(&Transcript) (structs.rs:192-221)
+    std::vector<std::uint8_t> to_bincode(const Challenges &ch, Transcript &tr) const {
+        lab_challenges cch{ch.pi.data(), ch.n_attempts, ch.psi, ch.omega.data(), ch.alpha.data(), ch.beta.data(), ch.c.data()};
+        lab_transcript in{tr.u_1.data(), tr.jl_attempt, tr.projection_int.data(), tr.projection.data(), tr.b_prime_prime.data(), tr.u_2.data(),
+                          tr.z.data(), tr.t_i_all.data(), tr.g_mat.data(), tr.h_mat.data(), nullptr, 0};
+        std::size_t size = 0;
+        if (int rc = lab_transcript_bincode(&c_, &in, &cch, nullptr, 0, &size); rc != LAB_OK) throw Error(rc, "lab_transcript_bincode");
+        std::vector<std::uint8_t> out(size);
+        if (int rc = lab_transcript_bincode(&c_, &in, &cch, out.data(), out.size(), &size); rc != LAB_OK) throw Error(rc, "lab_transcript_bincode");
+        return out;
     }
 
   private:

@@ -37,3 +37,14 @@ def combine_z(partial_canonical, all_reduce_sum):
     z = np.asarray(partial_canonical, dtype=np.int64).copy()
     z = all_reduce_sum(z)
     return np.mod(z, Q).astype(np.uint32)
+
+
+def rows_of(total, world, rank):
+    """The library's own rule (lab_comm_*, shard_rows in lab_api.cu): an equal slice of `total` output rows per rank when
+    the communicator size divides it, otherwise every rank computes all rows and nothing is exchanged.
+    Returns (x0, nx, sharded)."""
+    total, world, rank = int(total), int(world), int(rank)
+    if world > 1 and total % world == 0:
+        nx = total // world
+        return nx * rank, nx, True
+    return 0, total, False

@@ -59,6 +59,27 @@ extern "C" {
     pub fn lab_amortize_z(ctx: *mut lab_ctx, c: *const lab_constants, S: *const u32, ch: *const u32, z: *mut u32) -> c_int;
     pub fn lab_prove(ctx: *mut lab_ctx, c: *const lab_constants, seed: *const u8, S: *const u32, st: *const lab_state,
                      ch: *const lab_challenges, out: *mut lab_transcript) -> c_int;
+    pub fn lab_prove_batch(ctx: *mut lab_ctx, c: *const lab_constants, n_statements: usize, seeds: *const u8, shared_crs: c_int, S: *const u32,
+                           st: *const lab_state, ch: *const lab_challenges, out: *mut lab_transcript) -> c_int;
+    // Verifier::verify (verification.rs:25-438)
+    pub fn lab_verify(ctx: *mut lab_ctx, c: *const lab_constants, seed: *const u8, st: *const lab_state, ch: *const lab_challenges,
+                      tr: *const lab_transcript, accepted: *mut c_int, failed_check: *mut c_int, norm_sum: *mut u64) -> c_int;
+    // one process per GPU: NCCL communicator inside the library (the host moves the 128-byte id between ranks)
+    pub fn lab_comm_unique_id(id: *mut u8) -> c_int;
+    pub fn lab_comm_init(ctx: *mut lab_ctx, id: *const u8, rank: c_int, world: c_int) -> c_int;
+    pub fn lab_comm_destroy(ctx: *mut lab_ctx) -> c_int;
+    // CRS cache in HBM (transparent; off unless configured)
+    pub fn lab_crs_cache_configure(ctx: *mut lab_ctx, max_bytes: usize) -> c_int;
+    pub fn lab_crs_cache_stats(ctx: *const lab_ctx, bytes_used: *mut usize, hits: *mut u64, misses: *mut u64) -> c_int;
+    // bincode::serialize(&Transcript) byte layout (structs.rs:192-221); out = null returns the size
+    pub fn lab_transcript_bincode(c: *const lab_constants, tr: *const lab_transcript, ch: *const lab_challenges,
+                                  out: *mut u8, cap: usize, size: *mut usize) -> c_int;
+    // seeded generators on the device: fetch_challenge (verification.rs:460-489), generate_witness (proofgen.rs:460-518), State::gen_f (structs.rs:289-350)
+    pub fn lab_sample_challenge_polys_dev(ctx: *mut lab_ctx, seed: u64, first_idx: u32, count: u32, c_dev: *mut u32, candidates_dev: *mut u32) -> c_int;
+    pub fn lab_generate_witness_dev(ctx: *mut lab_ctx, c: *const lab_constants, seed: u64, S_dev: *mut u32, info: *mut u64) -> c_int;
+    pub fn lab_generate_state_dev(ctx: *mut lab_ctx, c: *const lab_constants, seed: u64, S_dev: *const u32, phi_dev: *mut u32, a_dev: *mut u32, b_dev: *mut u32) -> c_int;
     pub fn lab_malloc(ctx: *mut lab_ctx, bytes: usize, dptr: *mut *mut c_void) -> c_int;
     pub fn lab_free(ctx: *mut lab_ctx, dptr: *mut c_void) -> c_int;
+    pub fn lab_memcpy_h2d(ctx: *mut lab_ctx, dst: *mut c_void, src: *const c_void, bytes: usize) -> c_int;
+    pub fn lab_memcpy_d2h(ctx: *mut lab_ctx, dst: *mut c_void, src: *const c_void, bytes: usize) -> c_int;
 }

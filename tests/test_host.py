@@ -237,3 +237,22 @@ def test_transcript_bincode_matches_independent_packer(orc):
     assert got == ref
     # size: every Zq is 16 bytes; Pi dominates (R * 256 * N*64 entries)
     assert len(got) > R * 256 * N * 64 * 16
+
+
+def test_in_library_row_sharding_rule():
+    """shard.rows_of mirrors shard_rows() of lab_api.cu: equal slices that tile the row range exactly, or no sharding."""
+    from labrador_b200 import shard
+    for total in (128, 256, 2048, 4194304):
+        for world in (1, 2, 4, 8):
+            cover = []
+            for r in range(world):
+                x0, nx, sh = shard.rows_of(total, world, r)
+                assert sh == (world > 1)
+                cover.append((x0, nx))
+            if world > 1:
+                assert [c[0] for c in cover] == [i * (total // world) for i in range(world)]
+                assert sum(c[1] for c in cover) == total
+    assert shard.rows_of(130, 4, 3) == (0, 130, False)          # not divisible: computed unsharded on every rank
+    # kappa = N * 64 is divisible by 2, 4, 8 for every N, so T, u_1, u_2 always shard on one 8-GPU box
+    for N in (1, 2, 3, 5, 4096):
+        assert all(shard.rows_of(N * 64, w, 0)[2] for w in (2, 4, 8))
