@@ -4,6 +4,7 @@
 #include "../../include/labrador_b200.h"
 #include "lab_kernels.cuh"
 #include "lab_gen.cuh"
+#include "lab_umma.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -49,7 +50,7 @@ struct lab_ctx {
     // CRS cache (lab_crs_cache_configure): hats of the CRS polynomials a K_MV call generated, kept in HBM and re-used by
     // later calls with the same seed, item list and row range (the verifier right after the prover; further proofs under
     // the same CRS).  Bit-identical results; off by default so that a proof regenerates its CRS like the reference does.
-    struct CrsEntry { std::vector<unsigned char> key; uint32_t *dev; size_t bytes; };
+    struct CrsEntry { std::vector<unsigned char> key; uint32_t *dev; size_t bytes; };   // dev: hats (K_MV) or int8 limb planes (A)
     std::vector<CrsEntry> crs_cache;
     size_t crs_cache_max = 0, crs_cache_used = 0;
     uint64_t crs_cache_hits = 0, crs_cache_misses = 0;
@@ -420,6 +421,48 @@ static int d_inv_hat(lab_ctx *ctx, const uint32_t *in, uint32_t *out, size_t n) 
     LAUNCH(k_inv_hat, grid_for(n, 8, ctx->sms * 16), 256, in, out, n);
     return LAB_OK;
 }
+// ---- tensor-core commitment from the cached A (lab_umma.cuh) ----
+typedef CUresult (*lab_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                        const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static lab_encode_tiled_fn encode_tiled() {
+    static lab_encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (lab_encode_tiled_fn)p;
+    }
+    return fn;
+}
+// 2-D map over [rows][kpad] bytes, box = 128 bytes x box_rows rows, 128-byte swizzle (the layout tcgen05's K-major descriptors expect)
+static int make_map(lab_ctx *ctx, CUtensorMap *map, void *base, uint64_t rows, uint64_t kpad, uint32_t box_rows) {
+    lab_encode_tiled_fn enc = encode_tiled();
+    if (!enc) FAIL(LAB_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+    const cuuint64_t dims[2] = {kpad, rows}, strides[1] = {kpad};
+    const cuuint32_t box[2] = {128, box_rows}, estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) FAIL(LAB_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return LAB_OK;
+}
+// T[i][t_row_off + row] for vectors i in [ib, ib + ni) and all cached rows, from the int8 limb planes of A
+static int d_commit_umma(lab_ctx *ctx, uint8_t *acache, uint32_t ntiles, uint32_t kpad, const uint32_t *What, uint64_t N, uint64_t R, uint64_t ib, uint64_t ni,
+                         uint64_t nrows, uint32_t *T, uint64_t t_stride, uint64_t t_row_off) {
+    const uint32_t ncols = (uint32_t)((4 * ni + 15) / 16 * 16), rows_pad = ntiles * 64;
+    int8_t *Bp;
+    uint32_t *Th;
+    TRY(arena_alloc(ctx, (size_t)32 * ncols * kpad, &Bp));
+    TRY(arena_alloc(ctx, (size_t)32 * ni * rows_pad, &Th));
+    CK(cudaMemsetAsync(Bp, 0, (size_t)32 * ncols * kpad, ctx->stream));
+    LAUNCH(k_umma_build_b, grid_for(N * ni * 32, 256, ctx->sms * 16), 256, What, (uint32_t)N, (uint32_t)R, (uint32_t)ib, (uint32_t)ni, ncols, kpad, Bp);
+    CUtensorMap mapA, mapB;
+    TRY(make_map(ctx, &mapA, acache, (uint64_t)32 * ntiles * 128, kpad, 128));
+    TRY(make_map(ctx, &mapB, Bp, (uint64_t)32 * ncols, kpad, ncols));
+    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)ctx->sms, (uint64_t)32 * ntiles);
+    LAUNCH_SMEM(k_umma_commit, grid, UM_THREADS, UM_SMEM, mapA, mapB, ntiles, kpad / 128, ncols, (uint32_t)ni, rows_pad, Th);
+    LAUNCH(k_umma_finish, dim3(rows_pad / 32, (unsigned)ni), 256, Th, (uint32_t)ni, rows_pad, nrows, (uint32_t)ib, T, t_stride, t_row_off);
+    return LAB_OK;
+}
+
 static int d_commit_inner(lab_ctx *ctx, const LabSeed &seed, const uint32_t *What, uint64_t N, uint64_t R, uint64_t row0, uint64_t nrows, uint32_t *T,
                           uint64_t t_stride = 0, uint64_t t_row_off = 0) {
     if (!t_stride) t_stride = nrows;            // default: T is exactly [R][nrows][64]
@@ -432,26 +475,29 @@ static int d_commit_inner(lab_ctx *ctx, const LabSeed &seed, const uint32_t *Wha
     const unsigned grid = (unsigned)((nrows + KA_RT - 1) / KA_RT);
     // four consumer warps x IC witness vectors per pass
     const int IC = R > 32 ? 16 : (R > 16 ? 8 : (R > 8 ? 4 : (R > 4 ? 2 : 1)));
-    // CRS cache (lab_crs_cache_configure): A as transformed polynomials [nrows][N], keyed by seed, N and the row range
-    uint32_t *acache = nullptr;
-    int mode = 0;
-    if (ctx->crs_cache_max && (IC == 16 || IC == 1)) {
+    // CRS cache (lab_crs_cache_configure): A as int8 limb planes (lab_umma.cuh), keyed by seed, N and the row range.  The
+    // first use generates A with ChaCha20 and writes it through (MODE 1); every later use -- further passes over more
+    // witness vectors, the verifier's A z, the next proof under this CRS -- is the tcgen05 contraction d_commit_umma.
+    uint8_t *acache = nullptr;
+    bool hit = false;
+    const uint32_t kpad = (uint32_t)((2 * N + 127) / 128 * 128), ntiles = (uint32_t)((nrows + 63) / 64);
+    if (ctx->crs_cache_max && (IC == 16 || IC == 1) && N <= 16384) {
         std::vector<unsigned char> key(sizeof(seed.limb) + 4 * sizeof(uint64_t));
         const uint64_t tag = 0x41ull /* 'A' */, kv[4] = {tag, N, row0, nrows};
         std::memcpy(key.data(), seed.limb, sizeof(seed.limb));
         std::memcpy(key.data() + sizeof(seed.limb), kv, sizeof kv);
         for (auto &e : ctx->crs_cache)
-            if (e.key == key) { acache = e.dev; mode = 2; break; }
-        if (mode == 2) ctx->crs_cache_hits++;
+            if (e.key == key) { acache = (uint8_t *)e.dev; hit = true; break; }
+        if (hit) ctx->crs_cache_hits++;
         else {
             ctx->crs_cache_misses++;
-            const size_t need = (size_t)nrows * N * 32 * sizeof(uint32_t);
+            const size_t need = (size_t)32 * ntiles * 128 * kpad;
             if (ctx->crs_cache_used + need <= ctx->crs_cache_max) {
                 void *dev = nullptr;
                 if (cudaMalloc(&dev, need) == cudaSuccess) {
-                    acache = (uint32_t *)dev;
-                    mode = 1;
-                    ctx->crs_cache.push_back(lab_ctx::CrsEntry{std::move(key), acache, need});
+                    acache = (uint8_t *)dev;
+                    CK(cudaMemsetAsync(dev, 0, need, ctx->stream));          // padding rows / padding K stay zero
+                    ctx->crs_cache.push_back(lab_ctx::CrsEntry{std::move(key), (uint32_t *)dev, need});
                     ctx->crs_cache_used += need;
                 } else cudaGetLastError();
             }
@@ -459,20 +505,24 @@ static int d_commit_inner(lab_ctx *ctx, const LabSeed &seed, const uint32_t *Wha
     }
 #define KA_LAUNCH(ICV, MODEV)                                                                                                        \
     LAUNCH_SMEM((k_commit_inner<ICV, LAB_RM_COMMIT, LAB_KA_PP, MODEV>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, ICV), seed, What, \
-                (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T, t_stride, t_row_off, acache)
+                (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T, t_stride, t_row_off, acache, ntiles, kpad)
     for (uint64_t ib = 0; ib < R; ib += (uint64_t)KA_CONS * IC) {
+        if (hit) {                              // A is resident: tensor-core contraction for the vectors of this pass
+            TRY(d_commit_umma(ctx, acache, ntiles, kpad, What, N, R, ib, std::min<uint64_t>((uint64_t)KA_CONS * IC, R - ib), nrows, T, t_stride, t_row_off));
+            continue;
+        }
         switch (IC) {
             case 16:
-                if (mode == 2) KA_LAUNCH(16, 2); else if (mode == 1) KA_LAUNCH(16, 1); else KA_LAUNCH(16, 0);
+                if (acache) KA_LAUNCH(16, 1); else KA_LAUNCH(16, 0);
                 break;
             case 8: KA_LAUNCH(8, 0); break;
             case 4: KA_LAUNCH(4, 0); break;
             case 2: KA_LAUNCH(2, 0); break;
             default:
-                if (mode == 2) KA_LAUNCH(1, 2); else if (mode == 1) KA_LAUNCH(1, 1); else KA_LAUNCH(1, 0);
+                if (acache) KA_LAUNCH(1, 1); else KA_LAUNCH(1, 0);
                 break;
         }
-        if (mode == 1) mode = 2;          // later passes over more witness vectors (R > 64) already read the cache
+        if (acache) hit = true;                 // later passes (R > 64) already read the cache
     }
 #undef KA_LAUNCH
     return LAB_OK;

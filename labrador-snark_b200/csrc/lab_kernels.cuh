@@ -517,13 +517,14 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
 }
 
 // MODE 0: A regenerated from the seed (the reference's semantics).  MODE 1: the same, and every transformed polynomial is
-// also written to `acache` [nrows][N] hats (CRS cache, lab_crs_cache_configure).  MODE 2: the producers load the
-// polynomials from `acache` instead of running ChaCha20 -- the kernel is then bound by the consumers' IMADs (R = 64) or by
-// the HBM stream of A (R = 1, the verifier's A z).
+// also written to the CRS cache (lab_crs_cache_configure) as int8 limb planes -- the A operand of the tensor-core
+// commitment in lab_umma.cuh, which serves every later use of the same A: slot j, row block rb of 64 rows, limb l, row r,
+// byte k = 2n + {re, im} at ((j * a_ntiles + rb) * 128 + l * 64 + r) * a_kpad + k.
 template <int IC, uint32_t RM, int PP, int MODE = 0>
 __global__ void __launch_bounds__(ka_threads(PP), 1) k_commit_inner(LabSeed seed, const uint32_t *__restrict__ What, uint32_t N, uint32_t R,
                                                                      uint64_t row0, uint64_t nrows, uint32_t i_base, uint32_t *__restrict__ T,
-                                                                     uint64_t t_stride, uint64_t t_row_off, uint32_t *__restrict__ acache = nullptr) {
+                                                                     uint64_t t_stride, uint64_t t_row_off, uint8_t *__restrict__ acache = nullptr, uint32_t a_ntiles = 0,
+                                                                     uint32_t a_kpad = 0) {
     constexpr int PROD = ka_prod(PP), COLS = ka_cols(PP), TP = PROD * PP, THREADS = ka_threads(PP), NB = 2 * PP;
     __shared__ uint32_t Are[KA_DEPTH][TP][32], Aim[KA_DEPTH][TP][32], Anim[KA_DEPTH][TP][32];   // re, im, Q - im; polynomial col * 4 + row
     __shared__ uint64_t empty_bar[KA_DEPTH];                     // consumers -> producers: slot may be overwritten
@@ -558,18 +559,6 @@ __global__ void __launch_bounds__(ka_threads(PP), 1) k_commit_inner(LabSeed seed
             uint32_t c[NB];
 #pragma unroll
             for (int b = 0; b < NB; b++) c[b] = 0;
-            if (MODE == 2) {
-                if (row_ok) {
-#pragma unroll
-                    for (int p = 0; p < PP; p++) {
-                        const uint32_t col = COLS * t + gcol + p * (PROD / 4);
-                        if (col < N) {
-                            const uint32_t v = __ldcs(acache + ((rblk + grow) * (uint64_t)N + col) * 32 + lane);
-                            c[2 * p] = lab_re(v); c[2 * p + 1] = lab_im(v);
-                        }
-                    }
-                }
-            } else
             if (row_ok && COLS * t + gcol < N) {
                 const uint64_t s0 = seed.limb[0] + ctr;
                 const uint64_t ntag = ((uint64_t)(s0 < ctr) << 32) | (s0 >> 32);
@@ -610,7 +599,13 @@ __global__ void __launch_bounds__(ka_threads(PP), 1) k_commit_inner(LabSeed seed
                     if (PP > 1 && !(COLS * t + gcol + p * (PROD / 4) < N)) { c[2 * p] = 0; c[2 * p + 1] = 0; }   // column past N: zero polynomial
                     else {
                         lab_ntt32_fwd_warp_smem(c[2 * p], c[2 * p + 1], tws, lane, seed.one);
-                        if (MODE == 1) acache[((rblk + grow) * (uint64_t)N + COLS * t + gcol + p * (PROD / 4)) * 32 + lane] = lab_pack(c[2 * p], c[2 * p + 1]);
+                        if (MODE == 1) {
+                            const uint64_t row = rblk + grow, n = COLS * t + gcol + p * (PROD / 4);
+                            uint8_t *q8 = acache + (((uint64_t)lane * a_ntiles + (row >> 6)) * 128 + (row & 63)) * a_kpad + 2 * n;
+                            const uint32_t re_ = c[2 * p], im_ = c[2 * p + 1];
+                            *reinterpret_cast<uint16_t *>(q8) = (uint16_t)((re_ & 127u) | ((im_ & 127u) << 8));
+                            *reinterpret_cast<uint16_t *>(q8 + 64 * (uint64_t)a_kpad) = (uint16_t)((re_ >> 7) | ((im_ >> 7) << 8));
+                        }
                     }
                 }
             }
