@@ -1351,6 +1351,12 @@ extern "C" int lab_prove_batch(lab_ctx *ctx, const lab_constants *c, size_t n_st
         if (lab_ctx_create(ctx->device, &w) != LAB_OK) FAIL(LAB_ERR_CUDA, "cannot create batch worker context");
         ctx->workers.push_back(w);
     }
+    // one CRS for the whole batch: each worker keeps the transformed CRS polynomials of its first statement in HBM (CRS
+    // cache) and the remaining statements stream them back instead of re-running ChaCha20; dropped again at the end
+    const size_t worker_cache = (size_t)8 << 30;
+    if (shared_crs)
+        for (size_t t = 0; t < nw; t++)
+            if (!ctx->workers[t]->crs_cache_max) lab_crs_cache_configure(ctx->workers[t], worker_cache);
     std::vector<int> status(nw, LAB_OK);
     std::vector<std::thread> threads;
     for (size_t t = 0; t < nw; t++)
@@ -1364,6 +1370,8 @@ extern "C" int lab_prove_batch(lab_ctx *ctx, const lab_constants *c, size_t n_st
             }
         });
     for (auto &th : threads) th.join();
+    if (shared_crs)
+        for (size_t t = 0; t < nw; t++) lab_crs_cache_configure(ctx->workers[t], 0);
     for (size_t t = 0; t < nw; t++) {
         ctx->launches += ctx->workers[t]->launches;
         ctx->workers[t]->launches = 0;

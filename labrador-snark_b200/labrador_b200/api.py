@@ -387,7 +387,11 @@ class Context:
             outs.append(o)
             trs[i] = _lib.CTranscript(_p(o["u_1"]), 0, _p(o["projection_int"]), _p(o["projection"]), _p(o["b_prime_prime"]), _p(o["u_2"]),
                                       _p(o["z"]), _p(o["t"]), _p(o["g"]), _p(o["h"]), _p(o["phi_final"]), 0)
-        self._ck(self.L.lab_prove_batch(self._h, C.byref(c), C.c_size_t(B), _p(seedbuf), C.c_int(int(shared_crs)), _p(S), sts, chs, trs))
+        import time as _time
+        t0 = _time.perf_counter()
+        rc = self.L.lab_prove_batch(self._h, C.byref(c), C.c_size_t(B), _p(seedbuf), C.c_int(int(shared_crs)), _p(S), sts, chs, trs)
+        self.last_batch_seconds = _time.perf_counter() - t0        # the C call alone (host buffers in, transcripts out), without the ctypes marshalling above
+        self._ck(rc)
         for i in range(B):
             outs[i]["jl_attempt"] = trs[i].jl_attempt
             outs[i]["norm_sum"] = int(trs[i].norm_sum)

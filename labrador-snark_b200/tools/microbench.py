@@ -68,6 +68,22 @@ def main():
         print(json.dumps({"kernel": "commit_inner", "N": N, "R": R, "rows": rows, "ms_median": med,
                           "chacha_blocks_per_s": rows * N * 64 / (med * 1e-3)}), flush=True)
         ctx.free(dS); ctx.free(dT)
+    if "umma" in which:         # CRS-resident inner commitment on the tensor cores (lab_umma.cuh), cfg-3 shape on fewer rows
+        N, R, rows = 4096, 64, 64 * 148 * 2
+        c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
+        dS = ctx.malloc(R * N * 256)
+        ctx.synth_zq_dev(synth.SEED, 1, 0, R * N * 64, dS)
+        ctx.witness_load_dev(c, dS)
+        dT = ctx.malloc(R * rows * 256)
+        ctx.crs_cache_configure(rows * N * 128 + (1 << 20))
+        ctx.timer_start(); ctx.commit_inner_dev(SEED32, 0, rows, dT); t_fill = ctx.timer_stop()
+        best, med = timeit(ctx, lambda: ctx.commit_inner_dev(SEED32, 0, rows, dT), reps=3, warm=1)
+        a_bytes = rows * N * 128
+        print(json.dumps({"kernel": "commit_inner from the CRS cache (k_umma_commit + build_b + finish)", "N": N, "R": R, "rows": rows, "fill_ms": t_fill,
+                          "ms_median": med, "A_GBps": a_bytes / (med * 1e-3) / 1e9, "int8_TMACs_per_s": rows * N * R * 32 * 16 / (med * 1e-3) / 1e12,
+                          "cache": ctx.crs_cache_stats()}), flush=True)
+        ctx.crs_cache_configure(0)
+        ctx.free(dS); ctx.free(dT)
     if "prove" in which:        # default-size full proofs: latency, launch count, and the u_1 stage alone
         import time
         for (N, R) in ((2, 2), (4, 4), (8, 8)):
