@@ -665,8 +665,8 @@ def main():
                         "of its first double round and the dead tail of its last; "
                         "peak = LOP3+SHF microbenchmark measured in this run (no driver-measured INT32 peak exists); HBM is idle here"}
         # CRS-resident variant (reported beside the cold headline, never instead of it): with lab_crs_cache_configure the
-        # first commitment writes A through to HBM as transformed polynomials (137 GB at cfg 3); the next one under the
-        # same CRS streams it back and is bound by the consumers' IMADs instead of ChaCha20
+        # first commitment writes A through to HBM as int8 limb planes (137 GB at cfg 3); the next one under the same CRS is
+        # the tcgen05 contraction of lab_umma.cuh, which streams A once
         crs_cached = None
         if world == 1:
             try:
@@ -680,7 +680,11 @@ def main():
                     chk1 = int(T.view(torch.int64).sum().item())
                     crs_cached = {"commit_filling_cache_ms": t_fill, "commit_from_cache_ms": t_hit, "cache": ctx.crs_cache_stats(),
                                   "same_T_checksum": chk0 == chk1, "witness_coeffs_per_s_from_cache": N * R * D / (t_hit * 1e-3),
-                                  "imad_bound_ms": nrows * N * R * 32 * 4 / alu_peak * 1e3}
+                                  "cuda_core_imad_bound_ms": nrows * N * R * 32 * 4 / alu_peak * 1e3,
+                                  "roofline": {"kernel": "k_umma_commit (+ k_umma_build_b, k_umma_finish)", "bound": "hbm", "achieved": need / (t_hit * 1e-3) / 1e9,
+                                               "peak": float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0,
+                                               "unit": "GB/s", "algorithmic_bytes": need, "note": "A as int8 limb planes read once; achieved includes the B builder and the finish kernel"}}
+                    crs_cached["roofline"]["frac"] = crs_cached["roofline"]["achieved"] / crs_cached["roofline"]["peak"]
                 else:
                     crs_cached = {"skipped": f"needs {need} bytes of HBM for A, {free_b} free"}
             except Exception as e:

@@ -208,8 +208,11 @@ int lab_verify(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], con
  * D_ijk) through to HBM, and any later call on this ctx with the same seed, shape and row range -- Verifier::verify
  * recomputing u_1 / u_2 right after the proof (verification.rs:372-435), or further proofs under the same CRS object
  * (CRS is borrowed &mut but never mutated, proofgen.rs:30) -- streams them back at HBM speed instead of running
- * ChaCha20 (128 B per polynomial; (32,32) needs 103 GB).  Results are bit-identical.  Off by default (max_bytes = 0): a
- * single proof then regenerates its CRS exactly like the reference.  Entries that do not fit stay uncached. */
+ * ChaCha20 (128 B per polynomial; (32,32) needs 103 GB).  The inner commitment does the same for A (as int8 limb planes)
+ * and serves every later use of that A -- more than 64 witness vectors, the verifier's A z (verification.rs:274-279), the
+ * next proof -- with a tcgen05 int8 contraction that streams A once from HBM (cfg 3: 34 ms instead of 3 s).  Results are
+ * bit-identical.  Off by default (max_bytes = 0): a single proof then regenerates its CRS exactly like the reference.
+ * Entries that do not fit stay uncached. */
 int lab_crs_cache_configure(lab_ctx *ctx, size_t max_bytes);
 int lab_crs_cache_stats(const lab_ctx *ctx, size_t *bytes_used, uint64_t *hits, uint64_t *misses);
 
