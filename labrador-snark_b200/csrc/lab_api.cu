@@ -445,21 +445,30 @@ static int make_map(lab_ctx *ctx, CUtensorMap *map, void *base, uint64_t rows, u
     return LAB_OK;
 }
 // T[i][t_row_off + row] for vectors i in [ib, ib + ni) and all cached rows, from the int8 limb planes of A
+struct UmmaScratch { int8_t *Bp = nullptr; uint32_t *Th = nullptr; };      // B planes and slot planes, reused by the passes of one call
 static int d_commit_umma(lab_ctx *ctx, uint8_t *acache, uint32_t ntiles, uint32_t kpad, const uint32_t *What, uint64_t N, uint64_t R, uint64_t ib, uint64_t ni,
-                         uint64_t nrows, uint32_t *T, uint64_t t_stride, uint64_t t_row_off) {
+                         uint64_t nrows, uint32_t *T, uint64_t t_stride, uint64_t t_row_off, UmmaScratch &sc) {
     const uint32_t ncols = (uint32_t)((4 * ni + 15) / 16 * 16), rows_pad = ntiles * 64;
-    int8_t *Bp;
-    uint32_t *Th;
-    TRY(arena_alloc(ctx, (size_t)32 * ncols * kpad, &Bp));
-    TRY(arena_alloc(ctx, (size_t)32 * ni * rows_pad, &Th));
+    // s32 accumulators: at most 32768 bytes of K per contraction (32768 * 127^2 < 2^29.1); longer rows are cut into K-segments
+    // whose results k_umma_finish adds mod q
+    const uint32_t total_chunks = kpad / 128, seg_chunks = 256, nseg = (total_chunks + seg_chunks - 1) / seg_chunks;
+    const size_t seg_stride = (size_t)32 * ni * rows_pad;
+    if (!sc.Bp) {        // sized for a full pass of 64 vectors over this many rows; later passes and row chunks are never larger
+        TRY(arena_alloc(ctx, (size_t)32 * 256 * kpad, &sc.Bp));
+        TRY(arena_alloc(ctx, (size_t)32 * 64 * rows_pad * nseg, &sc.Th));
+    }
+    int8_t *Bp = sc.Bp;
+    uint32_t *Th = sc.Th;
     CK(cudaMemsetAsync(Bp, 0, (size_t)32 * ncols * kpad, ctx->stream));
     LAUNCH(k_umma_build_b, grid_for(N * ni * 32, 256, ctx->sms * 16), 256, What, (uint32_t)N, (uint32_t)R, (uint32_t)ib, (uint32_t)ni, ncols, kpad, Bp);
     CUtensorMap mapA, mapB;
     TRY(make_map(ctx, &mapA, acache, (uint64_t)32 * ntiles * 128, kpad, 128));
     TRY(make_map(ctx, &mapB, Bp, (uint64_t)32 * ncols, kpad, ncols));
     const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)ctx->sms, (uint64_t)32 * ntiles);
-    LAUNCH_SMEM(k_umma_commit, grid, UM_THREADS, UM_SMEM, mapA, mapB, ntiles, kpad / 128, ncols, (uint32_t)ni, rows_pad, Th);
-    LAUNCH(k_umma_finish, dim3(rows_pad / 32, (unsigned)ni), 256, Th, (uint32_t)ni, rows_pad, nrows, (uint32_t)ib, T, t_stride, t_row_off);
+    for (uint32_t g = 0; g < nseg; g++)
+        LAUNCH_SMEM(k_umma_commit, grid, UM_THREADS, UM_SMEM, mapA, mapB, ntiles, g * seg_chunks, std::min(seg_chunks, total_chunks - g * seg_chunks), ncols,
+                    (uint32_t)ni, rows_pad, Th + g * seg_stride);
+    LAUNCH(k_umma_finish, dim3(rows_pad / 32, (unsigned)ni), 256, Th, nseg, seg_stride, (uint32_t)ni, rows_pad, nrows, (uint32_t)ib, T, t_stride, t_row_off);
     return LAB_OK;
 }
 
@@ -481,7 +490,7 @@ static int d_commit_inner(lab_ctx *ctx, const LabSeed &seed, const uint32_t *Wha
     uint8_t *acache = nullptr;
     bool hit = false;
     const uint32_t kpad = (uint32_t)((2 * N + 127) / 128 * 128), ntiles = (uint32_t)((nrows + 63) / 64);
-    if (ctx->crs_cache_max && (IC == 16 || IC == 1) && N <= 16384) {
+    if (ctx->crs_cache_max && (IC == 16 || IC == 1)) {
         std::vector<unsigned char> key(sizeof(seed.limb) + 4 * sizeof(uint64_t));
         const uint64_t tag = 0x41ull /* 'A' */, kv[4] = {tag, N, row0, nrows};
         std::memcpy(key.data(), seed.limb, sizeof(seed.limb));
@@ -503,12 +512,54 @@ static int d_commit_inner(lab_ctx *ctx, const LabSeed &seed, const uint32_t *Wha
             }
         }
     }
+    // More than 64 witness vectors and no cached A: instead of regenerating A once per 64 vectors, generate it once per
+    // chunk of rows into a transient buffer of limb planes (first 64 vectors on the CUDA cores, MODE 1) and let the tensor
+    // cores contract the chunk with the remaining vectors.  ChaCha20 runs once per CRS coefficient again.
+    if (!acache && R > (uint64_t)KA_CONS * 16 && IC == 16) {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const size_t per_row = (size_t)32 * 2 * kpad;
+        // scratch the contraction itself needs (B planes, slot planes) is taken from the arena; leave room for it
+        const size_t reserve = (size_t)32 * 256 * kpad + ((size_t)8 << 30);
+        size_t budget = free_b > reserve ? (free_b - reserve) / 2 : 0;
+        budget = std::min<size_t>(budget, (size_t)64 << 30);
+        uint64_t rows_c = budget / per_row / 64 * 64;
+        if (rows_c > nrows) rows_c = (nrows + 63) / 64 * 64;
+        if (rows_c >= 64) {
+            void *chunk = nullptr;
+            if (cudaMalloc(&chunk, rows_c * per_row) == cudaSuccess) {
+                int rc = LAB_OK;
+                UmmaScratch sc;              // first use is the largest (rows_c rows): the arena allocation fits every chunk
+                for (uint64_t r0 = 0; r0 < nrows && rc == LAB_OK; r0 += rows_c) {
+                    const uint64_t nr = std::min<uint64_t>(rows_c, nrows - r0);
+                    const uint32_t nt = (uint32_t)((nr + 63) / 64);
+                    if ((nr & 63) || (2 * N) % 128) {                 // padding rows / padding K must read as zero
+                        cudaError_t e = cudaMemsetAsync(chunk, 0, (size_t)nt * 64 * per_row, ctx->stream);
+                        if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = LAB_ERR_CUDA; break; }
+                    }
+                    const unsigned g2 = (unsigned)((nr + KA_RT - 1) / KA_RT);
+                    rc = [&]() -> int {
+                        LAUNCH_SMEM((k_commit_inner<16, LAB_RM_COMMIT, LAB_KA_PP, 1>), g2, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, 16), seed, What, (uint32_t)N,
+                                    (uint32_t)R, row0 + r0, nr, 0u, T, t_stride, t_row_off + r0, (uint8_t *)chunk, nt, kpad);
+                        return LAB_OK;
+                    }();
+                    for (uint64_t ib = 64; ib < R && rc == LAB_OK; ib += 64)
+                        rc = d_commit_umma(ctx, (uint8_t *)chunk, nt, kpad, What, N, R, ib, std::min<uint64_t>(64, R - ib), nr, T, t_stride, t_row_off + r0, sc);
+                }
+                cudaStreamSynchronize(ctx->stream);
+                cudaFree(chunk);
+                return rc;
+            }
+            cudaGetLastError();          // no room for a chunk: fall through to one ChaCha20 pass per 64 vectors
+        }
+    }
 #define KA_LAUNCH(ICV, MODEV)                                                                                                        \
     LAUNCH_SMEM((k_commit_inner<ICV, LAB_RM_COMMIT, LAB_KA_PP, MODEV>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, ICV), seed, What, \
                 (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T, t_stride, t_row_off, acache, ntiles, kpad)
+    UmmaScratch sc;
     for (uint64_t ib = 0; ib < R; ib += (uint64_t)KA_CONS * IC) {
         if (hit) {                              // A is resident: tensor-core contraction for the vectors of this pass
-            TRY(d_commit_umma(ctx, acache, ntiles, kpad, What, N, R, ib, std::min<uint64_t>((uint64_t)KA_CONS * IC, R - ib), nrows, T, t_stride, t_row_off));
+            TRY(d_commit_umma(ctx, acache, ntiles, kpad, What, N, R, ib, std::min<uint64_t>((uint64_t)KA_CONS * IC, R - ib), nrows, T, t_stride, t_row_off, sc));
             continue;
         }
         switch (IC) {

@@ -71,8 +71,8 @@ __global__ void __launch_bounds__(256) k_umma_build_b(const uint32_t *__restrict
 
 // Th[j][v][rows_pad] packed slots (re | im << 16), v = vector index within the pass
 __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_commit(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                                                               uint32_t ntiles /* row blocks of 64 */, uint32_t nchunks /* K' / 128 */, uint32_t ncols /* N' */,
-                                                               uint32_t nvec, uint32_t rows_pad, uint32_t *__restrict__ Th) {
+                                                               uint32_t ntiles /* row blocks of 64 */, uint32_t chunk0, uint32_t nchunks /* K range in 128-byte chunks */,
+                                                               uint32_t ncols /* N' */, uint32_t nvec, uint32_t rows_pad, uint32_t *__restrict__ Th) {
     extern __shared__ __align__(1024) uint8_t um_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)um_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;                                   // [stages][128][128]
@@ -108,8 +108,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_commit(const __grid_cons
                     const uint32_t s = it % UM_STAGES;
                     if (it >= UM_STAGES) um_mbar_wait(&empty[s], ((it / UM_STAGES) - 1) & 1);
                     um_expect_tx(&full[s], stage_tx);
-                    um_tma_2d(sA + s * 128 * UM_KC, &mapA, (int)(c * UM_KC), rowA, &full[s]);
-                    um_tma_2d(sB + s * 256 * UM_KC, &mapB, (int)(c * UM_KC), rowB, &full[s]);
+                    um_tma_2d(sA + s * 128 * UM_KC, &mapA, (int)((chunk0 + c) * UM_KC), rowA, &full[s]);
+                    um_tma_2d(sB + s * 256 * UM_KC, &mapB, (int)((chunk0 + c) * UM_KC), rowB, &full[s]);
                 }
             }
         }
@@ -190,14 +190,22 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_commit(const __grid_cons
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "n"(512));
 }
 
-// slot planes -> T: CTA = (32 rows, one vector); transposes [32 slots][32 rows] through shared memory, inverse transform per row
-__global__ void __launch_bounds__(256) k_umma_finish(const uint32_t *__restrict__ Th, uint32_t nvec, uint32_t rows_pad, uint64_t nrows, uint32_t i_base,
-                                                     uint32_t *__restrict__ T, uint64_t t_stride, uint64_t t_row_off) {
+// slot planes -> T: CTA = (32 rows, one vector); sums the nseg K-segments (s32 accumulators hold at most 32768 bytes of K each),
+// transposes [32 slots][32 rows] through shared memory, inverse transform per row
+__global__ void __launch_bounds__(256) k_umma_finish(const uint32_t *__restrict__ Th, uint32_t nseg, size_t seg_stride, uint32_t nvec, uint32_t rows_pad,
+                                                     uint64_t nrows, uint32_t i_base, uint32_t *__restrict__ T, uint64_t t_stride, uint64_t t_row_off) {
     __shared__ uint32_t tile[32][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t vec = blockIdx.y;
     const uint64_t row0 = (uint64_t)blockIdx.x * 32;
-    for (int s = w; s < 32; s += 8) tile[s][lane] = Th[((size_t)s * nvec + vec) * rows_pad + row0 + lane];
+    for (int s = w; s < 32; s += 8) {
+        uint32_t re = 0, im = 0;
+        for (uint32_t g = 0; g < nseg; g++) {
+            const uint32_t v = Th[g * seg_stride + ((size_t)s * nvec + vec) * rows_pad + row0 + lane];
+            re += lab_re(v); im += lab_im(v);
+        }
+        tile[s][lane] = lab_pack(lab_canon(re), lab_canon(im));
+    }
     __syncthreads();
     const LabWarpTw tw = lab_warp_tw(lane);
     for (int rr = w; rr < 32; rr += 8) {

@@ -479,3 +479,16 @@ def test_crs_cache_is_transparent(ctx, orc):
         assert np.array_equal(tr4["u_1"], ref["u_1"])
     finally:
         c2.close()
+
+
+@pytest.mark.parametrize("N,R,row0,nrows", [(3, 70, 1, 21), (5, 130, 0, 70), (16400, 65, 2, 3)])
+def test_commit_inner_more_than_64_vectors_uses_one_chacha_pass(ctx, orc, N, R, row0, nrows):
+    """R > 64: A is generated once per row chunk into transient int8 limb planes (first 64 vectors on the CUDA cores) and
+    the remaining vectors are contracted on the tensor cores (lab_umma.cuh); N = 16400 needs two K-segments (s32
+    accumulators).  Bit-exact against the oracle, which multiplies row by row."""
+    c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
+    co, _ = orc.constants(N, R)
+    S = synth.uniform_witness(N, R, seed=N + R)
+    got = ctx.commit_inner(c, SEED32, S, row0=row0, nrows=nrows)
+    ref = orc.commit_inner_rows(co, SEED32, S, row0, nrows, ntt=True, nthreads=8)
+    assert np.array_equal(got, ref)
