@@ -54,6 +54,10 @@ struct lab_ctx {
     std::vector<CrsEntry> crs_cache;
     size_t crs_cache_max = 0, crs_cache_used = 0;
     uint64_t crs_cache_hits = 0, crs_cache_misses = 0;
+    // transient limb planes of the generate-then-contract path: kept between calls (a 64 GB cudaMalloc/cudaFree pair costs
+    // hundreds of milliseconds), released by lab_crs_cache_configure and lab_ctx_destroy
+    void *gc_chunk = nullptr;
+    size_t gc_chunk_bytes = 0;
     // worker contexts (own stream + arena each) for lab_prove_batch: independent statements overlap host-side
     // enqueueing of one proof with the GPU work of the others
     std::vector<lab_ctx *> workers;
@@ -203,6 +207,7 @@ extern "C" void lab_ctx_destroy(lab_ctx *ctx) {
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
     for (auto &p : ctx->mv_plans) cudaFree(p.dev);
     for (auto &e : ctx->crs_cache) cudaFree(e.dev);
+    if (ctx->gc_chunk) cudaFree(ctx->gc_chunk);
     for (lab_ctx *w : ctx->workers) lab_ctx_destroy(w);
     lab_comm_destroy(ctx);
     cudaStreamDestroy(ctx->stream);
@@ -472,6 +477,24 @@ static int d_commit_umma(lab_ctx *ctx, uint8_t *acache, uint32_t ntiles, uint32_
     return LAB_OK;
 }
 
+// transient limb planes for `rows_c` rows of `per_row` bytes (kept in the ctx between calls); nullptr when there is no room
+static void *gc_chunk_get(lab_ctx *ctx, size_t bytes) {
+    if (ctx->gc_chunk && ctx->gc_chunk_bytes >= bytes) return ctx->gc_chunk;
+    if (ctx->gc_chunk) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->gc_chunk); ctx->gc_chunk = nullptr; ctx->gc_chunk_bytes = 0; }
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    ctx->gc_chunk = p;
+    ctx->gc_chunk_bytes = bytes;
+    return p;
+}
+static void gc_chunk_release(lab_ctx *ctx) {
+    if (!ctx->gc_chunk) return;
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->gc_chunk);
+    ctx->gc_chunk = nullptr;
+    ctx->gc_chunk_bytes = 0;
+}
+
 static int d_commit_inner(lab_ctx *ctx, const LabSeed &seed, const uint32_t *What, uint64_t N, uint64_t R, uint64_t row0, uint64_t nrows, uint32_t *T,
                           uint64_t t_stride = 0, uint64_t t_row_off = 0) {
     if (!t_stride) t_stride = nrows;            // default: T is exactly [R][nrows][64]
@@ -481,99 +504,92 @@ static int d_commit_inner(lab_ctx *ctx, const LabSeed &seed, const uint32_t *Wha
         u128 last = ((u128)(row0 + nrows) * N + N) * 64;
         if (last >> 64) FAIL(LAB_ERR_PARAMS, "A counter exceeds 64 bits");
     }
-    const unsigned grid = (unsigned)((nrows + KA_RT - 1) / KA_RT);
-    // four consumer warps x IC witness vectors per pass
-    const int IC = R > 32 ? 16 : (R > 16 ? 8 : (R > 8 ? 4 : (R > 4 ? 2 : 1)));
-    // CRS cache (lab_crs_cache_configure): A as int8 limb planes (lab_umma.cuh), keyed by seed, N and the row range.  The
-    // first use generates A with ChaCha20 and writes it through (MODE 1); every later use -- further passes over more
-    // witness vectors, the verifier's A z, the next proof under this CRS -- is the tcgen05 contraction d_commit_umma.
-    uint8_t *acache = nullptr;
-    bool hit = false;
     const uint32_t kpad = (uint32_t)((2 * N + 127) / 128 * 128), ntiles = (uint32_t)((nrows + 63) / 64);
-    if (ctx->crs_cache_max && (IC == 16 || IC == 1)) {
+    const size_t per_row = (size_t)32 * 2 * kpad;                  // bytes of limb planes per row of A
+    auto gen_planes = [&](uint8_t *planes, uint64_t r0, uint64_t nr, uint32_t nt) -> int {
+        if ((nr & 63) || (2 * N) % 128) CK(cudaMemsetAsync(planes, 0, (size_t)nt * 64 * per_row, ctx->stream));   // padding rows / K read as zero
+        LAUNCH(k_gen_planes, (unsigned)(ctx->sms * 3), 32 * GP_WARPS, seed, (uint32_t)N, row0 + r0, nr, planes, nt, kpad);
+        return LAB_OK;
+    };
+    auto contract = [&](uint8_t *planes, uint64_t r0, uint64_t nr, uint32_t nt, UmmaScratch &sc) -> int {
+        for (uint64_t ib = 0; ib < R; ib += 64)
+            TRY(d_commit_umma(ctx, planes, nt, kpad, What, N, R, ib, std::min<uint64_t>(64, R - ib), nr, T, t_stride, t_row_off + r0, sc));
+        return LAB_OK;
+    };
+    // (1) CRS cache (lab_crs_cache_configure): A as int8 limb planes, keyed by seed, N and the row range.  A miss
+    //     regenerates A into the cache, a hit goes straight to the tensor-core contraction.
+    if (ctx->crs_cache_max) {
         std::vector<unsigned char> key(sizeof(seed.limb) + 4 * sizeof(uint64_t));
         const uint64_t tag = 0x41ull /* 'A' */, kv[4] = {tag, N, row0, nrows};
         std::memcpy(key.data(), seed.limb, sizeof(seed.limb));
         std::memcpy(key.data() + sizeof(seed.limb), kv, sizeof kv);
+        uint8_t *acache = nullptr;
         for (auto &e : ctx->crs_cache)
-            if (e.key == key) { acache = (uint8_t *)e.dev; hit = true; break; }
-        if (hit) ctx->crs_cache_hits++;
-        else {
-            ctx->crs_cache_misses++;
-            const size_t need = (size_t)32 * ntiles * 128 * kpad;
-            if (ctx->crs_cache_used + need <= ctx->crs_cache_max) {
-                void *dev = nullptr;
-                if (cudaMalloc(&dev, need) == cudaSuccess) {
-                    acache = (uint8_t *)dev;
-                    CK(cudaMemsetAsync(dev, 0, need, ctx->stream));          // padding rows / padding K stay zero
-                    ctx->crs_cache.push_back(lab_ctx::CrsEntry{std::move(key), (uint32_t *)dev, need});
-                    ctx->crs_cache_used += need;
-                } else cudaGetLastError();
+            if (e.key == key) { acache = (uint8_t *)e.dev; break; }
+        UmmaScratch sc;
+        if (acache) {
+            ctx->crs_cache_hits++;
+            return contract(acache, 0, nrows, ntiles, sc);
+        }
+        ctx->crs_cache_misses++;
+        const size_t need = (size_t)ntiles * 64 * per_row;
+        if (ctx->crs_cache_used + need <= ctx->crs_cache_max) {
+            void *dev = nullptr;
+            if (cudaMalloc(&dev, need) == cudaSuccess) {
+                ctx->crs_cache.push_back(lab_ctx::CrsEntry{std::move(key), (uint32_t *)dev, need});
+                ctx->crs_cache_used += need;
+                TRY(gen_planes((uint8_t *)dev, 0, nrows, ntiles));
+                return contract((uint8_t *)dev, 0, nrows, ntiles, sc);
             }
+            cudaGetLastError();
         }
     }
-    // More than 64 witness vectors and no cached A: instead of regenerating A once per 64 vectors, generate it once per
-    // chunk of rows into a transient buffer of limb planes (first 64 vectors on the CUDA cores, MODE 1) and let the tensor
-    // cores contract the chunk with the remaining vectors.  ChaCha20 runs once per CRS coefficient again.
-    if (!acache && R > (uint64_t)KA_CONS * 16 && IC == 16) {
+    // (2) Generate-then-contract, the large-shape cold path (cfg 3 / cfg 4) and every shape with more than 64 witness vectors:
+    //     per chunk of rows k_gen_planes regenerates A into transient limb planes with every warp of the GPU running ChaCha20
+    //     (no consumer warps competing for issue slots and the FMA pipe), then the tensor cores contract the chunk with all
+    //     witness vectors.  ChaCha20 runs once per CRS coefficient whatever R is; the contraction adds about 1 %.
+    uint64_t gc_min = (uint64_t)1 << 22;            // polynomials of A from which it pays (LAB_GEN_CONTRACT_MIN_POLYS overrides; 0 = never)
+    if (const char *e = std::getenv("LAB_GEN_CONTRACT_MIN_POLYS")) { gc_min = std::strtoull(e, nullptr, 10); if (!gc_min) gc_min = ~0ull; }
+    if ((uint64_t)nrows * N >= gc_min || (R > 64 && gc_min != ~0ull)) {
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
-        const size_t per_row = (size_t)32 * 2 * kpad;
-        // scratch the contraction itself needs (B planes, slot planes) is taken from the arena; leave room for it
-        const size_t reserve = (size_t)32 * 256 * kpad + ((size_t)8 << 30);
+        free_b += ctx->gc_chunk_bytes;                      // the chunk of an earlier call is reused or replaced
+        const size_t reserve = (size_t)32 * 256 * kpad + ((size_t)8 << 30);       // B planes, slot planes, other scratch
         size_t budget = free_b > reserve ? (free_b - reserve) / 2 : 0;
         budget = std::min<size_t>(budget, (size_t)64 << 30);
         uint64_t rows_c = budget / per_row / 64 * 64;
         if (rows_c > nrows) rows_c = (nrows + 63) / 64 * 64;
+        const uint64_t have = ctx->gc_chunk_bytes / per_row / 64 * 64;
+        if (have >= std::min<uint64_t>(rows_c, 4096)) rows_c = std::min<uint64_t>(rows_c, have);   // keep a chunk of useful size rather than reallocating
         if (rows_c >= 64) {
-            void *chunk = nullptr;
-            if (cudaMalloc(&chunk, rows_c * per_row) == cudaSuccess) {
-                int rc = LAB_OK;
+            uint8_t *chunk = (uint8_t *)gc_chunk_get(ctx, rows_c * per_row);
+            if (chunk) {
                 UmmaScratch sc;              // first use is the largest (rows_c rows): the arena allocation fits every chunk
-                for (uint64_t r0 = 0; r0 < nrows && rc == LAB_OK; r0 += rows_c) {
+                for (uint64_t r0 = 0; r0 < nrows; r0 += rows_c) {
                     const uint64_t nr = std::min<uint64_t>(rows_c, nrows - r0);
                     const uint32_t nt = (uint32_t)((nr + 63) / 64);
-                    if ((nr & 63) || (2 * N) % 128) {                 // padding rows / padding K must read as zero
-                        cudaError_t e = cudaMemsetAsync(chunk, 0, (size_t)nt * 64 * per_row, ctx->stream);
-                        if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = LAB_ERR_CUDA; break; }
-                    }
-                    const unsigned g2 = (unsigned)((nr + KA_RT - 1) / KA_RT);
-                    rc = [&]() -> int {
-                        LAUNCH_SMEM((k_commit_inner<16, LAB_RM_COMMIT, LAB_KA_PP, 1>), g2, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, 16), seed, What, (uint32_t)N,
-                                    (uint32_t)R, row0 + r0, nr, 0u, T, t_stride, t_row_off + r0, (uint8_t *)chunk, nt, kpad);
-                        return LAB_OK;
-                    }();
-                    for (uint64_t ib = 64; ib < R && rc == LAB_OK; ib += 64)
-                        rc = d_commit_umma(ctx, (uint8_t *)chunk, nt, kpad, What, N, R, ib, std::min<uint64_t>(64, R - ib), nr, T, t_stride, t_row_off + r0, sc);
+                    TRY(gen_planes(chunk, r0, nr, nt));
+                    TRY(contract(chunk, r0, nr, nt, sc));
                 }
-                cudaStreamSynchronize(ctx->stream);
-                cudaFree(chunk);
-                return rc;
+                return LAB_OK;
             }
-            cudaGetLastError();          // no room for a chunk: fall through to one ChaCha20 pass per 64 vectors
         }
     }
-#define KA_LAUNCH(ICV, MODEV)                                                                                                        \
-    LAUNCH_SMEM((k_commit_inner<ICV, LAB_RM_COMMIT, LAB_KA_PP, MODEV>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, ICV), seed, What, \
-                (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T, t_stride, t_row_off, acache, ntiles, kpad)
-    UmmaScratch sc;
+    // (3) K_A: the fused warp-specialised kernel (small and medium shapes; also the fallback when there is no room for a
+    //     chunk, then with one ChaCha20 pass per 64 witness vectors)
+    const unsigned grid = (unsigned)((nrows + KA_RT - 1) / KA_RT);
+    const int IC = R > 32 ? 16 : (R > 16 ? 8 : (R > 8 ? 4 : (R > 4 ? 2 : 1)));      // four consumer warps x IC witness vectors per pass
+#define KA_LAUNCH(ICV)                                                                                                               \
+    LAUNCH_SMEM((k_commit_inner<ICV, LAB_RM_COMMIT, LAB_KA_PP>), grid, ka_threads(LAB_KA_PP), ka_dyn_smem(LAB_KA_PP, ICV), seed, What, \
+                (uint32_t)N, (uint32_t)R, row0, nrows, (uint32_t)ib, T, t_stride, t_row_off)
     for (uint64_t ib = 0; ib < R; ib += (uint64_t)KA_CONS * IC) {
-        if (hit) {                              // A is resident: tensor-core contraction for the vectors of this pass
-            TRY(d_commit_umma(ctx, acache, ntiles, kpad, What, N, R, ib, std::min<uint64_t>((uint64_t)KA_CONS * IC, R - ib), nrows, T, t_stride, t_row_off, sc));
-            continue;
-        }
         switch (IC) {
-            case 16:
-                if (acache) KA_LAUNCH(16, 1); else KA_LAUNCH(16, 0);
-                break;
-            case 8: KA_LAUNCH(8, 0); break;
-            case 4: KA_LAUNCH(4, 0); break;
-            case 2: KA_LAUNCH(2, 0); break;
-            default:
-                if (acache) KA_LAUNCH(1, 1); else KA_LAUNCH(1, 0);
-                break;
+            case 16: KA_LAUNCH(16); break;
+            case 8: KA_LAUNCH(8); break;
+            case 4: KA_LAUNCH(4); break;
+            case 2: KA_LAUNCH(2); break;
+            default: KA_LAUNCH(1); break;
         }
-        if (acache) hit = true;                 // later passes (R > 64) already read the cache
     }
 #undef KA_LAUNCH
     return LAB_OK;
@@ -1434,6 +1450,7 @@ extern "C" int lab_prove_batch(lab_ctx *ctx, const lab_constants *c, size_t n_st
 extern "C" int lab_crs_cache_configure(lab_ctx *ctx, size_t max_bytes) {
     if (!ctx) return LAB_ERR_PARAMS;
     cudaSetDevice(ctx->device);
+    gc_chunk_release(ctx);                          // the transient planes of the cold path make room for cache entries
     if (max_bytes < ctx->crs_cache_used) {          // shrinking: drop everything (entries are regenerated on demand)
         CK(cudaStreamSynchronize(ctx->stream));
         for (auto &e : ctx->crs_cache) cudaFree(e.dev);

@@ -516,15 +516,10 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
     return v;
 }
 
-// MODE 0: A regenerated from the seed (the reference's semantics).  MODE 1: the same, and every transformed polynomial is
-// also written to the CRS cache (lab_crs_cache_configure) as int8 limb planes -- the A operand of the tensor-core
-// commitment in lab_umma.cuh, which serves every later use of the same A: slot j, row block rb of 64 rows, limb l, row r,
-// byte k = 2n + {re, im} at ((j * a_ntiles + rb) * 128 + l * 64 + r) * a_kpad + k.
-template <int IC, uint32_t RM, int PP, int MODE = 0>
+template <int IC, uint32_t RM, int PP>
 __global__ void __launch_bounds__(ka_threads(PP), 1) k_commit_inner(LabSeed seed, const uint32_t *__restrict__ What, uint32_t N, uint32_t R,
                                                                      uint64_t row0, uint64_t nrows, uint32_t i_base, uint32_t *__restrict__ T,
-                                                                     uint64_t t_stride, uint64_t t_row_off, uint8_t *__restrict__ acache = nullptr, uint32_t a_ntiles = 0,
-                                                                     uint32_t a_kpad = 0) {
+                                                                     uint64_t t_stride, uint64_t t_row_off) {
     constexpr int PROD = ka_prod(PP), COLS = ka_cols(PP), TP = PROD * PP, THREADS = ka_threads(PP), NB = 2 * PP;
     __shared__ uint32_t Are[KA_DEPTH][TP][32], Aim[KA_DEPTH][TP][32], Anim[KA_DEPTH][TP][32];   // re, im, Q - im; polynomial col * 4 + row
     __shared__ uint64_t empty_bar[KA_DEPTH];                     // consumers -> producers: slot may be overwritten
@@ -599,13 +594,6 @@ __global__ void __launch_bounds__(ka_threads(PP), 1) k_commit_inner(LabSeed seed
                     if (PP > 1 && !(COLS * t + gcol + p * (PROD / 4) < N)) { c[2 * p] = 0; c[2 * p + 1] = 0; }   // column past N: zero polynomial
                     else {
                         lab_ntt32_fwd_warp_smem(c[2 * p], c[2 * p + 1], tws, lane, seed.one);
-                        if (MODE == 1) {
-                            const uint64_t row = rblk + grow, n = COLS * t + gcol + p * (PROD / 4);
-                            uint8_t *q8 = acache + (((uint64_t)lane * a_ntiles + (row >> 6)) * 128 + (row & 63)) * a_kpad + 2 * n;
-                            const uint32_t re_ = c[2 * p], im_ = c[2 * p + 1];
-                            *reinterpret_cast<uint16_t *>(q8) = (uint16_t)((re_ & 127u) | ((im_ & 127u) << 8));
-                            *reinterpret_cast<uint16_t *>(q8 + 64 * (uint64_t)a_kpad) = (uint16_t)((re_ >> 7) | ((im_ >> 7) << 8));
-                        }
                     }
                 }
             }

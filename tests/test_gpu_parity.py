@@ -492,3 +492,19 @@ def test_commit_inner_more_than_64_vectors_uses_one_chacha_pass(ctx, orc, N, R, 
     got = ctx.commit_inner(c, SEED32, S, row0=row0, nrows=nrows)
     ref = orc.commit_inner_rows(co, SEED32, S, row0, nrows, ntt=True, nthreads=8)
     assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("N,R,row0,nrows", [(1, 1, 0, 5), (3, 2, 1, 21), (5, 130, 0, 70), (33, 64, 3, 130), (16400, 3, 2, 3)])
+def test_commit_inner_generate_then_contract(ctx, orc, N, R, row0, nrows, monkeypatch):
+    """The large-shape cold path (k_gen_planes: every warp regenerates A into int8 limb planes; k_umma_commit: tensor-core
+    contraction with all witness vectors), forced on small shapes the oracle can check: ragged rows and columns (zero
+    padding of planes), R = 1 (N' = 16), several passes of 64 vectors, two K-segments."""
+    monkeypatch.setenv("LAB_GEN_CONTRACT_MIN_POLYS", "1")
+    c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
+    co, _ = orc.constants(N, R)
+    S = synth.uniform_witness(N, R, seed=3 * N + R)
+    got = ctx.commit_inner(c, SEED32, S, row0=row0, nrows=nrows)
+    ref = orc.commit_inner_rows(co, SEED32, S, row0, nrows, ntt=True, nthreads=8)
+    assert np.array_equal(got, ref)
+    monkeypatch.setenv("LAB_GEN_CONTRACT_MIN_POLYS", "0")          # 0 = never: the warp-specialised K_A path
+    assert np.array_equal(ctx.commit_inner(c, SEED32, S, row0=row0, nrows=nrows), ref)
