@@ -54,7 +54,11 @@ __device__ __forceinline__ uint64_t um_desc(uint32_t saddr) {
 // runs of 16 consecutive columns of one row, so that the two 16-bit stores per lane and polynomial fill whole 32-byte
 // sectors in L2 before they reach HBM.
 constexpr int GP_WARPS = 8;
-__global__ void __launch_bounds__(32 * GP_WARPS, 3) k_gen_planes(LabSeed seed, uint32_t N, uint64_t row0, uint64_t nrows, uint8_t *__restrict__ planes,
+#ifndef LAB_GP_MINB
+#define LAB_GP_MINB 3
+#endif
+template <int MINB>
+__global__ void __launch_bounds__(32 * GP_WARPS, MINB) k_gen_planes(LabSeed seed, uint32_t N, uint64_t row0, uint64_t nrows, uint8_t *__restrict__ planes,
                                                                  uint32_t ntiles, uint32_t kpad) {
     __shared__ uint32_t tws[LAB_TWS_ROWS][32];
     __shared__ uint32_t hoist[GP_WARPS][16];

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <vector>
 #include "lab_kernels.cuh"
+#include "lab_umma.cuh"
 
 using namespace lab;
 
@@ -213,6 +214,24 @@ int main(int argc, char **argv) {
         bench_expand<0x22222222u>(tm, seed, out, n, start, ref, n_small);
         bench_expand<0x88888888u>(tm, seed, out, n, start, ref, n_small);
         cudaFree(out);
+    }
+    {   // generation into limb planes: occupancy variants
+        const uint32_t N = 4096;
+        const uint64_t rows = 148 * 32;
+        const uint32_t kpad = 2 * N, nt = (uint32_t)(rows / 64);
+        uint8_t *planes;
+        CK(cudaMalloc(&planes, (size_t)nt * 64 * 32 * 2 * kpad));
+        auto report = [&](const char *name, float ms) {
+            printf("{\"kernel\": \"k_gen_planes\", \"variant\": \"%s\", \"rows\": %llu, \"N\": %u, \"ms\": %.4f, \"blocks_per_s\": %.4e}\n", name, (unsigned long long)rows, N, ms,
+                   (double)rows * N * 64 / (ms * 1e-3));
+            fflush(stdout);
+        };
+        report("minblocks 2 (16 warps/SM)", tm.run([&] { k_gen_planes<2><<<148 * 2, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); }, 2));
+        report("minblocks 3 (24 warps/SM)", tm.run([&] { k_gen_planes<3><<<148 * 3, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); }, 2));
+        report("minblocks 4 (32 warps/SM)", tm.run([&] { k_gen_planes<4><<<148 * 4, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); }, 2));
+        report("minblocks 5 (40 warps/SM)", tm.run([&] { k_gen_planes<5><<<148 * 5, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); }, 2));
+        CK(cudaGetLastError());
+        cudaFree(planes);
     }
     {   // inner commitment
         const uint32_t N = argc > 1 ? atoi(argv[1]) : 1024, R = 64;
