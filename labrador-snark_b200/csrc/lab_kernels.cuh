@@ -7,10 +7,14 @@
 //
 // Kernels (roofline that bounds each is named; see DESIGN.md for the byte/op counts)
 //   k_ntt_fwd_regs / k_ntt_inv_regs / k_polymul_regs   lane-per-poly, swizzled smem staging   HBM
-//   k_crs_expand                                       thread per coefficient                  INT32 ALU
-//   k_commit_inner                                     CRS gen + warp NTT + reuse over R       INT32 ALU
-//   k_crs_matvec + k_finish_rows                       CRS gen + warp NTT + mat-vec            INT32 ALU
+//   k_crs_expand                                       thread per 2 coefficients (trimmed ChaCha20) INT32 ALU
+//   k_commit_inner (K_A)                               warp-specialised: ChaCha20 + warp NTT producers,
+//                                                      TMA-fed IMAD consumers; shapes < 2^22 polynomials  INT32 ALU
+//   k_crs_matvec<FILL_CACHE> + k_finish_rows (K_MV)    CRS gen + warp NTT + mat-vec (optionally write-through) INT32 ALU
+//   k_cached_matvec                                    the same mat-vec from the CRS cache     HBM
 //   k_fwd_hat / k_inv_hat / k_decomp_fwd / k_ip_hat / k_pointwise / k_jl / k_piT_omega / ...   HBM / L2
+// lab_umma.cuh: k_gen_planes (ChaCha20 -> int8 limb planes, INT32 ALU) + k_umma_commit (tcgen05 contraction, HBM) --
+// the large-shape inner commitment; lab_gen.cuh: device-side challenge / witness / statement generation.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -413,10 +417,12 @@ __global__ void __launch_bounds__(256) k_digit_norm_sq(const uint32_t *__restric
 // ------------------------------------------------------------------------------------------------
 // CRS expansion (structs.rs:35-45,147-171): thread per coefficient, coalesced stores.  INT32-ALU bound.
 // ------------------------------------------------------------------------------------------------
-// FMA-pipe rotation masks (lab_chacha.cuh), one per kernel: chosen on a B200 so that the ALU and FMA pipes carry the
-// same load next to whatever else the kernel issues (tools/kbench.cu sweeps them; profiles/ holds the results)
+// FMA-pipe rotation masks (lab_chacha.cuh), one per kernel.  Measured on a B200 (tools/kbench.cu,
+// profiles/kbench_r1_rotation_masks.jsonl): IMAD.HI is half rate, so a rotation on the FMA pipe costs three issue slots'
+// worth of pipe time -- it gains 3 % in k_crs_expand with two of the 32 rotations of a double round moved and loses
+// everywhere else, hence 0 for the kernels that also multiply.
 #ifndef LAB_RM_EXPAND
-#define LAB_RM_EXPAND 0x00000000u
+#define LAB_RM_EXPAND 0x00010001u
 #endif
 #ifndef LAB_RM_COMMIT
 #define LAB_RM_COMMIT 0x00000000u
