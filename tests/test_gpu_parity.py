@@ -508,3 +508,16 @@ def test_commit_inner_generate_then_contract(ctx, orc, N, R, row0, nrows, monkey
     assert np.array_equal(got, ref)
     monkeypatch.setenv("LAB_GEN_CONTRACT_MIN_POLYS", "0")          # 0 = never: the warp-specialised K_A path
     assert np.array_equal(ctx.commit_inner(c, SEED32, S, row0=row0, nrows=nrows), ref)
+
+
+@pytest.mark.parametrize("low", [(5 << 32) + (1 << 32) - 64 * 5 - 20, (1 << 64) - 64 * 3 - 10])
+def test_generate_then_contract_counter_boundaries(ctx, orc, low, monkeypatch):
+    """k_gen_planes at the 2^32 boundary of seed + counter (hoisted ChaCha20 state changes inside polynomial 5) and at the
+    2^64 carry into the upper seed limbs (inside polynomial 3): same seeds as the K_A boundary tests."""
+    monkeypatch.setenv("LAB_GEN_CONTRACT_MIN_POLYS", "1")
+    N, R = 4, 2
+    seed = bytes(range(7, 31)) + low.to_bytes(8, "big")
+    c = lb.RuntimeConstants.new(N, R)
+    co, _ = orc.constants(N, R)
+    S = synth.uniform_witness(N, R, seed=9)
+    assert np.array_equal(ctx.commit_inner(c, seed, S, 0, 8), orc.commit_inner_rows(co, seed, S, 0, 8))
