@@ -43,6 +43,10 @@ struct lab_ctx {
     uint32_t *What = nullptr;          // owned, [N][R][32]
     size_t What_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // second stream of lab_prove: the outer commitment u_1 (all of a small proof's ChaCha20) runs beside the chain of
+    // small dependent kernels of stages S5-S9, which do not need it
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // K_MV work-item lists depend only on the shape: kept on the device so that a proof needs no mid-stream H2D copy
     // (an H2D copy from pageable memory first synchronises the stream and would stall the enqueueing thread)
     struct MvPlan { std::vector<unsigned char> host; void *dev; };
@@ -205,6 +209,7 @@ extern "C" void lab_ctx_destroy(lab_ctx *ctx) {
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->What) cudaFree(ctx->What);
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
+    if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); }
     for (auto &p : ctx->mv_plans) cudaFree(p.dev);
     for (auto &e : ctx->crs_cache) cudaFree(e.dev);
     if (ctx->gc_chunk) cudaFree(ctx->gc_chunk);
@@ -1108,11 +1113,31 @@ static int prove_one(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_by
     // S3: u_1 (proofgen.rs:101-153)
     uint32_t *du1;
     TRY(arena_alloc(ctx, K1 * 64, &du1));
+    bool u1_forked = false;
     {
         uint64_t x0, nx;
         const bool sharded = shard_rows(ctx, K1, &x0, &nx);
+        // Nothing before the final downloads reads u_1: without a communicator (NCCL wants one stream per communicator) it is
+        // enqueued on the second stream, behind an event that marks T and g, and joined before the downloads.
+        struct StreamSwap {
+            lab_ctx *c; cudaStream_t saved; bool on;
+            ~StreamSwap() { if (on) c->stream = saved; }
+        } swap{ctx, ctx->stream, false};
+        if (!ctx->comm && !std::getenv("LAB_NO_FORK")) {
+            if (!ctx->stream2) {
+                CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+                CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+            }
+            CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+            ctx->stream = ctx->stream2;
+            swap.on = true;
+            u1_forked = true;
+        }
         TRY(d_outer_u1(ctx, c, seed, dT, dG, du1, x0, nx));
         if (sharded) TRY(allgather_rows(ctx, du1, 1, 0, K1, 64));
+        if (u1_forked) CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
     }
     TRACE("u1 enqueued");
     // S9: z (proofgen.rs:380-399) -- independent of the JL outcome, enqueued first
@@ -1178,6 +1203,7 @@ static int prove_one(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_by
         LAUNCH(k_digit_norm_sq, grid_for(R * R * 64, 2048, ctx->sms * 8), 256, dG, (size_t)(R * R * 64), (uint32_t)c->B_2, (int)T2, dnorm);
         LAUNCH(k_digit_norm_sq, grid_for(R * R * 64, 2048, ctx->sms * 8), 256, dH, (size_t)(R * R * 64), (uint32_t)c->B_1, (int)T1, dnorm);
         if (out->phi_final) TRY(d_inv_hat(ctx, PFhat, pf_tmp, R * N));
+        if (u1_forked) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));     // join the u_1 stream
         TRACE("all kernels enqueued");
         // ---- downloads ----
         TRY(download(ctx, out->u_1, du1, K1 * 64));
