@@ -213,7 +213,7 @@ int lab_verify(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], con
  * next proof -- with a tcgen05 int8 contraction that streams A once from HBM (cfg 3: 34 ms instead of 3 s).  Results are
  * bit-identical.  Off by default (max_bytes = 0): a single proof then regenerates its CRS exactly like the reference.
  * Entries that do not fit stay uncached.
- * Any call also releases the up to 64 GB of transient limb planes the cold large-shape commitment keeps in the ctx
+ * Any call also releases the few GB of transient limb planes the cold large-shape commitment keeps in the ctx
  * between calls (lab_crs_cache_configure(ctx, 0) is the "give the memory back" call). */
 int lab_crs_cache_configure(lab_ctx *ctx, size_t max_bytes);
 int lab_crs_cache_stats(const lab_ctx *ctx, size_t *bytes_used, uint64_t *hits, uint64_t *misses);

@@ -58,8 +58,8 @@ struct lab_ctx {
     std::vector<CrsEntry> crs_cache;
     size_t crs_cache_max = 0, crs_cache_used = 0;
     uint64_t crs_cache_hits = 0, crs_cache_misses = 0;
-    // transient limb planes of the generate-then-contract path: kept between calls (a 64 GB cudaMalloc/cudaFree pair costs
-    // hundreds of milliseconds), released by lab_crs_cache_configure and lab_ctx_destroy
+    // transient limb planes of the generate-then-contract path (a few GB): kept between calls, released by
+    // lab_crs_cache_configure and lab_ctx_destroy
     void *gc_chunk = nullptr;
     size_t gc_chunk_bytes = 0;
     // worker contexts (own stream + arena each) for lab_prove_batch: independent statements overlap host-side
@@ -455,7 +455,9 @@ static int make_map(lab_ctx *ctx, CUtensorMap *map, void *base, uint64_t rows, u
     return LAB_OK;
 }
 // T[i][t_row_off + row] for vectors i in [ib, ib + ni) and all cached rows, from the int8 limb planes of A
-struct UmmaScratch { int8_t *Bp = nullptr; uint32_t *Th = nullptr; };      // B planes and slot planes, reused by the passes of one call
+// scratch of one commitment call: the witness-side B planes of every pass of 64 vectors (built once, reused by all row
+// chunks) and the slot planes of one pass
+struct UmmaScratch { std::vector<int8_t *> Bp; uint32_t *Th = nullptr; };
 static int d_commit_umma(lab_ctx *ctx, uint8_t *acache, uint32_t ntiles, uint32_t kpad, const uint32_t *What, uint64_t N, uint64_t R, uint64_t ib, uint64_t ni,
                          uint64_t nrows, uint32_t *T, uint64_t t_stride, uint64_t t_row_off, UmmaScratch &sc) {
     const uint32_t ncols = (uint32_t)((4 * ni + 15) / 16 * 16), rows_pad = ntiles * 64;
@@ -463,14 +465,16 @@ static int d_commit_umma(lab_ctx *ctx, uint8_t *acache, uint32_t ntiles, uint32_
     // whose results k_umma_finish adds mod q
     const uint32_t total_chunks = kpad / 128, seg_chunks = 256, nseg = (total_chunks + seg_chunks - 1) / seg_chunks;
     const size_t seg_stride = (size_t)32 * ni * rows_pad;
-    if (!sc.Bp) {        // sized for a full pass of 64 vectors over this many rows; later passes and row chunks are never larger
-        TRY(arena_alloc(ctx, (size_t)32 * 256 * kpad, &sc.Bp));
-        TRY(arena_alloc(ctx, (size_t)32 * 64 * rows_pad * nseg, &sc.Th));
+    if (!sc.Th) TRY(arena_alloc(ctx, (size_t)32 * 64 * rows_pad * nseg, &sc.Th));   // the first row chunk of a call is the largest
+    const size_t pass = (size_t)(ib / 64);
+    if (sc.Bp.size() <= pass) sc.Bp.resize(pass + 1, nullptr);
+    if (!sc.Bp[pass]) {
+        TRY(arena_alloc(ctx, (size_t)32 * ncols * kpad, &sc.Bp[pass]));
+        CK(cudaMemsetAsync(sc.Bp[pass], 0, (size_t)32 * ncols * kpad, ctx->stream));
+        LAUNCH(k_umma_build_b, grid_for(N * ni * 32, 256, ctx->sms * 16), 256, What, (uint32_t)N, (uint32_t)R, (uint32_t)ib, (uint32_t)ni, ncols, kpad, sc.Bp[pass]);
     }
-    int8_t *Bp = sc.Bp;
+    int8_t *Bp = sc.Bp[pass];
     uint32_t *Th = sc.Th;
-    CK(cudaMemsetAsync(Bp, 0, (size_t)32 * ncols * kpad, ctx->stream));
-    LAUNCH(k_umma_build_b, grid_for(N * ni * 32, 256, ctx->sms * 16), 256, What, (uint32_t)N, (uint32_t)R, (uint32_t)ib, (uint32_t)ni, ncols, kpad, Bp);
     CUtensorMap mapA, mapB;
     TRY(make_map(ctx, &mapA, acache, (uint64_t)32 * ntiles * 128, kpad, 128));
     TRY(make_map(ctx, &mapB, Bp, (uint64_t)32 * ncols, kpad, ncols));
@@ -561,11 +565,11 @@ static int d_commit_inner(lab_ctx *ctx, const LabSeed &seed, const uint32_t *Wha
         free_b += ctx->gc_chunk_bytes;                      // the chunk of an earlier call is reused or replaced
         const size_t reserve = (size_t)32 * 256 * kpad + ((size_t)8 << 30);       // B planes, slot planes, other scratch
         size_t budget = free_b > reserve ? (free_b - reserve) / 2 : 0;
-        budget = std::min<size_t>(budget, (size_t)64 << 30);
+        size_t chunk_cap = (size_t)4 << 30;              // enough rows per chunk to keep launch tails below 1 %; LAB_GC_CHUNK_MB overrides
+        if (const char *e = std::getenv("LAB_GC_CHUNK_MB")) chunk_cap = (size_t)std::strtoull(e, nullptr, 10) << 20;
+        budget = std::min<size_t>(budget, chunk_cap);
         uint64_t rows_c = budget / per_row / 64 * 64;
         if (rows_c > nrows) rows_c = (nrows + 63) / 64 * 64;
-        const uint64_t have = ctx->gc_chunk_bytes / per_row / 64 * 64;
-        if (have >= std::min<uint64_t>(rows_c, 4096)) rows_c = std::min<uint64_t>(rows_c, have);   // keep a chunk of useful size rather than reallocating
         if (rows_c >= 64) {
             uint8_t *chunk = (uint8_t *)gc_chunk_get(ctx, rows_c * per_row);
             if (chunk) {
