@@ -43,6 +43,19 @@ def main():
                                   "digest": {k: digest(tr[k]) for k in ("t", "g", "u_1", "projection_int", "b_prime_prime", "phi_final", "h", "u_2", "z")},
                                   "witness": digest(S), "z0": tr["z"][0, :8].tolist(), "u1_0": tr["u_1"][0, :8].tolist()}
     out["proofs"] = proofs
+    # wire format: sha256 and length of bincode::serialize(&Transcript) (structs.rs:192-221) for the (1,2) proof above, produced by
+    # the independent struct.pack restatement in tests/test_host.py (the product's lab_transcript_bincode must reproduce it)
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    sys.path.insert(0, os.path.join(HERE, "..", "..", "labrador-snark_b200"))
+    from test_host import _bincode_reference
+    import labrador_b200 as lb
+    c, _ = oracle.constants(1, 2)
+    S = oracle.generate_witness(c, 12)
+    phi, a, b = oracle.generate_state(c, S, 12)
+    ch = oracle.sample_challenges(c, 12, 2)
+    rc, tr = oracle.prove(c, seed, S, phi, a, b, ch, ntt=False, nthreads=8)
+    blob = _bincode_reference(lb.RuntimeConstants.new(1, 2), tr, ch, int(tr["jl_attempt"]))
+    out["bincode_1,2,12"] = {"len": len(blob), "sha256": hashlib.sha256(blob).hexdigest()}
     json.dump(out, open(os.path.join(HERE, "golden.json"), "w"), indent=1)
     print("wrote golden.json")
 

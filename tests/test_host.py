@@ -256,3 +256,21 @@ def test_in_library_row_sharding_rule():
     # kappa = N * 64 is divisible by 2, 4, 8 for every N, so T, u_1, u_2 always shard on one 8-GPU box
     for N in (1, 2, 3, 5, 4096):
         assert all(shard.rows_of(N * 64, w, 0)[2] for w in (2, 4, 8))
+
+
+def test_transcript_bincode_golden(orc):
+    """The committed digest of the (1,2) proof's wire bytes (tests/golden/golden.json, made by the struct.pack restatement)."""
+    import hashlib
+    import json
+    from labrador_b200.api import transcript_bincode
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))["bincode_1,2,12"]
+    c = lb.RuntimeConstants.new(1, 2)
+    co, _ = orc.constants(1, 2)
+    S = orc.generate_witness(co, 12)
+    phi, a, b = orc.generate_state(co, S, 12)
+    ch = orc.sample_challenges(co, 12, 2)
+    rc, tr = orc.prove(co, bytes(range(32)), S, phi, a, b, ch, ntt=True, nthreads=4)
+    assert rc == 0
+    blob = transcript_bincode(c, tr, ch)
+    assert len(blob) == gold["len"]
+    assert hashlib.sha256(blob).hexdigest() == gold["sha256"]
