@@ -1442,7 +1442,9 @@ extern "C" int lab_prove_batch(lab_ctx *ctx, const lab_constants *c, size_t n_st
     TRY(check_consts(ctx, c, true));
     if (!n_statements) return LAB_OK;
     const size_t wsz = c->R * c->N * 64;
-    const size_t nw = std::min<size_t>(n_statements, 4);
+    size_t max_workers = 8;                          // worker contexts (stream + arena each); LAB_BATCH_WORKERS overrides
+    if (const char *e = std::getenv("LAB_BATCH_WORKERS")) max_workers = std::max<size_t>(1, std::strtoull(e, nullptr, 10));
+    const size_t nw = std::min<size_t>(n_statements, max_workers);
     while (ctx->workers.size() < nw) {
         lab_ctx *w = nullptr;
         if (lab_ctx_create(ctx->device, &w) != LAB_OK) FAIL(LAB_ERR_CUDA, "cannot create batch worker context");
@@ -1583,6 +1585,7 @@ extern "C" int lab_witness_load_dev(lab_ctx *ctx, const lab_constants *c, const 
 extern "C" int lab_commit_inner_dev(lab_ctx *ctx, const uint8_t seed[32], uint64_t row0, uint64_t nrows, uint32_t *T_dev) {
     NEED_WITNESS();
     if (row0 + nrows > ctx->wc.KAPPA) FAIL(LAB_ERR_SHAPE, "row range exceeds KAPPA");
+    arena_reset(ctx);       // the contraction's scratch (B planes, slot planes) is per call: a loop over row shards must not accumulate it
     return d_commit_inner(ctx, make_seed(seed), ctx->What, ctx->wc.N, ctx->wc.R, row0, nrows, T_dev);
 }
 extern "C" int lab_gram_dev(lab_ctx *ctx, uint64_t i0, uint64_t ni, uint32_t *G_dev) {
