@@ -46,7 +46,7 @@ struct lab_ctx {
     // second stream of lab_prove: the outer commitment u_1 (all of a small proof's ChaCha20) runs beside the chain of
     // small dependent kernels of stages S5-S9, which do not need it
     cudaStream_t stream2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_tg = nullptr;
     // K_MV work-item lists depend only on the shape: kept on the device so that a proof needs no mid-stream H2D copy
     // (an H2D copy from pageable memory first synchronises the stream and would stall the enqueueing thread)
     struct MvPlan { std::vector<unsigned char> host; void *dev; };
@@ -209,7 +209,7 @@ extern "C" void lab_ctx_destroy(lab_ctx *ctx) {
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->What) cudaFree(ctx->What);
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
-    if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); }
+    if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->ev_tg); }
     for (auto &p : ctx->mv_plans) cudaFree(p.dev);
     for (auto &e : ctx->crs_cache) cudaFree(e.dev);
     if (ctx->gc_chunk) cudaFree(ctx->gc_chunk);
@@ -1069,7 +1069,7 @@ static int prove_one(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_by
 
     // All host->device copies come first: a copy from pageable host memory synchronises the stream, so none may follow
     // the long kernels.  (The K_MV item lists are cached on the device per shape for the same reason.)
-    uint32_t *dS, *What, *dT;
+    uint32_t *dS, *What;
     TRY(load_witness(ctx, c, S, &dS, &What));
     uint32_t *dc, *dphi, *dom, *da, *dab;
     TRY(upload(ctx, ch->c, R * 64, &dc));
@@ -1081,9 +1081,52 @@ static int prove_one(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_by
     std::memcpy(ab + 64, ch->beta, 64 * sizeof(uint32_t));
     TRY(upload(ctx, ab, (size_t)128, &dab));
     TRACE("uploads done");
-    // S4: JL with retries (proofgen.rs:161-186: initial attempt + at most 5 retries).  It depends on the witness only, so it
-    // is enqueued FIRST: the host sync that the accept/reject decision needs then waits for a few microseconds of GPU work
-    // instead of for the outer commitment, and everything after it runs without another sync until the end.
+    // Two independent strands start here.  (a) S1-S3: inner commitments, g and the outer commitment u_1 -- all of a small
+    // proof's ChaCha20 -- which nothing but the final downloads (u_1) and the S5-S8 chain (T, g) reads; (b) S4: the JL
+    // projection, whose accept/reject decision needs a host sync.  Without a communicator (NCCL wants one stream per
+    // communicator) strand (a) goes to the second stream, so the JL sync and the chain of small dependent kernels of S5-S9
+    // run beside u_1 instead of before / after it.
+    uint32_t *dT, *Ghat, *dG, *du1;
+    TRY(arena_alloc(ctx, R * K * 64, &dT));
+    TRY(arena_alloc(ctx, R * R * 32, &Ghat));
+    TRY(arena_alloc(ctx, R * R * 64, &dG));
+    TRY(arena_alloc(ctx, K1 * 64, &du1));
+    const bool forked = !ctx->comm && !std::getenv("LAB_NO_FORK");
+    auto strand_a = [&]() -> int {
+        {   // S1 (proofgen.rs:35-49); with a communicator this rank regenerates only its rows of A, T is completed in place by R grouped all-gathers
+            uint64_t x0, nx;
+            const bool sharded = shard_rows(ctx, K, &x0, &nx);
+            TRY(d_commit_inner(ctx, seed, What, N, R, x0, nx, dT, K, x0));
+            if (sharded) TRY(allgather_rows(ctx, dT, R, K * 64, K, 64));
+        }
+        TRY(d_gram(ctx, What, N, R, 0, R, Ghat, dG));                        // S2 (proofgen.rs:59-70)
+        if (forked) CK(cudaEventRecord(ctx->ev_tg, ctx->stream));            // T and g are complete
+        {   // S3 (proofgen.rs:101-153)
+            uint64_t x0, nx;
+            const bool sharded = shard_rows(ctx, K1, &x0, &nx);
+            TRY(d_outer_u1(ctx, c, seed, dT, dG, du1, x0, nx));
+            if (sharded) TRY(allgather_rows(ctx, du1, 1, 0, K1, 64));
+        }
+        if (forked) CK(cudaEventRecord(ctx->ev_join, ctx->stream));
+        return LAB_OK;
+    };
+    if (forked) {
+        if (!ctx->stream2) {
+            CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_tg, cudaEventDisableTiming));
+        }
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));                      // uploads and the transformed witness are enqueued
+        CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+        struct StreamSwap {
+            lab_ctx *c; cudaStream_t saved;
+            ~StreamSwap() { c->stream = saved; }
+        } swap{ctx, ctx->stream};
+        ctx->stream = ctx->stream2;
+        TRY(strand_a());
+    }
+    // S4: JL with retries (proofgen.rs:161-186: initial attempt + at most 5 retries)
     int8_t *dPi;
     unsigned long long *dp;
     TRY(arena_alloc(ctx, R * LAB_JL_ROWS * ND, &dPi));
@@ -1101,48 +1144,9 @@ static int prove_one(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_by
     }
     out->jl_attempt = att;
     TRACE("jl accepted");
-    // S1: inner commitments (proofgen.rs:35-49)
-    TRY(arena_alloc(ctx, R * K * 64, &dT));
-    {   // with a communicator: this rank regenerates only its rows of A; T is completed in place by R grouped all-gathers
-        uint64_t x0, nx;
-        const bool sharded = shard_rows(ctx, K, &x0, &nx);
-        TRY(d_commit_inner(ctx, seed, What, N, R, x0, nx, dT, K, x0));
-        if (sharded) TRY(allgather_rows(ctx, dT, R, K * 64, K, 64));
-    }
-    // S2: g (proofgen.rs:59-70)
-    uint32_t *Ghat, *dG;
-    TRY(arena_alloc(ctx, R * R * 32, &Ghat));
-    TRY(arena_alloc(ctx, R * R * 64, &dG));
-    TRY(d_gram(ctx, What, N, R, 0, R, Ghat, dG));
-    // S3: u_1 (proofgen.rs:101-153)
-    uint32_t *du1;
-    TRY(arena_alloc(ctx, K1 * 64, &du1));
-    bool u1_forked = false;
-    {
-        uint64_t x0, nx;
-        const bool sharded = shard_rows(ctx, K1, &x0, &nx);
-        // Nothing before the final downloads reads u_1: without a communicator (NCCL wants one stream per communicator) it is
-        // enqueued on the second stream, behind an event that marks T and g, and joined before the downloads.
-        struct StreamSwap {
-            lab_ctx *c; cudaStream_t saved; bool on;
-            ~StreamSwap() { if (on) c->stream = saved; }
-        } swap{ctx, ctx->stream, false};
-        if (!ctx->comm && !std::getenv("LAB_NO_FORK")) {
-            if (!ctx->stream2) {
-                CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
-                CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-                CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-            }
-            CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
-            CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-            ctx->stream = ctx->stream2;
-            swap.on = true;
-            u1_forked = true;
-        }
-        TRY(d_outer_u1(ctx, c, seed, dT, dG, du1, x0, nx));
-        if (sharded) TRY(allgather_rows(ctx, du1, 1, 0, K1, 64));
-        if (u1_forked) CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
-    }
+    if (forked) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_tg, 0));         // the rest of the main strand reads T and g
+    else TRY(strand_a());
+    const bool u1_forked = forked;
     TRACE("u1 enqueued");
     // S9: z (proofgen.rs:380-399) -- independent of the JL outcome, enqueued first
     uint32_t *Chat, *zhat, *dz;
