@@ -68,6 +68,17 @@ def main():
         print(json.dumps({"kernel": "commit_inner", "N": N, "R": R, "rows": rows, "ms_median": med,
                           "chacha_blocks_per_s": rows * N * 64 / (med * 1e-3)}), flush=True)
         ctx.free(dS); ctx.free(dT)
+    if "gen" in which:          # cold large-shape commitment (generate-then-contract) on a slice of cfg 3, for ncu captures of k_gen_planes
+        N, R, rows = 4096, 64, 148 * 32
+        c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
+        dS = ctx.malloc(R * N * 256)
+        ctx.synth_zq_dev(synth.SEED, 1, 0, R * N * 64, dS)
+        ctx.witness_load_dev(c, dS)
+        dT = ctx.malloc(R * rows * 256)
+        best, med = timeit(ctx, lambda: ctx.commit_inner_dev(SEED32, 0, rows, dT), reps=3, warm=1)
+        print(json.dumps({"kernel": "commit_inner cold (k_gen_planes + k_umma_commit)", "N": N, "R": R, "rows": rows, "ms_median": med,
+                          "chacha_blocks_per_s": rows * N * 64 / (med * 1e-3)}), flush=True)
+        ctx.free(dS); ctx.free(dT)
     if "umma" in which:         # CRS-resident inner commitment on the tensor cores (lab_umma.cuh), cfg-3 shape on fewer rows
         N, R, rows = 4096, 64, 64 * 148 * 2
         c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
