@@ -226,6 +226,15 @@ int main(int argc, char **argv) {
                    (double)rows * N * 64 / (ms * 1e-3));
             fflush(stdout);
         };
+        {
+            int nb2 = 0, nb3 = 0, nb4 = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, k_gen_planes<2>, 32 * GP_WARPS, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb3, k_gen_planes<3>, 32 * GP_WARPS, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb4, k_gen_planes<4>, 32 * GP_WARPS, 0);
+            printf("{\"kernel\": \"k_gen_planes\", \"resident_ctas_per_sm\": {\"minblocks2\": %d, \"minblocks3\": %d, \"minblocks4\": %d}}\n", nb2, nb3, nb4);
+        }
+        report("minblocks 3, grid 148 x 6", tm.run([&] { k_gen_planes<3><<<148 * 6, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); }, 2));
+        report("minblocks 3, grid 148 x 12", tm.run([&] { k_gen_planes<3><<<148 * 12, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); }, 2));
         report("minblocks 2 (16 warps/SM)", tm.run([&] { k_gen_planes<2><<<148 * 2, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); }, 2));
         report("minblocks 3 (24 warps/SM)", tm.run([&] { k_gen_planes<3><<<148 * 3, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); }, 2));
         report("minblocks 4 (32 warps/SM)", tm.run([&] { k_gen_planes<4><<<148 * 4, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); }, 2));
