@@ -486,6 +486,14 @@ static int d_commit_umma(lab_ctx *ctx, uint8_t *acache, uint32_t ntiles, uint32_
     return LAB_OK;
 }
 
+static int ensure_stream2(lab_ctx *ctx) {
+    if (ctx->stream2) return LAB_OK;
+    CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_tg, cudaEventDisableTiming));
+    return LAB_OK;
+}
 // transient limb planes for `rows_c` rows of `per_row` bytes (kept in the ctx between calls); nullptr when there is no room
 static void *gc_chunk_get(lab_ctx *ctx, size_t bytes) {
     if (ctx->gc_chunk && ctx->gc_chunk_bytes >= bytes) return ctx->gc_chunk;
@@ -504,9 +512,13 @@ static void gc_chunk_release(lab_ctx *ctx) {
     ctx->gc_chunk_bytes = 0;
 }
 
+// T_host (optional, host layout [R][nrows][64], only with the default device layout): the rows of every finished chunk of the
+// generate-then-contract path are copied out on the second stream while the next chunk is generated; *host_done tells the
+// caller that nothing is left to download
 static int d_commit_inner(lab_ctx *ctx, const LabSeed &seed, const uint32_t *What, uint64_t N, uint64_t R, uint64_t row0, uint64_t nrows, uint32_t *T,
-                          uint64_t t_stride = 0, uint64_t t_row_off = 0) {
+                          uint64_t t_stride = 0, uint64_t t_row_off = 0, uint32_t *T_host = nullptr, bool *host_done = nullptr) {
     if (!t_stride) t_stride = nrows;            // default: T is exactly [R][nrows][64]
+    if (host_done) *host_done = false;
     if (!nrows) return LAB_OK;
     if (N >= (1ull << 32) || R >= (1ull << 32)) FAIL(LAB_ERR_PARAMS, "N, R must be < 2^32");
     {   // counters of A stay below 2^64 (structs.rs:62): (row * N + n) * 64
@@ -575,11 +587,24 @@ static int d_commit_inner(lab_ctx *ctx, const LabSeed &seed, const uint32_t *Wha
             uint8_t *chunk = (uint8_t *)gc_chunk_get(ctx, rows_c * per_row);
             if (chunk) {
                 UmmaScratch sc;              // first use is the largest (rows_c rows): the arena allocation fits every chunk
+                const bool stream_out = T_host && host_done && t_stride == nrows && t_row_off == 0;
+                if (stream_out) TRY(ensure_stream2(ctx));
                 for (uint64_t r0 = 0; r0 < nrows; r0 += rows_c) {
                     const uint64_t nr = std::min<uint64_t>(rows_c, nrows - r0);
                     const uint32_t nt = (uint32_t)((nr + 63) / 64);
                     TRY(gen_planes(chunk, r0, nr, nt));
                     TRY(contract(chunk, r0, nr, nt, sc));
+                    if (stream_out) {            // rows [r0, r0 + nr) of every t_i: R strips of nr * 256 bytes
+                        CK(cudaEventRecord(ctx->ev_tg, ctx->stream));
+                        CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_tg, 0));
+                        CK(cudaMemcpy2DAsync(T_host + r0 * 64, nrows * 64 * sizeof(uint32_t), T + r0 * 64, nrows * 64 * sizeof(uint32_t), nr * 64 * sizeof(uint32_t), R,
+                                             cudaMemcpyDeviceToHost, ctx->stream2));
+                    }
+                }
+                if (stream_out) {
+                    CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
+                    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+                    *host_done = true;
                 }
                 return LAB_OK;
             }
@@ -924,8 +949,9 @@ extern "C" int lab_commit_inner(lab_ctx *ctx, const lab_constants *c, const uint
     uint32_t *dS, *What, *dT;
     TRY(load_witness(ctx, c, S, &dS, &What));
     TRY(arena_alloc(ctx, c->R * nrows * 64, &dT));
-    TRY(d_commit_inner(ctx, make_seed(seed), What, c->N, c->R, row0, nrows, dT));
-    TRY(download(ctx, T, dT, c->R * nrows * 64));
+    bool host_done = false;
+    TRY(d_commit_inner(ctx, make_seed(seed), What, c->N, c->R, row0, nrows, dT, 0, 0, T, &host_done));
+    if (!host_done) TRY(download(ctx, T, dT, c->R * nrows * 64));
     return lab_sync(ctx);
 }
 extern "C" int lab_gram(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, uint32_t *G) {
@@ -1112,12 +1138,7 @@ static int prove_one(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_by
         return LAB_OK;
     };
     if (forked) {
-        if (!ctx->stream2) {
-            CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
-            CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&ctx->ev_tg, cudaEventDisableTiming));
-        }
+        TRY(ensure_stream2(ctx));
         CK(cudaEventRecord(ctx->ev_fork, ctx->stream));                      // uploads and the transformed witness are enqueued
         CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
         struct StreamSwap {

@@ -500,6 +500,7 @@ def test_commit_inner_generate_then_contract(ctx, orc, N, R, row0, nrows, monkey
     contraction with all witness vectors), forced on small shapes the oracle can check: ragged rows and columns (zero
     padding of planes), R = 1 (N' = 16), several passes of 64 vectors, two K-segments."""
     monkeypatch.setenv("LAB_GEN_CONTRACT_MIN_POLYS", "1")
+    monkeypatch.setenv("LAB_GC_CHUNK_MB", "1")          # 1 MB of limb planes per chunk: several row chunks, T streamed out per chunk
     c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
     co, _ = orc.constants(N, R)
     S = synth.uniform_witness(N, R, seed=3 * N + R)
