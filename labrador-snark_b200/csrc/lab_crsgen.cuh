@@ -1,0 +1,61 @@
+// One CRS polynomial per warp, straight into the transform domain -- the producer step shared by the CRS-regenerating
+// kernels (k_gen_planes, k_crs_matvec): trimmed ChaCha20 for coefficients lane and lane + 32 (lab_chacha.cuh), rand-0.8.5
+// sampling, generic path for rejected draws and for polynomials that straddle a 2^32 boundary of seed + counter, warp
+// transform with the constants in shared memory.  The hoisted part of the first double round lives in a per-warp shared-
+// memory slot (15 words) and is recomputed when the high part of seed + counter changes, so a producer thread carries
+// two ChaCha20 states and little else (72 registers, three CTAs of 256 threads per SM).
+#pragma once
+#include "lab_chacha.cuh"
+#include "lab_ntt.cuh"
+
+struct LabWarpGen {
+    uint64_t tag_lo = ~0ull, tag_hi = ~0ull;      // which counter range the warp's hoist slot is valid for
+};
+
+__device__ __forceinline__ void lab_hoist_store(uint32_t *q, const LabHoist &hh) {
+    q[0] = hh.k3; q[1] = hh.P0; q[2] = hh.P1; q[3] = hh.Q0; q[4] = hh.A5; q[5] = hh.A10; q[6] = hh.Q1; q[7] = hh.Q2;
+    q[8] = hh.A6; q[9] = hh.A2; q[10] = hh.A8; q[11] = hh.A13; q[12] = hh.A4; q[13] = hh.A9; q[14] = hh.A14;
+}
+__device__ __forceinline__ void lab_hoist_load(const uint32_t *q, LabHoist &h) {
+    h.k3 = q[0]; h.P0 = q[1]; h.P1 = q[2]; h.Q0 = q[3]; h.A5 = q[4]; h.A10 = q[5]; h.Q1 = q[6]; h.Q2 = q[7];
+    h.A6 = q[8]; h.A2 = q[9]; h.A8 = q[10]; h.A13 = q[11]; h.A4 = q[12]; h.A9 = q[13]; h.A14 = q[14];
+}
+
+// polynomial whose coefficient 0 sits at counter (chi:clo); all lanes of the warp call with the same arguments.
+// hoist_slot: 16 words of shared memory owned by this warp; tws: lab_warp_tw_to_smem table.  Returns the packed slots.
+__device__ __forceinline__ void lab_crs_poly_hat_warp(const LabSeed &seed, LabWarpGen &g, uint32_t *hoist_slot, const uint32_t (*tws)[32], uint64_t clo,
+                                                      uint64_t chi, int lane, uint32_t &re, uint32_t &im) {
+    const uint64_t s0 = seed.limb[0] + clo;
+    const uint64_t ntag = ((uint64_t)(s0 < clo) << 32) | (s0 >> 32);
+    if (ntag != g.tag_lo || chi != g.tag_hi) {                   // warp-uniform, once per 2^32 counters
+        LabHoist hh;
+        lab_hoist_compute(seed, clo, chi, hh);
+        __syncwarp();
+        if (lane == 0) lab_hoist_store(hoist_slot, hh);
+        __syncwarp();
+        g.tag_lo = ntag;
+        g.tag_hi = chi;
+    }
+    const uint32_t lo32 = (uint32_t)s0;
+    const bool straddle = lo32 > 0xFFFFFFFFu - 63u;
+    LabHoist h;
+    lab_hoist_load(hoist_slot, h);
+    const uint32_t k7[2] = {lab_bswap32(lo32 + (uint32_t)lane), lab_bswap32(lo32 + (uint32_t)lane + 32u)};
+    uint32_t wd[2][4], c[2];
+    lab_chacha_w03<2, 0u>(seed, h, k7, wd);
+    uint32_t slow = straddle ? 3u : 0u;
+    slow |= lab_sample_u128(wd[0][0], wd[0][1], wd[0][2], wd[0][3], c[0]) ? 0u : 1u;
+    slow |= lab_sample_u128(wd[1][0], wd[1][1], wd[1][2], wd[1][3], c[1]) ? 0u : 2u;
+    if (slow) {
+        if (slow & 1u) {
+            const uint64_t l0 = clo + (uint64_t)lane;
+            c[0] = lab_crs_coeff_generic(seed, l0, chi + (l0 < clo), straddle ? 0u : 1u);
+        }
+        if (slow & 2u) {
+            const uint64_t l1 = clo + (uint64_t)lane + 32u;
+            c[1] = lab_crs_coeff_generic(seed, l1, chi + (l1 < clo), straddle ? 0u : 1u);
+        }
+    }
+    re = c[0]; im = c[1];
+    lab_ntt32_fwd_warp_smem(re, im, tws, lane, seed.one);
+}

@@ -18,8 +18,7 @@
 // reduction mod q, coalesced store into slot planes); accumulators double-buffered in the 512 TMEM columns.
 #pragma once
 #include <cuda.h>
-#include "lab_chacha.cuh"
-#include "lab_ntt.cuh"
+#include "lab_crsgen.cuh"
 
 namespace lab {
 
@@ -67,46 +66,17 @@ __global__ void __launch_bounds__(32 * GP_WARPS, MINB) k_gen_planes(LabSeed seed
     __syncthreads();
     const uint64_t runs_per_row = (N + 15) / 16, total_runs = nrows * runs_per_row;
     const uint64_t nwarps = (uint64_t)gridDim.x * GP_WARPS;
-    uint64_t tag = ~0ull;
+    LabWarpGen g;
     for (uint64_t run = (uint64_t)blockIdx.x * GP_WARPS + w; run < total_runs; run += nwarps) {
         const uint64_t row = run / runs_per_row;
         const uint32_t n0 = (uint32_t)(run % runs_per_row) * 16, n1 = min(n0 + 16u, N);
         uint8_t *q8 = planes + (((uint64_t)lane * ntiles + (row >> 6)) * 128 + (row & 63)) * kpad;
         for (uint32_t n = n0; n < n1; n++) {
             const uint64_t ctr = ((row0 + row) * (uint64_t)N + n) * 64ull;          // structs.rs:55-72
-            const uint64_t s0 = seed.limb[0] + ctr;
-            const uint64_t ntag = ((uint64_t)(s0 < ctr) << 32) | (s0 >> 32);
-            if (ntag != tag) {                                                        // warp-uniform, once per 2^32 counters
-                LabHoist hh;
-                lab_hoist_compute(seed, ctr, 0ull, hh);
-                __syncwarp();
-                if (lane == 0) {
-                    uint32_t *q = hoist[w];
-                    q[0] = hh.k3; q[1] = hh.P0; q[2] = hh.P1; q[3] = hh.Q0; q[4] = hh.A5; q[5] = hh.A10; q[6] = hh.Q1; q[7] = hh.Q2;
-                    q[8] = hh.A6; q[9] = hh.A2; q[10] = hh.A8; q[11] = hh.A13; q[12] = hh.A4; q[13] = hh.A9; q[14] = hh.A14;
-                }
-                __syncwarp();
-                tag = ntag;
-            }
-            const uint32_t lo32 = (uint32_t)s0;
-            const bool straddle = lo32 > 0xFFFFFFFFu - 63u;
-            LabHoist h;
-            const uint32_t *q = hoist[w];
-            h.k3 = q[0]; h.P0 = q[1]; h.P1 = q[2]; h.Q0 = q[3]; h.A5 = q[4]; h.A10 = q[5]; h.Q1 = q[6]; h.Q2 = q[7];
-            h.A6 = q[8]; h.A2 = q[9]; h.A8 = q[10]; h.A13 = q[11]; h.A4 = q[12]; h.A9 = q[13]; h.A14 = q[14];
-            const uint32_t k7[2] = {lab_bswap32(lo32 + (uint32_t)lane), lab_bswap32(lo32 + (uint32_t)lane + 32u)};
-            uint32_t wd[2][4], c[2];
-            lab_chacha_w03<2, 0u>(seed, h, k7, wd);
-            uint32_t slow = straddle ? 3u : 0u;
-            slow |= lab_sample_u128(wd[0][0], wd[0][1], wd[0][2], wd[0][3], c[0]) ? 0u : 1u;
-            slow |= lab_sample_u128(wd[1][0], wd[1][1], wd[1][2], wd[1][3], c[1]) ? 0u : 2u;
-            if (slow) {
-                if (slow & 1u) c[0] = lab_crs_coeff_generic(seed, ctr + lane, 0ull, straddle ? 0u : 1u);
-                if (slow & 2u) c[1] = lab_crs_coeff_generic(seed, ctr + lane + 32u, 0ull, straddle ? 0u : 1u);
-            }
-            lab_ntt32_fwd_warp_smem(c[0], c[1], tws, lane, seed.one);
-            *reinterpret_cast<uint16_t *>(q8 + 2 * n) = (uint16_t)((c[0] & 127u) | ((c[1] & 127u) << 8));
-            *reinterpret_cast<uint16_t *>(q8 + 64 * (uint64_t)kpad + 2 * n) = (uint16_t)((c[0] >> 7) | ((c[1] >> 7) << 8));
+            uint32_t re, im;
+            lab_crs_poly_hat_warp(seed, g, hoist[w], tws, ctr, 0ull, lane, re, im);
+            *reinterpret_cast<uint16_t *>(q8 + 2 * n) = (uint16_t)((re & 127u) | ((im & 127u) << 8));
+            *reinterpret_cast<uint16_t *>(q8 + 64 * (uint64_t)kpad + 2 * n) = (uint16_t)((re >> 7) | ((im >> 7) << 8));
         }
     }
 }
