@@ -128,7 +128,10 @@ int lab_crs_offset(const lab_constants *c, int which, uint64_t i, uint64_t j, ui
 
 /* ---- prover stages (proofgen.rs) ---- */
 /* S1 inner Ajtai commitments t_i[row] = <A_row, s_i> for rows [row0,row0+nrows) (proofgen.rs:41-49).
- * T: [R][nrows][64].  Row-sharding across GPUs = disjoint [row0,row0+nrows) per rank. */
+ * T: [R][nrows][64].  Row-sharding across GPUs = disjoint [row0,row0+nrows) per rank.
+ * Shapes from 2^22 polynomials of A (or more than 64 witness vectors) run as generate-then-contract: ChaCha20 + transform
+ * into int8 limb planes, then a tcgen05 contraction, in row chunks of 4 GB; the rows of T leave for the host chunk by chunk
+ * while the next chunk is generated (pinned host memory makes that copy asynchronous).  Smaller shapes: one fused kernel. */
 int lab_commit_inner(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], const uint32_t *S,
                      uint64_t row0, uint64_t nrows, uint32_t *T);
 /* S2 garbage polynomials g_ij = <s_i, s_j>, all R^2 (proofgen.rs:59-70) */
