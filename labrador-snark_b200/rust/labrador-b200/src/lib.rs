@@ -47,6 +47,21 @@ impl Context {
         Ok(Context(p))
     }
 }
+impl Context {
+    /// One process per GPU: rank 0 makes the id, the host distributes it (any transport), every rank attaches.
+    /// Afterwards `Prover::proof_gen` / `verify`, called by all ranks with the same arguments, shard the CRS-regenerating
+    /// stages by rows inside the library and all-gather them over NVLink (the reference: rayon, proofgen.rs:101-124).
+    pub fn comm_unique_id() -> [u8; 128] {
+        let mut id = [0u8; 128];
+        assert_eq!(unsafe { sys::lab_comm_unique_id(id.as_mut_ptr()) }, sys::LAB_OK);
+        id
+    }
+    pub fn comm_init(&self, id: &[u8; 128], rank: i32, world: i32) -> Result<(), String> {
+        if unsafe { sys::lab_comm_init(self.0, id.as_ptr(), rank, world) } == sys::LAB_OK { Ok(()) } else { Err(last_error(self.0)) }
+    }
+    /// Keep transformed CRS polynomials in HBM between calls (verify right after prove, proofs under one CRS); 0 = off.
+    pub fn crs_cache_configure(&self, max_bytes: usize) { unsafe { sys::lab_crs_cache_configure(self.0, max_bytes) }; }
+}
 impl Drop for Context { fn drop(&mut self) { unsafe { sys::lab_ctx_destroy(self.0) } } }
 fn last_error(ctx: *const sys::lab_ctx) -> String {
     unsafe { CStr::from_ptr(sys::lab_last_error(ctx)).to_string_lossy().into_owned() }
@@ -146,4 +161,22 @@ impl<'a> Prover<'a> {
             norm_sum: tr.norm_sum,
         }
     }
+}
+
+/// Verifier::verify (verification.rs:25-438) for a transcript kept in the dense ABI form: `Ok(())` or the number of the
+/// reference's check that failed (8..20).  `raw` are the buffers `lab_prove` filled.
+pub fn verify_dense(ctx: &Context, c: &RuntimeConstants, crs: &CRS, st: &sys::lab_state, ch: &sys::lab_challenges, raw: &sys::lab_transcript) -> Result<(), i32> {
+    let (mut accepted, mut failed, mut norm) = (0i32, 0i32, 0u64);
+    let rc = unsafe { sys::lab_verify(ctx.0, c, crs.base_seed.as_ptr(), st, ch, raw, &mut accepted, &mut failed, &mut norm) };
+    assert_eq!(rc, sys::LAB_OK, "{}", last_error(ctx.0));
+    if accepted != 0 { Ok(()) } else { Err(failed) }
+}
+
+/// The bytes `bincode::serialize(&Transcript)` gives in the reference (structs.rs:192-221), from the dense ABI form.
+pub fn transcript_bincode(c: &RuntimeConstants, raw: &sys::lab_transcript, ch: &sys::lab_challenges) -> Vec<u8> {
+    let mut size = 0usize;
+    assert_eq!(unsafe { sys::lab_transcript_bincode(c, raw, ch, std::ptr::null_mut(), 0, &mut size) }, sys::LAB_OK);
+    let mut out = vec![0u8; size];
+    assert_eq!(unsafe { sys::lab_transcript_bincode(c, raw, ch, out.as_mut_ptr(), out.len(), &mut size) }, sys::LAB_OK);
+    out
 }
