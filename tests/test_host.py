@@ -291,3 +291,38 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["metric"] == "witness_coeffs_per_s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_limb_split_contraction_identity():
+    """The arithmetic of lab_umma.cuh restated in numpy: int8 limb planes of A, the four signed B columns per witness vector,
+    s32 accumulation, recombination with 2^7 and 2^14 = 2 (mod q) -- equal to the complex dot product over F_{q^2}, and
+    the accumulators stay inside s32 for K' <= 32768."""
+    rng = np.random.default_rng(5)
+    N, R, rows = 37, 5, 6
+    are, aim = rng.integers(0, Q, (rows, N)), rng.integers(0, Q, (rows, N))
+    sre, sim = rng.integers(0, Q, (N, R)), rng.integers(0, Q, (N, R))
+    # direct: t = sum_n a * s over F_q[i]
+    tre = (are @ sre - aim @ sim) % Q
+    tim = (are @ sim + aim @ sre) % Q
+    # A limb planes, K-major: k = 2n + {re, im}
+    A = np.empty((rows, 2 * N), np.int64); A[:, 0::2] = are; A[:, 1::2] = aim
+    A_lo, A_hi = A & 127, A >> 7
+    assert A_lo.max() <= 127 and A_hi.max() <= 63
+    # B columns per vector: (RE,lo) (RE,hi) (IM,lo) (IM,hi)
+    B = np.zeros((4 * R, 2 * N), np.int64)
+    for i in range(R):
+        rl, rh, il, ih = sre[:, i] & 127, sre[:, i] >> 7, sim[:, i] & 127, sim[:, i] >> 7
+        B[4 * i + 0, 0::2], B[4 * i + 0, 1::2] = rl, -il
+        B[4 * i + 1, 0::2], B[4 * i + 1, 1::2] = rh, -ih
+        B[4 * i + 2, 0::2], B[4 * i + 2, 1::2] = il, rl
+        B[4 * i + 3, 0::2], B[4 * i + 3, 1::2] = ih, rh
+    assert np.abs(B).max() <= 127                        # fits signed 8 bit
+    D_lo, D_hi = A_lo @ B.T, A_hi @ B.T
+    OFF = Q * 131072
+    can = lambda d: (d + OFF) % Q                        # what the epilogue does with the signed accumulator
+    for i in range(R):
+        re = (can(D_lo[:, 4 * i]) + 128 * (can(D_lo[:, 4 * i + 1]) + can(D_hi[:, 4 * i])) + 2 * can(D_hi[:, 4 * i + 1])) % Q
+        im = (can(D_lo[:, 4 * i + 2]) + 128 * (can(D_lo[:, 4 * i + 3]) + can(D_hi[:, 4 * i + 2])) + 2 * can(D_hi[:, 4 * i + 3])) % Q
+        assert np.array_equal(re, tre[:, i]) and np.array_equal(im, tim[:, i])
+    assert (1 << 14) % Q == 2
+    assert 32768 * 127 * 127 < OFF < (1 << 31) - 32768 * 127 * 127      # K-segment bound: accumulator + OFF stays a positive s32
