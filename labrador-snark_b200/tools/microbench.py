@@ -79,6 +79,17 @@ def main():
         print(json.dumps({"kernel": "commit_inner cold (k_gen_planes + k_umma_commit)", "N": N, "R": R, "rows": rows, "ms_median": med,
                           "chacha_blocks_per_s": rows * N * 64 / (med * 1e-3)}), flush=True)
         ctx.free(dS); ctx.free(dT)
+    if "gen4" in which:         # a slice of cfg 4 (N = 2^16, R = 2^8): 4 passes x 4 K-segments of contraction per row chunk
+        N, R, rows = 65536, 256, 4736
+        c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
+        dS = ctx.malloc(R * N * 256)
+        ctx.synth_zq_dev(synth.SEED, 1, 0, R * N * 64, dS)
+        ctx.witness_load_dev(c, dS)
+        dT = ctx.malloc(R * rows * 256)
+        best, med = timeit(ctx, lambda: ctx.commit_inner_dev(SEED32, 0, rows, dT), reps=2, warm=1)
+        print(json.dumps({"kernel": "commit_inner cold, cfg-4 shape", "N": N, "R": R, "rows": rows, "chunk_mb": os.environ.get("LAB_GC_CHUNK_MB", "default"),
+                          "ms_median": med, "chacha_blocks_per_s": rows * N * 64 / (med * 1e-3)}), flush=True)
+        ctx.free(dS); ctx.free(dT)
     if "umma" in which:         # CRS-resident inner commitment on the tensor cores (lab_umma.cuh), cfg-3 shape on fewer rows
         N, R, rows = 4096, 64, 64 * 148 * 2
         c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
