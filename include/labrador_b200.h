@@ -89,6 +89,18 @@ int lab_timer_stop(lab_ctx *ctx, double *elapsed_ms);     /* synchronises on the
 int lab_comm_unique_id(uint8_t id[LAB_COMM_ID_BYTES]);
 int lab_comm_init(lab_ctx *ctx, const uint8_t id[LAB_COMM_ID_BYTES], int rank, int world);
 int lab_comm_destroy(lab_ctx *ctx);
+/* Collectives of the stage-sharded path, on the ctx stream, in place, device buffers (north star: "JL partial sums and
+ * aggregated z are combined with NCCL over NVLink as int64 followed by mod-q reduction").  Without a communicator (or with
+ * one rank) they are no-ops, so single-GPU callers run the same code.
+ *   lab_comm_allreduce_i64_dev : ncclSum over int64[n]                      (JL partials: 256 words; z: N*64 words)
+ *   lab_comm_allgather_dev     : rank r's bytes_per_rank bytes sit at buf + r * bytes_per_rank; all ranks get all slices
+ *   lab_comm_rank              : rank / world of the attached communicator (0 / 1 without one)
+ *   lab_comm_shard             : the contiguous balanced share [x0, x0 + nx) of `total` units this rank owns (the split
+ *                                used by the *_sharded_dev stage calls below; no divisibility requirement) */
+int lab_comm_allreduce_i64_dev(lab_ctx *ctx, int64_t *buf_dev, size_t n);
+int lab_comm_allgather_dev(lab_ctx *ctx, void *buf_dev, size_t bytes_per_rank);
+int lab_comm_rank(const lab_ctx *ctx, int *rank, int *world);
+int lab_comm_shard(const lab_ctx *ctx, uint64_t total, uint64_t *x0, uint64_t *nx);
 
 /* RuntimeConstants::new(N, R)  (constants.rs:234-264). Returns LAB_ERR_PARAMS (and fills out,
  * degenerate = 1) where the reference's formulas leave the range in which it terminates. */
@@ -143,6 +155,23 @@ int lab_jl_project(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, cons
  * p_partial the exact partial sums -- the per-rank piece of the int64 all-reduce when S4 is sharded by i */
 int lab_jl_project_part(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, const int8_t *pi_part, uint64_t i0, uint64_t ni,
                         int64_t p_partial[LAB_JL_ROWS]);
+/* ---- 2-bit packed JL matrices ("pi2") ----
+ * Entries of Pi are in {-1,0,1} (verification.rs:553-566); 16 consecutive entries c = 16 w + k of a row share one 32-bit
+ * word: bit k = (entry == +1), bit 16 + k = (entry == -1).  pi2: uint32_t[R][256][N*4] -- a quarter of the int8 bytes over
+ * PCIe and HBM.  Every int8 entry point above has a packed twin; the int8 forms pack on the device and run the same kernels.
+ * lab_pi_pack / lab_pi_unpack are host-side marshalling (no ctx, no arithmetic on ring elements). */
+int lab_pi_pack(const int8_t *pi, size_t n_entries /* multiple of 16 */, uint32_t *pi2);
+int lab_pi_unpack(const uint32_t *pi2, size_t n_entries /* multiple of 16 */, int8_t *pi);
+int lab_pi_pack_dev(lab_ctx *ctx, const int8_t *pi_dev, size_t n_entries, uint32_t *pi2_dev);
+int lab_jl_project2(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, const uint32_t *pi2, int64_t p[LAB_JL_ROWS], int *accepted);
+int lab_jl_project2_part(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, const uint32_t *pi2_part, uint64_t i0, uint64_t ni,
+                         int64_t p_partial[LAB_JL_ROWS]);
+int lab_aggregate_phi2(lab_ctx *ctx, const lab_constants *c, const uint32_t *phi, const uint32_t *pi2, uint32_t psi,
+                       const uint32_t omega[LAB_JL_ROWS], uint32_t *phi_pp);
+/* S2 / S9 for a shard of witness vectors, host buffers: rows [i0,i0+ni) of g ([ni][R][64]) and the partial sum
+ * z = sum_{i in shard} c_i s_i (canonical; partials of different shards add up mod q) */
+int lab_gram_part(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, uint64_t i0, uint64_t ni, uint32_t *G_part);
+int lab_amortize_z_part(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, const uint32_t *ch, uint64_t i0, uint64_t ni, uint32_t *z_partial);
 /* S3 u_1 = sum B_ik dig_k(t_i) + sum_{i<=j} dig_k(g_ij) C_ijk (proofgen.rs:101-153) */
 int lab_commit_outer_u1(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], const uint32_t *T, const uint32_t *G, uint32_t *u1);
 /* S8 u_2 = sum_{i<=j,k<T_1} dig_k(h_ij) D_ijk (proofgen.rs:364-378) */
@@ -166,13 +195,14 @@ typedef struct {                 /* State (structs.rs:269-286) with K = L = 1 */
  * draws these from thread_rng inside Verifier (verification.rs:441-513,553-566); for bit-exact
  * parity they are injected. */
 typedef struct {
-    const int8_t *pi;            /* [n_attempts][R][256][N*64] */
+    const int8_t *pi;            /* [n_attempts][R][256][N*64]; may be NULL when pi2 is given */
     int n_attempts;              /* 1..6 */
     uint32_t psi;
     const uint32_t *omega;       /* [256] */
     const uint32_t *alpha;       /* [64] */
     const uint32_t *beta;        /* [64] */
     const uint32_t *c;           /* [R][64] */
+    const uint32_t *pi2;         /* optional: the same matrices 2-bit packed, [n_attempts][R][256][N*4]; used when non-NULL */
 } lab_challenges;
 
 /* Transcript (structs.rs:192-209), dense; buffers caller-allocated (host). pi_i_all is the accepted
@@ -243,6 +273,22 @@ int lab_jl_project_dev(lab_ctx *ctx, const int8_t *pi_dev, uint64_t i0, uint64_t
 /* z restricted to witness vectors [i0,i0+ni) as exact int64 partial sums are not needed: z is mod q;
  * z_dev: [N][64] canonical partial (sum over the given i range) */
 int lab_amortize_z_dev(lab_ctx *ctx, const uint32_t *ch_dev, uint64_t i0, uint64_t ni, uint32_t *z_dev);
+/* packed twin of lab_jl_project_dev: pi2_dev holds the rows of vectors [i0,i0+ni) only, [ni][256][N*4] */
+int lab_jl_project2_dev(lab_ctx *ctx, const uint32_t *pi2_dev, uint64_t i0, uint64_t ni, int64_t *p_dev);
+/* Stage calls sharded over the communicator (all ranks call them; shard = lab_comm_shard(R)); results complete on every rank:
+ *   JL: pi2_part_dev = this rank's vectors; p_dev = int64 all-reduce of the partials                 (G4)
+ *   z : canonical partial widened to int64, all-reduced, reduced mod q                               (G9)
+ *   g : this rank's rows of the (i, j) grid, completed by an exchange over all ranks; G_dev [R][R][64] (G2)
+ * Without a communicator they compute everything locally. */
+int lab_jl_project_sharded_dev(lab_ctx *ctx, const uint32_t *pi2_part_dev, int64_t *p_dev);
+int lab_amortize_z_sharded_dev(lab_ctx *ctx, const uint32_t *ch_dev, uint32_t *z_dev);
+int lab_gram_sharded_dev(lab_ctx *ctx, uint32_t *G_dev);
+/* Host-buffer twin of lab_witness_load_dev: uploads S ([R][N][64], host) into memory the ctx owns and transforms it, so
+ * that the stage calls of one proof share one upload (lab_commit_inner_resident, the *_dev and *_sharded_dev calls). */
+int lab_witness_load(lab_ctx *ctx, const lab_constants *c, const uint32_t *S_host);
+/* lab_commit_inner for the loaded witness with a HOST destination: rows of T leave for T_host ([R][nrows][64], pinned memory
+ * makes the copies asynchronous) chunk by chunk while the next chunk is generated; returns after the last copy. */
+int lab_commit_inner_resident(lab_ctx *ctx, const uint8_t seed[32], uint64_t row0, uint64_t nrows, uint32_t *T_host);
 
 
 /* ---- seeded synthetic inputs / device-side challenge source ----
@@ -252,6 +298,8 @@ int lab_amortize_z_dev(lab_ctx *ctx, const uint32_t *ch_dev, uint64_t i0, uint64
  * entry from stream 5 + (attempt << 8), row-major fill order. */
 int lab_synth_zq_dev(lab_ctx *ctx, uint64_t seed, uint64_t stream, uint64_t start, size_t n, uint32_t *out_dev);
 int lab_synth_pi_dev(lab_ctx *ctx, uint64_t seed, uint64_t attempt, uint64_t first_entry /* multiple of 32 */, size_t total, int8_t *out_dev);
+/* the same entries written directly in the packed form (total a multiple of 32): out_dev uint32_t[total / 16] */
+int lab_synth_pi2_dev(lab_ctx *ctx, uint64_t seed, uint64_t attempt, uint64_t first_entry /* multiple of 32 */, size_t total, uint32_t *out_dev);
 /* Verifier::fetch_challenge (verification.rs:460-489) on the device, seeded: challenge polynomials first_idx ..
  * first_idx + count - 1 into c_dev [count][64]; streams 10 / 11 + (idx << 8) for the draws without replacement from
  * {0 x23, 1 x31, 2 x10} with random signs (util.rs:83-104) and for the 1000 operator-norm samples (util.rs:227-246,

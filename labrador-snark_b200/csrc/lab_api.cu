@@ -5,11 +5,15 @@
 #include "lab_kernels.cuh"
 #include "lab_gen.cuh"
 #include "lab_umma.cuh"
+#include "lab_jl.cuh"
 
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
+#include <atomic>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -39,7 +43,9 @@ struct lab_ctx {
     std::vector<void *> overflow;
     // resident witness (device-stage API)
     lab_constants wc{};
-    const uint32_t *S_dev = nullptr;   // caller-owned
+    const uint32_t *S_dev = nullptr;   // caller-owned, or S_own after lab_witness_load
+    uint32_t *S_own = nullptr;         // device copy made by lab_witness_load (host-buffer twin of lab_witness_load_dev)
+    size_t S_own_bytes = 0;
     uint32_t *What = nullptr;          // owned, [N][R][32]
     size_t What_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -98,11 +104,12 @@ struct lab_ctx {
 
 #define LAUNCH_SMEM(kern, grid, block, smem, ...)                                                   \
     do {                                                                                             \
-        /* per call site (= per instantiation) and device; idempotent, so racing threads are harmless */ \
-        static bool attr_set_[64] = {};                                                              \
-        if (!attr_set_[ctx->device & 63]) {                                                          \
+        /* per call site (= per instantiation) and device; the attribute call is idempotent and the flag atomic, */ \
+        /* so batch worker threads may race here                                                              */ \
+        static std::atomic<bool> attr_set_[64];                                                      \
+        if (!attr_set_[ctx->device & 63].load(std::memory_order_acquire)) {                          \
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); \
-            attr_set_[ctx->device & 63] = true;                                                      \
+            attr_set_[ctx->device & 63].store(true, std::memory_order_release);                      \
         }                                                                                            \
         kern<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);                                 \
         ctx->launches++;                                                                             \
@@ -208,6 +215,7 @@ extern "C" void lab_ctx_destroy(lab_ctx *ctx) {
     for (void *p : ctx->overflow) cudaFree(p);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->What) cudaFree(ctx->What);
+    if (ctx->S_own) cudaFree(ctx->S_own);
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
     if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->ev_tg); }
     for (auto &p : ctx->mv_plans) cudaFree(p.dev);
@@ -262,15 +270,15 @@ struct LabNccl {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 static LabNccl *nccl_api(std::string &err) {
     static LabNccl api;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static std::once_flag once;
+    std::call_once(once, [] {
         void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
         if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
         if (h) {
@@ -281,9 +289,10 @@ static LabNccl *nccl_api(std::string &err) {
             api.GroupStart = (decltype(api.GroupStart))dlsym(h, "ncclGroupStart");
             api.GroupEnd = (decltype(api.GroupEnd))dlsym(h, "ncclGroupEnd");
             api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
-            if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.GroupStart && api.GroupEnd && api.GetErrorString) api.h = h;
+            api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+            if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.AllReduce && api.GroupStart && api.GroupEnd && api.GetErrorString) api.h = h;
         }
-    }
+    });
     if (!api.h) { err = "libnccl.so.2 not found or incomplete (needed only for lab_comm_*)"; return nullptr; }
     return &api;
 }
@@ -352,6 +361,46 @@ static int allgather_rows(lab_ctx *ctx, uint32_t *buf, uint64_t blocks, uint64_t
         NCCLCK(nc->AllGather(base + (uint64_t)ctx->rank * cnt, base, cnt, ncclUint32, ctx->comm, ctx->stream));
     }
     NCCLCK(nc->GroupEnd());
+    return LAB_OK;
+}
+
+// in-place int64 sum over the ranks (JL partial sums, z partial sums) and in-place all-gather of equal byte slices
+static int allreduce_i64(lab_ctx *ctx, long long *buf, size_t n) {
+    if (!ctx->comm || ctx->world <= 1 || !n) return LAB_OK;
+    LabNccl *nc = nccl_api(ctx->err);
+    if (!nc) return LAB_ERR_CUDA;
+    NCCLCK(nc->AllReduce(buf, buf, n, ncclInt64, ncclSum, ctx->comm, ctx->stream));
+    return LAB_OK;
+}
+static int allgather_bytes(lab_ctx *ctx, void *buf, size_t bytes_per_rank) {
+    if (!ctx->comm || ctx->world <= 1 || !bytes_per_rank) return LAB_OK;
+    LabNccl *nc = nccl_api(ctx->err);
+    if (!nc) return LAB_ERR_CUDA;
+    NCCLCK(nc->AllGather((const char *)buf + (size_t)ctx->rank * bytes_per_rank, buf, bytes_per_rank, ncclUint8, ctx->comm, ctx->stream));
+    return LAB_OK;
+}
+extern "C" int lab_comm_allreduce_i64_dev(lab_ctx *ctx, int64_t *buf_dev, size_t n) {
+    if (!ctx || (!buf_dev && n)) return LAB_ERR_PARAMS;
+    return allreduce_i64(ctx, reinterpret_cast<long long *>(buf_dev), n);
+}
+extern "C" int lab_comm_allgather_dev(lab_ctx *ctx, void *buf_dev, size_t bytes_per_rank) {
+    if (!ctx || (!buf_dev && bytes_per_rank)) return LAB_ERR_PARAMS;
+    return allgather_bytes(ctx, buf_dev, bytes_per_rank);
+}
+extern "C" int lab_comm_rank(const lab_ctx *ctx, int *rank, int *world) {
+    if (!ctx) return LAB_ERR_PARAMS;
+    if (rank) *rank = ctx->comm ? ctx->rank : 0;
+    if (world) *world = ctx->comm ? ctx->world : 1;
+    return LAB_OK;
+}
+// contiguous balanced split of `total` units over the ranks (labrador_b200/shard.py split(): the first total % world ranks
+// get one unit more)
+extern "C" int lab_comm_shard(const lab_ctx *ctx, uint64_t total, uint64_t *x0, uint64_t *nx) {
+    if (!ctx || !x0 || !nx) return LAB_ERR_PARAMS;
+    const uint64_t world = ctx->comm ? (uint64_t)ctx->world : 1, rank = ctx->comm ? (uint64_t)ctx->rank : 0;
+    const uint64_t base = total / world, rem = total % world;
+    *x0 = rank * base + std::min(rank, rem);
+    *nx = base + (rank < rem ? 1 : 0);
     return LAB_OK;
 }
 
@@ -436,11 +485,12 @@ typedef CUresult (*lab_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuui
                                         const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static lab_encode_tiled_fn encode_tiled() {
     static lab_encode_tiled_fn fn = nullptr;
-    if (!fn) {
+    static std::once_flag once;
+    std::call_once(once, [] {
         void *p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (lab_encode_tiled_fn)p;
-    }
+    });
     return fn;
 }
 // 2-D map over [rows][kpad] bytes, box = 128 bytes x box_rows rows, 128-byte swizzle (the layout tcgen05's K-major descriptors expect)
@@ -494,6 +544,16 @@ static int ensure_stream2(lab_ctx *ctx) {
     CK(cudaEventCreateWithFlags(&ctx->ev_tg, cudaEventDisableTiming));
     return LAB_OK;
 }
+// Work forked to the second stream uses arena buffers.  Every exit path that has not joined the strand back into the
+// main stream (an error, a rejected JL projection) must wait for it, or the next call on this ctx would reset the arena
+// under kernels that are still running.
+struct Stream2Guard {
+    cudaStream_t s2;
+    bool armed = true;
+    explicit Stream2Guard(cudaStream_t s) : s2(s) {}
+    void disarm() { armed = false; }
+    ~Stream2Guard() { if (armed && s2) cudaStreamSynchronize(s2); }
+};
 // transient limb planes for `rows_c` rows of `per_row` bytes (kept in the ctx between calls); nullptr when there is no room
 static void *gc_chunk_get(lab_ctx *ctx, size_t bytes) {
     if (ctx->gc_chunk && ctx->gc_chunk_bytes >= bytes) return ctx->gc_chunk;
@@ -510,6 +570,38 @@ static void gc_chunk_release(lab_ctx *ctx) {
     cudaFree(ctx->gc_chunk);
     ctx->gc_chunk = nullptr;
     ctx->gc_chunk_bytes = 0;
+}
+
+// ---- CRS cache bookkeeping ----
+// An entry is registered only after the launches that fill it were accepted (a failed fill must not be served as a hit later).
+// When there is no room, entries generated under a different seed (the key starts with the seed limbs) are dropped, oldest
+// first; entries of the current seed are kept -- they are what the next verify / proof under this CRS will ask for.
+static uint32_t *crs_cache_lookup(lab_ctx *ctx, const std::vector<unsigned char> &key) {
+    for (size_t e = 0; e < ctx->crs_cache.size(); e++)
+        if (ctx->crs_cache[e].key == key) {
+            if (e + 1 != ctx->crs_cache.size()) std::rotate(ctx->crs_cache.begin() + e, ctx->crs_cache.begin() + e + 1, ctx->crs_cache.end());   // most recent last
+            return ctx->crs_cache.back().dev;
+        }
+    return nullptr;
+}
+static void *crs_cache_reserve(lab_ctx *ctx, const std::vector<unsigned char> &key, size_t need) {
+    if (need > ctx->crs_cache_max) return nullptr;
+    for (size_t e = 0; e < ctx->crs_cache.size() && ctx->crs_cache_used + need > ctx->crs_cache_max;) {
+        auto &en = ctx->crs_cache[e];
+        if (en.key.size() >= 32 && key.size() >= 32 && std::memcmp(en.key.data(), key.data(), 32) == 0) { e++; continue; }
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(en.dev);
+        ctx->crs_cache_used -= en.bytes;
+        ctx->crs_cache.erase(ctx->crs_cache.begin() + e);
+    }
+    if (ctx->crs_cache_used + need > ctx->crs_cache_max) return nullptr;
+    void *dev = nullptr;
+    if (cudaMalloc(&dev, need) != cudaSuccess) { cudaGetLastError(); return nullptr; }      // no room on the device: the call stays uncached
+    return dev;
+}
+static void crs_cache_commit(lab_ctx *ctx, std::vector<unsigned char> &&key, void *dev, size_t bytes) {
+    ctx->crs_cache.push_back(lab_ctx::CrsEntry{std::move(key), (uint32_t *)dev, bytes});
+    ctx->crs_cache_used += bytes;
 }
 
 // T_host (optional, host layout [R][nrows][64], only with the default device layout): the rows of every finished chunk of the
@@ -545,9 +637,7 @@ static int d_commit_inner(lab_ctx *ctx, const LabSeed &seed, const uint32_t *Wha
         const uint64_t tag = 0x41ull /* 'A' */, kv[4] = {tag, N, row0, nrows};
         std::memcpy(key.data(), seed.limb, sizeof(seed.limb));
         std::memcpy(key.data() + sizeof(seed.limb), kv, sizeof kv);
-        uint8_t *acache = nullptr;
-        for (auto &e : ctx->crs_cache)
-            if (e.key == key) { acache = (uint8_t *)e.dev; break; }
+        uint8_t *acache = (uint8_t *)crs_cache_lookup(ctx, key);
         UmmaScratch sc;
         if (acache) {
             ctx->crs_cache_hits++;
@@ -555,15 +645,11 @@ static int d_commit_inner(lab_ctx *ctx, const LabSeed &seed, const uint32_t *Wha
         }
         ctx->crs_cache_misses++;
         const size_t need = (size_t)ntiles * 64 * per_row;
-        if (ctx->crs_cache_used + need <= ctx->crs_cache_max) {
-            void *dev = nullptr;
-            if (cudaMalloc(&dev, need) == cudaSuccess) {
-                ctx->crs_cache.push_back(lab_ctx::CrsEntry{std::move(key), (uint32_t *)dev, need});
-                ctx->crs_cache_used += need;
-                TRY(gen_planes((uint8_t *)dev, 0, nrows, ntiles));
-                return contract((uint8_t *)dev, 0, nrows, ntiles, sc);
-            }
-            cudaGetLastError();
+        if (void *dev = crs_cache_reserve(ctx, key, need)) {
+            int rc = gen_planes((uint8_t *)dev, 0, nrows, ntiles);
+            if (rc != LAB_OK) { cudaFree(dev); return rc; }
+            crs_cache_commit(ctx, std::move(key), dev, need);
+            return contract((uint8_t *)dev, 0, nrows, ntiles, sc);
         }
     }
     // (2) Generate-then-contract, the large-shape cold path (cfg 3 / cfg 4) and every shape with more than 64 witness vectors:
@@ -589,6 +675,7 @@ static int d_commit_inner(lab_ctx *ctx, const LabSeed &seed, const uint32_t *Wha
                 UmmaScratch sc;              // first use is the largest (rows_c rows): the arena allocation fits every chunk
                 const bool stream_out = T_host && host_done && t_stride == nrows && t_row_off == 0;
                 if (stream_out) TRY(ensure_stream2(ctx));
+                Stream2Guard s2guard(stream_out ? ctx->stream2 : nullptr);
                 for (uint64_t r0 = 0; r0 < nrows; r0 += rows_c) {
                     const uint64_t nr = std::min<uint64_t>(rows_c, nrows - r0);
                     const uint32_t nt = (uint32_t)((nr + 63) / 64);
@@ -606,6 +693,7 @@ static int d_commit_inner(lab_ctx *ctx, const LabSeed &seed, const uint32_t *Wha
                     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
                     *host_done = true;
                 }
+                s2guard.disarm();
                 return LAB_OK;
             }
         }
@@ -685,30 +773,31 @@ static int d_crs_matvec(lab_ctx *ctx, const LabSeed &seed, const std::vector<MvS
     const uint64_t warps = n_rows * ipr;
     // CRS cache: key = seed, row range, item list
     uint32_t *cache_hit = nullptr, *cache_fill = nullptr;
+    std::vector<unsigned char> fill_key;
+    size_t fill_bytes = 0;
     if (ctx->crs_cache_max) {
         std::vector<unsigned char> key(sizeof(seed.limb) + 2 * sizeof(uint64_t) + ibytes);
         std::memcpy(key.data(), seed.limb, sizeof(seed.limb));
         std::memcpy(key.data() + sizeof(seed.limb), &x0, 8);
         std::memcpy(key.data() + sizeof(seed.limb) + 8, &n_rows, 8);
         std::memcpy(key.data() + sizeof(seed.limb) + 16, items.data(), ibytes);
-        for (auto &e : ctx->crs_cache)
-            if (e.key == key) { cache_hit = e.dev; break; }
+        cache_hit = crs_cache_lookup(ctx, key);
         const size_t need = (size_t)n_rows * total_polys * 32 * sizeof(uint32_t);
         if (cache_hit) ctx->crs_cache_hits++;
         else {
             ctx->crs_cache_misses++;
-            if (ctx->crs_cache_used + need <= ctx->crs_cache_max) {
-                void *dev = nullptr;
-                if (cudaMalloc(&dev, need) == cudaSuccess) {
-                    cache_fill = (uint32_t *)dev;
-                    ctx->crs_cache.push_back(lab_ctx::CrsEntry{std::move(key), cache_fill, need});
-                    ctx->crs_cache_used += need;
-                } else cudaGetLastError();         // no room: this call simply stays uncached
-            }
+            cache_fill = (uint32_t *)crs_cache_reserve(ctx, key, need);
+            if (cache_fill) { fill_key = std::move(key); fill_bytes = need; }
         }
     }
     if (cache_hit) LAUNCH(k_cached_matvec, (unsigned)((warps + 7) / 8), 256, cache_hit, total_polys, d_items, ipr, n_rows, V, partial);
-    else if (cache_fill) LAUNCH(k_crs_matvec<true>, (unsigned)((warps + 7) / 8), 256, seed, d_items, ipr, n_rows, x0, V, partial, cache_fill, total_polys);
+    else if (cache_fill) {
+        k_crs_matvec<true><<<(unsigned)((warps + 7) / 8), 256, 0, ctx->stream>>>(seed, d_items, ipr, n_rows, x0, V, partial, cache_fill, total_polys);
+        ctx->launches++;
+        cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) { cudaFree(cache_fill); ctx->err = std::string("k_crs_matvec<true>: ") + cudaGetErrorString(le); return LAB_ERR_CUDA; }
+        crs_cache_commit(ctx, std::move(fill_key), cache_fill, fill_bytes);      // registered only once the fill was accepted
+    }
     else LAUNCH(k_crs_matvec<false>, (unsigned)((warps + 7) / 8), 256, seed, d_items, ipr, n_rows, x0, V, partial, (uint32_t *)nullptr, total_polys);
     LAUNCH(k_finish_rows, (unsigned)((n_rows + 7) / 8), 256, partial, ipr, n_rows, out);
     return LAB_OK;
@@ -764,11 +853,22 @@ static int d_gram(lab_ctx *ctx, const uint32_t *What, uint64_t N, uint64_t R, ui
     LAUNCH(k_ip_hat, (unsigned)(ni * R), 256, What + i0 * 32, (size_t)R, (size_t)1, What, (size_t)R, (size_t)1, (size_t)N, (size_t)R, 1u, 0, Ghat);
     return d_inv_hat(ctx, Ghat, dG, ni * R);
 }
-static int d_jl(lab_ctx *ctx, const int8_t *dPi, const uint32_t *dS, uint64_t ND, uint64_t i0, uint64_t ni, unsigned long long *dp) {
+// int8 {-1,0,1} entries -> 2-bit packed words (lab_jl.cuh); n_entries is a multiple of 64
+static int d_pack_pi(lab_ctx *ctx, const int8_t *dPi8, size_t n_entries, uint32_t *dPi2) {
+    if (!n_entries) return LAB_OK;
+    LAUNCH(k_pi_pack, grid_for(n_entries / 16, 256, ctx->sms * 16), 256, dPi8, n_entries / 16, dPi2);
+    return LAB_OK;
+}
+// partial projection of witness vectors [i0, i0 + ni): dPi2 holds their rows only ([ni][256][ND / 16]), dS the whole witness
+static int d_jl(lab_ctx *ctx, const uint32_t *dPi2, const uint32_t *dS, uint64_t ND, uint64_t i0, uint64_t ni, unsigned long long *dp) {
     CK(cudaMemsetAsync(dp, 0, LAB_JL_ROWS * sizeof(unsigned long long), ctx->stream));
     if (!ni) return LAB_OK;
-    const size_t chunks = (ND + JL_CH - 1) / JL_CH;
-    LAUNCH(k_jl, (unsigned)(ni * chunks), 256, dPi, dS, (size_t)ND, (size_t)i0, dp);
+    if (ND / 16 >= (1ull << 32) || i0 + ni >= (1ull << 32)) FAIL(LAB_ERR_PARAMS, "JL: shape exceeds 32-bit word indexing");
+    const uint64_t upv = (ND + JL2_UNIT - 1) / JL2_UNIT, total = ni * upv;
+    // persistent CTAs, three per SM (64 KB of tables each); a lane's int32 row accumulators take 2^14 units of at most 2^17 each
+    uint64_t grid = std::min<uint64_t>(total, (uint64_t)ctx->sms * 3);
+    grid = std::max<uint64_t>(grid, (total + 8191) / 8192);
+    LAUNCH_SMEM(k_jl2, (unsigned)grid, JL2_THREADS, JL2_SMEM, dPi2, dS, ND, (uint32_t)(ND / 16), (uint32_t)i0, (uint32_t)upv, total, dp);
     return LAB_OK;
 }
 // Verifier::valid_projection (verification.rs:568-579), literal f64: sqrt(sum p^2) <= sqrt(128) * beta
@@ -954,51 +1054,66 @@ extern "C" int lab_commit_inner(lab_ctx *ctx, const lab_constants *c, const uint
     if (!host_done) TRY(download(ctx, T, dT, c->R * nrows * 64));
     return lab_sync(ctx);
 }
-extern "C" int lab_gram(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, uint32_t *G) {
+extern "C" int lab_gram_part(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, uint64_t i0, uint64_t ni, uint32_t *G_part) {
     CallScope cs(ctx);
     TRY(check_consts(ctx, c, false));
+    if (i0 + ni > c->R) FAIL(LAB_ERR_SHAPE, "witness range exceeds R");
+    if (!ni) return LAB_OK;
     uint32_t *dS, *What, *Ghat, *dG;
     TRY(load_witness(ctx, c, S, &dS, &What));
-    TRY(arena_alloc(ctx, c->R * c->R * 32, &Ghat));
-    TRY(arena_alloc(ctx, c->R * c->R * 64, &dG));
-    TRY(d_gram(ctx, What, c->N, c->R, 0, c->R, Ghat, dG));
-    TRY(download(ctx, G, dG, c->R * c->R * 64));
+    TRY(arena_alloc(ctx, ni * c->R * 32, &Ghat));
+    TRY(arena_alloc(ctx, ni * c->R * 64, &dG));
+    TRY(d_gram(ctx, What, c->N, c->R, i0, ni, Ghat, dG));
+    TRY(download(ctx, G_part, dG, ni * c->R * 64));
+    return lab_sync(ctx);
+}
+extern "C" int lab_gram(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, uint32_t *G) {
+    if (!c) return LAB_ERR_PARAMS;
+    return lab_gram_part(ctx, c, S, 0, c->R, G);
+}
+static int upload_pi2(lab_ctx *ctx, const int8_t *pi8, const uint32_t *pi2, uint64_t nvec, uint64_t ND, uint32_t *dPi2, int8_t *dPi8_scratch);
+// host-buffer JL for witness vectors [i0, i0 + ni) (whole witness S given; only those vectors travel)
+static int jl_host(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, const int8_t *pi8, const uint32_t *pi2, uint64_t i0, uint64_t ni, int64_t *p) {
+    TRY(check_consts(ctx, c, false));
+    if (i0 + ni > c->R) FAIL(LAB_ERR_SHAPE, "witness range exceeds R");
+    const uint64_t ND = c->N * LAB_D;
+    uint32_t *dS = nullptr, *dPi2 = nullptr;
+    int8_t *dPi8 = nullptr;
+    unsigned long long *dp;
+    TRY(arena_alloc(ctx, LAB_JL_ROWS, &dp));
+    if (ni) {
+        TRY(upload(ctx, S + i0 * ND, ni * ND, &dS));                  // device buffer indexed from i0
+        TRY(arena_alloc(ctx, ni * LAB_JL_ROWS * ND / 16, &dPi2));
+        if (!pi2) TRY(arena_alloc(ctx, ni * LAB_JL_ROWS * ND, &dPi8));
+        TRY(upload_pi2(ctx, pi8, pi2, ni, ND, dPi2, dPi8));
+    }
+    TRY(d_jl(ctx, dPi2, dS, ND, 0, ni, dp));
+    CK(cudaMemcpyAsync(p, dp, LAB_JL_ROWS * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     return lab_sync(ctx);
 }
 extern "C" int lab_jl_project(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, const int8_t *pi, int64_t p[LAB_JL_ROWS], int *accepted) {
     CallScope cs(ctx);
-    TRY(check_consts(ctx, c, false));
-    const uint64_t ND = c->N * LAB_D;
-    uint32_t *dS;
-    int8_t *dPi;
-    unsigned long long *dp;
-    TRY(upload(ctx, S, c->R * ND, &dS));
-    TRY(upload(ctx, pi, c->R * LAB_JL_ROWS * ND, &dPi));
-    TRY(arena_alloc(ctx, LAB_JL_ROWS, &dp));
-    TRY(d_jl(ctx, dPi, dS, ND, 0, c->R, dp));
-    CK(cudaMemcpyAsync(p, dp, LAB_JL_ROWS * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    TRY(lab_sync(ctx));
+    TRY(jl_host(ctx, c, S, pi, nullptr, 0, c ? c->R : 0, p));
+    if (accepted) *accepted = valid_projection(c, p) ? 1 : 0;
+    return LAB_OK;
+}
+extern "C" int lab_jl_project2(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, const uint32_t *pi2, int64_t p[LAB_JL_ROWS], int *accepted) {
+    CallScope cs(ctx);
+    if (!pi2) FAIL(LAB_ERR_PARAMS, "null pi2");
+    TRY(jl_host(ctx, c, S, nullptr, pi2, 0, c ? c->R : 0, p));
     if (accepted) *accepted = valid_projection(c, p) ? 1 : 0;
     return LAB_OK;
 }
 extern "C" int lab_jl_project_part(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, const int8_t *pi_part, uint64_t i0, uint64_t ni,
                                    int64_t p_partial[LAB_JL_ROWS]) {
     CallScope cs(ctx);
-    TRY(check_consts(ctx, c, false));
-    if (i0 + ni > c->R) FAIL(LAB_ERR_SHAPE, "witness range exceeds R");
-    const uint64_t ND = c->N * LAB_D;
-    uint32_t *dS = nullptr;
-    int8_t *dPi = nullptr;
-    unsigned long long *dp;
-    TRY(arena_alloc(ctx, LAB_JL_ROWS, &dp));
-    if (ni) {
-        // only the witness vectors of this part travel: device buffer indexed from i0
-        TRY(upload(ctx, S + i0 * ND, ni * ND, &dS));
-        TRY(upload(ctx, pi_part, ni * LAB_JL_ROWS * ND, &dPi));
-    }
-    TRY(d_jl(ctx, dPi, dS, ND, 0, ni, dp));
-    CK(cudaMemcpyAsync(p_partial, dp, LAB_JL_ROWS * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    return lab_sync(ctx);
+    return jl_host(ctx, c, S, pi_part, nullptr, i0, ni, p_partial);
+}
+extern "C" int lab_jl_project2_part(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, const uint32_t *pi2_part, uint64_t i0, uint64_t ni,
+                                    int64_t p_partial[LAB_JL_ROWS]) {
+    CallScope cs(ctx);
+    if (ni && !pi2_part) FAIL(LAB_ERR_PARAMS, "null pi2");
+    return jl_host(ctx, c, S, nullptr, pi2_part, i0, ni, p_partial);
 }
 extern "C" int lab_commit_outer_u1(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], const uint32_t *T, const uint32_t *G, uint32_t *u1) {
     CallScope cs(ctx);
@@ -1021,33 +1136,65 @@ extern "C" int lab_commit_outer_u2(lab_ctx *ctx, const lab_constants *c, const u
     TRY(download(ctx, u2, du2, c->KAPPA_2 * 64));
     return lab_sync(ctx);
 }
-static int d_aggregate_phi(lab_ctx *ctx, const lab_constants *c, const uint32_t *dphi, const int8_t *dPi, uint32_t psi, const uint32_t *domega, uint32_t *dpp) {
-    const uint64_t ND = c->N * LAB_D, total = c->R * ND;
+// phi''_i for vectors [i0, i0 + ni): dphi, dpp point at vector i0 ([ni][N][64]); dPi2 holds the rows of those vectors
+static int d_aggregate_phi(lab_ctx *ctx, const lab_constants *c, const uint32_t *dphi, const uint32_t *dPi2, uint32_t psi, const uint32_t *domega, uint32_t *dpp,
+                           uint64_t ni = ~0ull) {
+    if (ni == ~0ull) ni = c->R;
+    const uint64_t ND = c->N * LAB_D, total = ni * ND;
+    if (!total) return LAB_OK;
     uint32_t *v;
     TRY(arena_alloc(ctx, total, &v));
-    LAUNCH(k_piT_omega, (unsigned)((total + 255) / 256), 256, dPi, domega, (size_t)total, (size_t)ND, v);
+    LAUNCH(k_piT_omega2, (unsigned)((total / 16 + 255) / 256), 256, dPi2, domega, total / 16, (uint32_t)(ND / 16), v);
     LAUNCH(k_phi_pp, (unsigned)((total + 255) / 256), 256, dphi, v, psi % LAB_Q, (size_t)total, dpp);
     return LAB_OK;
+}
+// uploads JL matrices for `nvec` vectors: packed words when the caller has them, otherwise int8 entries packed on the device
+static int upload_pi2(lab_ctx *ctx, const int8_t *pi8, const uint32_t *pi2, uint64_t nvec, uint64_t ND, uint32_t *dPi2, int8_t *dPi8_scratch) {
+    const size_t entries = nvec * LAB_JL_ROWS * ND;
+    if (!entries) return LAB_OK;
+    if (pi2) {
+        CK(cudaMemcpyAsync(dPi2, pi2, entries / 4, cudaMemcpyHostToDevice, ctx->stream));
+        return LAB_OK;
+    }
+    if (!pi8) FAIL(LAB_ERR_PARAMS, "no JL matrix given (pi or pi2)");
+    CK(cudaMemcpyAsync(dPi8_scratch, pi8, entries, cudaMemcpyHostToDevice, ctx->stream));
+    return d_pack_pi(ctx, dPi8_scratch, entries, dPi2);
+}
+static int aggregate_phi_host(lab_ctx *ctx, const lab_constants *c, const uint32_t *phi, const int8_t *pi8, const uint32_t *pi2, uint32_t psi,
+                              const uint32_t *omega, uint32_t *phi_pp) {
+    TRY(check_consts(ctx, c, false));
+    const uint64_t ND = c->N * LAB_D;
+    uint32_t *dphi, *dom, *dpp, *dPi2;
+    int8_t *dPi8 = nullptr;
+    TRY(upload(ctx, phi, c->R * ND, &dphi));
+    TRY(arena_alloc(ctx, c->R * LAB_JL_ROWS * ND / 16, &dPi2));
+    if (!pi2) TRY(arena_alloc(ctx, c->R * LAB_JL_ROWS * ND, &dPi8));
+    TRY(upload_pi2(ctx, pi8, pi2, c->R, ND, dPi2, dPi8));
+    TRY(upload(ctx, omega, (size_t)LAB_JL_ROWS, &dom));
+    TRY(arena_alloc(ctx, c->R * ND, &dpp));
+    TRY(d_aggregate_phi(ctx, c, dphi, dPi2, psi, dom, dpp));
+    TRY(download(ctx, phi_pp, dpp, c->R * ND));
+    return lab_sync(ctx);
 }
 extern "C" int lab_aggregate_phi(lab_ctx *ctx, const lab_constants *c, const uint32_t *phi, const int8_t *pi, uint32_t psi,
                                  const uint32_t omega[LAB_JL_ROWS], uint32_t *phi_pp) {
     CallScope cs(ctx);
-    TRY(check_consts(ctx, c, false));
-    const uint64_t ND = c->N * LAB_D;
-    uint32_t *dphi, *dom, *dpp;
-    int8_t *dPi;
-    TRY(upload(ctx, phi, c->R * ND, &dphi));
-    TRY(upload(ctx, pi, c->R * LAB_JL_ROWS * ND, &dPi));
-    TRY(upload(ctx, omega, (size_t)LAB_JL_ROWS, &dom));
-    TRY(arena_alloc(ctx, c->R * ND, &dpp));
-    TRY(d_aggregate_phi(ctx, c, dphi, dPi, psi, dom, dpp));
-    TRY(download(ctx, phi_pp, dpp, c->R * ND));
-    return lab_sync(ctx);
+    return aggregate_phi_host(ctx, c, phi, pi, nullptr, psi, omega, phi_pp);
 }
-static int d_h_gram(lab_ctx *ctx, const uint32_t *PFhat, const uint32_t *What, uint64_t N, uint64_t R, uint32_t *Hhat, uint32_t *dH) {
+extern "C" int lab_aggregate_phi2(lab_ctx *ctx, const lab_constants *c, const uint32_t *phi, const uint32_t *pi2, uint32_t psi,
+                                  const uint32_t omega[LAB_JL_ROWS], uint32_t *phi_pp) {
+    CallScope cs(ctx);
+    if (!pi2) FAIL(LAB_ERR_PARAMS, "null pi2");
+    return aggregate_phi_host(ctx, c, phi, nullptr, pi2, psi, omega, phi_pp);
+}
+// rows [i0, i0 + ni) of h (default: all): Hhat / dH point at row 0 of the full R x R arrays
+static int d_h_gram(lab_ctx *ctx, const uint32_t *PFhat, const uint32_t *What, uint64_t N, uint64_t R, uint32_t *Hhat, uint32_t *dH,
+                    uint64_t i0 = 0, uint64_t ni = ~0ull) {
+    if (ni == ~0ull) ni = R;
+    if (!ni) return LAB_OK;
     // 2^-1 = 2^(Q-2) = 4096 (proofgen.rs:341-346)
-    LAUNCH(k_ip_hat, (unsigned)(R * R), 256, PFhat, (size_t)R, (size_t)1, What, (size_t)R, (size_t)1, (size_t)N, (size_t)R, 4096u, 1, Hhat);
-    return d_inv_hat(ctx, Hhat, dH, R * R);
+    LAUNCH(k_ip_hat, (unsigned)(ni * R), 256, PFhat, (size_t)R, (size_t)1, What, (size_t)R, (size_t)1, (size_t)N, (size_t)R, 4096u, 1, Hhat + i0 * R * 32, (size_t)i0);
+    return d_inv_hat(ctx, Hhat + i0 * R * 32, dH + i0 * R * 64, ni * R);
 }
 extern "C" int lab_h_gram(lab_ctx *ctx, const lab_constants *c, const uint32_t *phi_final, const uint32_t *S, uint32_t *H) {
     CallScope cs(ctx);
@@ -1065,9 +1212,10 @@ static int d_amortize(lab_ctx *ctx, const uint32_t *Chat, const uint32_t *What, 
     LAUNCH(k_amortize, grid_for(N, 8, ctx->sms * 16), 256, Chat, What, (size_t)N, (size_t)R, (size_t)i0, (size_t)ni, zhat);
     return d_inv_hat(ctx, zhat, dz, N);
 }
-extern "C" int lab_amortize_z(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, const uint32_t *ch, uint32_t *z) {
+extern "C" int lab_amortize_z_part(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, const uint32_t *ch, uint64_t i0, uint64_t ni, uint32_t *z) {
     CallScope cs(ctx);
     TRY(check_consts(ctx, c, false));
+    if (i0 + ni > c->R) FAIL(LAB_ERR_SHAPE, "witness range exceeds R");
     uint32_t *dS, *What, *dc, *Chat, *zhat, *dz;
     TRY(load_witness(ctx, c, S, &dS, &What));
     TRY(upload(ctx, ch, c->R * 64, &dc));
@@ -1075,9 +1223,13 @@ extern "C" int lab_amortize_z(lab_ctx *ctx, const lab_constants *c, const uint32
     TRY(arena_alloc(ctx, c->N * 32, &zhat));
     TRY(arena_alloc(ctx, c->N * 64, &dz));
     TRY(d_fwd_hat(ctx, dc, Chat, c->R, 0, 0));
-    TRY(d_amortize(ctx, Chat, What, c->N, c->R, 0, c->R, zhat, dz));
+    TRY(d_amortize(ctx, Chat, What, c->N, c->R, i0, ni, zhat, dz));
     TRY(download(ctx, z, dz, c->N * 64));
     return lab_sync(ctx);
+}
+extern "C" int lab_amortize_z(lab_ctx *ctx, const lab_constants *c, const uint32_t *S, const uint32_t *ch, uint32_t *z) {
+    if (!c) return LAB_ERR_PARAMS;
+    return lab_amortize_z_part(ctx, c, S, ch, 0, c->R, z);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1087,10 +1239,15 @@ static int prove_one(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_by
                      const lab_challenges *ch, lab_transcript *out) {
     const uint64_t R = c->R, N = c->N, K = c->KAPPA, K1 = c->KAPPA_1, K2 = c->KAPPA_2, ND = N * LAB_D;
     const uint64_t T1 = (uint64_t)c->T_1, T2 = (uint64_t)c->T_2;
-    if (!S || !st || !ch || !out || !st->phi || !st->a || !st->b || !ch->pi || !ch->omega || !ch->alpha || !ch->beta || !ch->c)
+    if (!S || !st || !ch || !out || !st->phi || !st->a || !st->b || (!ch->pi && !ch->pi2) || !ch->omega || !ch->alpha || !ch->beta || !ch->c)
         FAIL(LAB_ERR_PARAMS, "null argument");
     if (ch->n_attempts < 1) FAIL(LAB_ERR_PARAMS, "need at least one JL attempt");
     const LabSeed seed = make_seed(seed_bytes);
+    // Under a communicator the witness-vector stages are sharded too: this rank owns vectors [vi0, vi0 + vni) for S2 (rows of
+    // g), S4 (JL partial, int64 all-reduce), S5 (phi''_i, all-gather), S7 (rows of h) and S9 (z partial, int64 all-reduce then
+    // mod q).  Same rule as for rows: equal slices when the communicator size divides R, otherwise every rank does everything.
+    uint64_t vi0, vni;
+    const bool vsharded = shard_rows(ctx, R, &vi0, &vni);
     const uint32_t psi = ch->psi % LAB_Q;
     const double t_trace0 = now_us();
 
@@ -1126,7 +1283,11 @@ static int prove_one(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_by
             TRY(d_commit_inner(ctx, seed, What, N, R, x0, nx, dT, K, x0));
             if (sharded) TRY(allgather_rows(ctx, dT, R, K * 64, K, 64));
         }
-        TRY(d_gram(ctx, What, N, R, 0, R, Ghat, dG));                        // S2 (proofgen.rs:59-70)
+        TRY(d_gram(ctx, What, N, R, vi0, vni, Ghat + vi0 * R * 32, dG + vi0 * R * 64));   // S2 (proofgen.rs:59-70): this rank's rows of g
+        if (vsharded) {
+            TRY(allgather_bytes(ctx, Ghat, vni * R * 32 * sizeof(uint32_t)));
+            TRY(allgather_bytes(ctx, dG, vni * R * 64 * sizeof(uint32_t)));
+        }
         if (forked) CK(cudaEventRecord(ctx->ev_tg, ctx->stream));            // T and g are complete
         {   // S3 (proofgen.rs:101-153)
             uint64_t x0, nx;
@@ -1137,8 +1298,9 @@ static int prove_one(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_by
         if (forked) CK(cudaEventRecord(ctx->ev_join, ctx->stream));
         return LAB_OK;
     };
+    if (forked) TRY(ensure_stream2(ctx));
+    Stream2Guard s2guard(forked ? ctx->stream2 : nullptr);                   // joins strand (a) on every early return below
     if (forked) {
-        TRY(ensure_stream2(ctx));
         CK(cudaEventRecord(ctx->ev_fork, ctx->stream));                      // uploads and the transformed witness are enqueued
         CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
         struct StreamSwap {
@@ -1148,19 +1310,24 @@ static int prove_one(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_by
         ctx->stream = ctx->stream2;
         TRY(strand_a());
     }
-    // S4: JL with retries (proofgen.rs:161-186: initial attempt + at most 5 retries)
-    int8_t *dPi;
+    // S4: JL with retries (proofgen.rs:161-186: initial attempt + at most 5 retries).  Only the rows of this rank's vectors
+    // travel to the device: 2-bit packed when the caller has them packed, otherwise int8 entries packed on arrival.
+    uint32_t *dPi2;
+    int8_t *dPi8 = nullptr;
     unsigned long long *dp;
-    TRY(arena_alloc(ctx, R * LAB_JL_ROWS * ND, &dPi));
+    TRY(arena_alloc(ctx, vni * LAB_JL_ROWS * ND / 16, &dPi2));
+    if (!ch->pi2) TRY(arena_alloc(ctx, vni * LAB_JL_ROWS * ND, &dPi8));
     TRY(arena_alloc(ctx, (size_t)LAB_JL_ROWS, &dp));
     int att = 0, rejections = 0;
     for (;;) {
         if (att >= ch->n_attempts) FAIL(LAB_ERR_JL_REJECTED, "JL projection rejected and no further attempt supplied");
-        CK(cudaMemcpyAsync(dPi, ch->pi + (size_t)att * R * LAB_JL_ROWS * ND, R * LAB_JL_ROWS * ND, cudaMemcpyHostToDevice, ctx->stream));
-        TRY(d_jl(ctx, dPi, dS, ND, 0, R, dp));
+        const size_t first = ((size_t)att * R + vi0) * LAB_JL_ROWS * ND;         // first entry of this rank's rows in attempt `att`
+        TRY(upload_pi2(ctx, ch->pi2 ? nullptr : ch->pi + first, ch->pi2 ? ch->pi2 + first / 16 : nullptr, vni, ND, dPi2, dPi8));
+        TRY(d_jl(ctx, dPi2, dS, ND, vi0, vni, dp));
+        if (vsharded) TRY(allreduce_i64(ctx, reinterpret_cast<long long *>(dp), LAB_JL_ROWS));
         CK(cudaMemcpyAsync(out->projection_int, dp, LAB_JL_ROWS * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         TRY(lab_sync(ctx));
-        if (valid_projection(c, out->projection_int)) break;
+        if (valid_projection(c, out->projection_int)) break;                      // the same exact sums, hence the same decision, on every rank
         if (++rejections > 5) FAIL(LAB_ERR_JL_REJECTED, "failed JL... (proofgen.rs:175-176)");
         att++;
     }
@@ -1176,7 +1343,14 @@ static int prove_one(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_by
     TRY(arena_alloc(ctx, N * 32, &zhat));
     TRY(arena_alloc(ctx, N * 64, &dz));
     TRY(d_fwd_hat(ctx, dc, Chat, R, 0, 0));
-    TRY(d_amortize(ctx, Chat, What, N, R, 0, R, zhat, dz));
+    TRY(d_amortize(ctx, Chat, What, N, R, vi0, vni, zhat, dz));
+    if (vsharded) {          // canonical partials -> int64, ncclSum over the ranks, mod q
+        long long *z64;
+        TRY(arena_alloc(ctx, N * 64, &z64));
+        LAUNCH(k_widen_u32_i64, grid_for(N * 64, 1024, ctx->sms * 8), 256, dz, (size_t)(N * 64), z64);
+        TRY(allreduce_i64(ctx, z64, N * 64));
+        LAUNCH(k_modq_i64_u32, grid_for(N * 64, 1024, ctx->sms * 8), 256, z64, (size_t)(N * 64), dz);
+    }
     // (all device->host copies are issued at the very end: a copy into pageable host memory blocks the calling thread
     //  until the stream reaches it, which would serialise the enqueueing of the remaining stages behind u_1)
     // statement / challenge operands of S5-S8
@@ -1209,7 +1383,8 @@ static int prove_one(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_by
     unsigned long long hnorm = 0;
     {
         // S5: aggregation (proofgen.rs:189-289), upper_bound = 1
-        TRY(d_aggregate_phi(ctx, c, dphi, dPi, psi, dom, dpp));
+        TRY(d_aggregate_phi(ctx, c, dphi + vi0 * ND, dPi2, psi, dom, dpp + vi0 * ND, vni));      // phi''_i of this rank's vectors
+        if (vsharded) TRY(allgather_bytes(ctx, dpp, vni * ND * sizeof(uint32_t)));
         TRY(d_fwd_hat(ctx, dpp, PPhat, R * N, N, R));
         LAUNCH(k_ip_hat, (unsigned)R, 256, PPhat, (size_t)R, (size_t)1, What, (size_t)R, (size_t)1, (size_t)N, (size_t)0, 1u, 2, diag);
         LAUNCH(k_sum_hats, 1, 32, diag, (size_t)R, (size_t)1, sums + 32, (size_t)1);
@@ -1218,7 +1393,8 @@ static int prove_one(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_by
         LAUNCH(k_pointwise, grid_for(R * N * 32, 256, ctx->sms * 16), 256, ABhat, (size_t)1, (size_t)0, Phihat, ABhat + 32, (size_t)1, (size_t)0, PPhat,
                PFhat, (size_t)(R * N));
         // S7: h (proofgen.rs:320-358)
-        TRY(d_h_gram(ctx, PFhat, What, N, R, Hhat, dH));
+        TRY(d_h_gram(ctx, PFhat, What, N, R, Hhat, dH, vi0, vni));                                  // this rank's rows of h
+        if (vsharded) TRY(allgather_bytes(ctx, dH, vni * R * 64 * sizeof(uint32_t)));
         // S8: u_2 (proofgen.rs:364-378)
         {
             uint64_t x0, nx;
@@ -1234,6 +1410,7 @@ static int prove_one(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_by
         LAUNCH(k_digit_norm_sq, grid_for(R * R * 64, 2048, ctx->sms * 8), 256, dH, (size_t)(R * R * 64), (uint32_t)c->B_1, (int)T1, dnorm);
         if (out->phi_final) TRY(d_inv_hat(ctx, PFhat, pf_tmp, R * N));
         if (u1_forked) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));     // join the u_1 stream
+        s2guard.disarm();                                                          // the main stream now waits for strand (a)
         TRACE("all kernels enqueued");
         // ---- downloads ----
         TRY(download(ctx, out->u_1, du1, K1 * 64));
@@ -1306,8 +1483,8 @@ extern "C" int lab_verify(lab_ctx *ctx, const lab_constants *c, const uint8_t se
         for (uint64_t j = 0; j < R; j++)
             if (std::memcmp(tr->h + (i * R + j) * 64, tr->h + (j * R + i) * 64, 256)) { fc = 9; break; }
     // uploads
-    uint32_t *dz, *dT, *dG, *dH, *du1, *du2, *dphi, *dom, *da, *dsmall, *dc;
-    int8_t *dPi;
+    uint32_t *dz, *dT, *dG, *dH, *du1, *du2, *dphi, *dom, *da, *dsmall, *dc, *dPi2;
+    int8_t *dPi8 = nullptr;
     TRY(upload(ctx, tr->z, N * 64, &dz));
     TRY(upload(ctx, tr->t, R * K * 64, &dT));
     TRY(upload(ctx, tr->g, R * R * 64, &dG));
@@ -1318,7 +1495,13 @@ extern "C" int lab_verify(lab_ctx *ctx, const lab_constants *c, const uint8_t se
     TRY(upload(ctx, ch->omega, (size_t)LAB_JL_ROWS, &dom));
     TRY(upload(ctx, st->a, R * R * 64, &da));
     TRY(upload(ctx, ch->c, R * 64, &dc));
-    TRY(upload(ctx, ch->pi + (size_t)tr->jl_attempt * R * LAB_JL_ROWS * ND, R * LAB_JL_ROWS * ND, &dPi));
+    if (!ch->pi && !ch->pi2) FAIL(LAB_ERR_PARAMS, "no JL matrix given (pi or pi2)");
+    TRY(arena_alloc(ctx, R * LAB_JL_ROWS * ND / 16, &dPi2));
+    if (!ch->pi2) TRY(arena_alloc(ctx, R * LAB_JL_ROWS * ND, &dPi8));
+    {
+        const size_t first = (size_t)tr->jl_attempt * R * LAB_JL_ROWS * ND;
+        TRY(upload_pi2(ctx, ch->pi2 ? nullptr : ch->pi + first, ch->pi2 ? ch->pi2 + first / 16 : nullptr, R, ND, dPi2, dPi8));
+    }
     uint32_t small[4 * 64];                                     // alpha, beta, b, b''
     std::memcpy(small, ch->alpha, 256); std::memcpy(small + 64, ch->beta, 256);
     std::memcpy(small + 128, st->b, 256); std::memcpy(small + 192, tr->b_prime_prime, 256);
@@ -1359,7 +1542,7 @@ extern "C" int lab_verify(lab_ctx *ctx, const lab_constants *c, const uint8_t se
     TRY(d_fwd_hat(ctx, dsmall, SMhat, 4, 0, 0));
     const uint32_t *alpha_h = SMhat, *beta_h = SMhat + 32, *b_h = SMhat + 64, *bpp_h = SMhat + 96;
     // lines 3-6: phi'' and phi = alpha phi + beta phi''
-    TRY(d_aggregate_phi(ctx, c, dphi, dPi, psi, dom, dpp));
+    TRY(d_aggregate_phi(ctx, c, dphi, dPi2, psi, dom, dpp));
     TRY(d_fwd_hat(ctx, dphi, Phihat, R * N, N, R));
     TRY(d_fwd_hat(ctx, dpp, PPhat, R * N, N, R));
     LAUNCH(k_pointwise, grid_for(R * N * 32, 256, ctx->sms * 16), 256, alpha_h, (size_t)1, (size_t)0, Phihat, beta_h, (size_t)1, (size_t)0, PPhat, PFhat,
@@ -1555,18 +1738,27 @@ struct BinWriter {
 }  // namespace
 extern "C" int lab_transcript_bincode(const lab_constants *c, const lab_transcript *tr, const lab_challenges *ch, uint8_t *out, size_t cap, size_t *size) {
     if (!c || !tr || !ch || !size) return LAB_ERR_PARAMS;
-    if (!tr->u_1 || !tr->projection || !tr->b_prime_prime || !tr->u_2 || !tr->z || !tr->t || !tr->g || !tr->h || !ch->pi || !ch->omega || !ch->alpha ||
+    if (!tr->u_1 || !tr->projection || !tr->b_prime_prime || !tr->u_2 || !tr->z || !tr->t || !tr->g || !tr->h || (!ch->pi && !ch->pi2) || !ch->omega || !ch->alpha ||
         !ch->beta || !ch->c || tr->jl_attempt < 0 || tr->jl_attempt >= ch->n_attempts)
         return LAB_ERR_PARAMS;
     const uint64_t R = c->R, N = c->N, K = c->KAPPA, ND = N * LAB_D;
     BinWriter w{out, out ? cap : 0};
     w.vec_rq(tr->u_1, c->KAPPA_1);                                                   // u_1: Vec<Rq>
     w.u64(R);                                                                        // pi_i_all: Vec<Array2<Zq>>
-    const int8_t *pi = ch->pi + (size_t)tr->jl_attempt * R * LAB_JL_ROWS * ND;
+    const size_t pi_first = (size_t)tr->jl_attempt * R * LAB_JL_ROWS * ND;
     for (uint64_t i = 0; i < R; i++) {
         w.array2_header(LAB_JL_ROWS, ND);
-        const int8_t *p = pi + i * LAB_JL_ROWS * ND;
-        for (uint64_t e = 0; e < LAB_JL_ROWS * ND; e++) w.zq(p[e] < 0 ? LAB_Q - 1 : (uint32_t)p[e]);
+        if (ch->pi2) {                                   // packed: bit k / bit 16 + k of word e / 16 (lab_jl.cuh)
+            const uint32_t *p2 = ch->pi2 + (pi_first + i * LAB_JL_ROWS * ND) / 16;
+            for (uint64_t e = 0; e < LAB_JL_ROWS * ND; e++) {
+                const uint32_t wd = p2[e >> 4];
+                const unsigned k = (unsigned)(e & 15);
+                w.zq((wd >> k & 1u) ? 1u : ((wd >> (16 + k) & 1u) ? LAB_Q - 1 : 0u));
+            }
+        } else {
+            const int8_t *p = ch->pi + pi_first + i * LAB_JL_ROWS * ND;
+            for (uint64_t e = 0; e < LAB_JL_ROWS * ND; e++) w.zq(p[e] < 0 ? LAB_Q - 1 : (uint32_t)p[e]);
+        }
     }
     w.u64(LAB_JL_ROWS);                                                              // projection: Vec<Zq>
     for (int j = 0; j < LAB_JL_ROWS; j++) w.zq(tr->projection[j]);
@@ -1714,10 +1906,135 @@ extern "C" int lab_bench_alu_peak(lab_ctx *ctx, double *lane_ops_per_s) {
     *lane_ops_per_s = best;
     return LAB_OK;
 }
+extern "C" int lab_jl_project2_dev(lab_ctx *ctx, const uint32_t *pi2_dev, uint64_t i0, uint64_t ni, int64_t *p_dev) {
+    NEED_WITNESS();
+    if (i0 + ni > ctx->wc.R) FAIL(LAB_ERR_SHAPE, "witness range exceeds R");
+    return d_jl(ctx, pi2_dev, ctx->S_dev, ctx->wc.N * LAB_D, i0, ni, reinterpret_cast<unsigned long long *>(p_dev));
+}
 extern "C" int lab_jl_project_dev(lab_ctx *ctx, const int8_t *pi_dev, uint64_t i0, uint64_t ni, int64_t *p_dev) {
     NEED_WITNESS();
     if (i0 + ni > ctx->wc.R) FAIL(LAB_ERR_SHAPE, "witness range exceeds R");
-    return d_jl(ctx, pi_dev, ctx->S_dev, ctx->wc.N * LAB_D, i0, ni, reinterpret_cast<unsigned long long *>(p_dev));
+    arena_reset(ctx);
+    const size_t entries = ni * LAB_JL_ROWS * ctx->wc.N * LAB_D;
+    uint32_t *dPi2;
+    TRY(arena_alloc(ctx, entries / 16, &dPi2));
+    TRY(d_pack_pi(ctx, pi_dev, entries, dPi2));                 // int8 entries are packed first: one compute path
+    return d_jl(ctx, dPi2, ctx->S_dev, ctx->wc.N * LAB_D, i0, ni, reinterpret_cast<unsigned long long *>(p_dev));
+}
+extern "C" int lab_pi_pack_dev(lab_ctx *ctx, const int8_t *pi_dev, size_t n_entries, uint32_t *pi2_dev) {
+    if (n_entries % 16) FAIL(LAB_ERR_PARAMS, "n_entries must be a multiple of 16");
+    return d_pack_pi(ctx, pi_dev, n_entries, pi2_dev);
+}
+extern "C" int lab_pi_pack(const int8_t *pi, size_t n_entries, uint32_t *pi2) {
+    if (!pi || !pi2 || n_entries % 16) return LAB_ERR_PARAMS;
+    for (size_t w = 0; w < n_entries / 16; w++) {
+        uint32_t word = 0;
+        for (int k = 0; k < 16; k++) {
+            const int8_t e = pi[w * 16 + k];
+            if (e == 1) word |= 1u << k;
+            else if (e == -1) word |= 1u << (16 + k);
+            else if (e != 0) return LAB_ERR_PARAMS;              // entries are in {-1, 0, 1} (verification.rs:555-557)
+        }
+        pi2[w] = word;
+    }
+    return LAB_OK;
+}
+extern "C" int lab_pi_unpack(const uint32_t *pi2, size_t n_entries, int8_t *pi) {
+    if (!pi || !pi2 || n_entries % 16) return LAB_ERR_PARAMS;
+    for (size_t e = 0; e < n_entries; e++) {
+        const uint32_t wd = pi2[e >> 4];
+        const unsigned k = (unsigned)(e & 15);
+        pi[e] = (wd >> k & 1u) ? 1 : ((wd >> (16 + k) & 1u) ? -1 : 0);
+    }
+    return LAB_OK;
+}
+extern "C" int lab_synth_pi2_dev(lab_ctx *ctx, uint64_t seed, uint64_t attempt, uint64_t first_entry, size_t total, uint32_t *out_dev) {
+    if (!total) return LAB_OK;
+    if (first_entry % 32 || total % 32) FAIL(LAB_ERR_PARAMS, "first_entry and total must be multiples of 32");
+    const uint64_t base = prg_base(seed, 5 + (attempt << 8)) + (first_entry / 32) * 0x9E3779B97F4A7C15ull;
+    LAUNCH(k_synth_pi2, grid_for(total / 32, 256, ctx->sms * 16), 256, base, total / 32, out_dev);
+    return LAB_OK;
+}
+// ---- stage calls sharded over the communicator ----
+extern "C" int lab_jl_project_sharded_dev(lab_ctx *ctx, const uint32_t *pi2_part_dev, int64_t *p_dev) {
+    NEED_WITNESS();
+    uint64_t i0, ni;
+    lab_comm_shard(ctx, ctx->wc.R, &i0, &ni);
+    TRY(d_jl(ctx, pi2_part_dev, ctx->S_dev, ctx->wc.N * LAB_D, i0, ni, reinterpret_cast<unsigned long long *>(p_dev)));
+    return allreduce_i64(ctx, reinterpret_cast<long long *>(p_dev), LAB_JL_ROWS);
+}
+extern "C" int lab_amortize_z_sharded_dev(lab_ctx *ctx, const uint32_t *ch_dev, uint32_t *z_dev) {
+    NEED_WITNESS();
+    uint64_t i0, ni;
+    lab_comm_shard(ctx, ctx->wc.R, &i0, &ni);
+    arena_reset(ctx);
+    const uint64_t N = ctx->wc.N;
+    uint32_t *Chat, *zhat;
+    TRY(arena_alloc(ctx, ctx->wc.R * 32, &Chat));
+    TRY(arena_alloc(ctx, N * 32, &zhat));
+    TRY(d_fwd_hat(ctx, ch_dev, Chat, ctx->wc.R, 0, 0));
+    TRY(d_amortize(ctx, Chat, ctx->What, N, ctx->wc.R, i0, ni, zhat, z_dev));
+    if (ctx->comm && ctx->world > 1) {
+        long long *z64;
+        TRY(arena_alloc(ctx, N * 64, &z64));
+        LAUNCH(k_widen_u32_i64, grid_for(N * 64, 1024, ctx->sms * 8), 256, z_dev, (size_t)(N * 64), z64);
+        TRY(allreduce_i64(ctx, z64, N * 64));
+        LAUNCH(k_modq_i64_u32, grid_for(N * 64, 1024, ctx->sms * 8), 256, z64, (size_t)(N * 64), z_dev);
+    }
+    return LAB_OK;
+}
+extern "C" int lab_gram_sharded_dev(lab_ctx *ctx, uint32_t *G_dev) {
+    NEED_WITNESS();
+    const uint64_t R = ctx->wc.R;
+    uint64_t i0, ni;
+    lab_comm_shard(ctx, R, &i0, &ni);
+    arena_reset(ctx);
+    uint32_t *Ghat;
+    TRY(arena_alloc(ctx, std::max<uint64_t>(ni, 1) * R * 32, &Ghat));
+    const bool multi = ctx->comm && ctx->world > 1;
+    if (multi && R % (uint64_t)ctx->world == 0) {        // equal slices: in-place all-gather
+        TRY(d_gram(ctx, ctx->What, ctx->wc.N, R, i0, ni, Ghat, G_dev + i0 * R * 64));
+        return allgather_bytes(ctx, G_dev, ni * R * 64 * sizeof(uint32_t));
+    }
+    if (multi) {                                          // ragged split: every rank fills its rows of a zeroed buffer; the int64 sum is the union
+        long long *g64;
+        TRY(arena_alloc(ctx, R * R * 64, &g64));
+        CK(cudaMemsetAsync(G_dev, 0, R * R * 64 * sizeof(uint32_t), ctx->stream));
+        TRY(d_gram(ctx, ctx->What, ctx->wc.N, R, i0, ni, Ghat, G_dev + i0 * R * 64));
+        LAUNCH(k_widen_u32_i64, grid_for(R * R * 64, 1024, ctx->sms * 8), 256, G_dev, (size_t)(R * R * 64), g64);
+        TRY(allreduce_i64(ctx, g64, R * R * 64));
+        LAUNCH(k_modq_i64_u32, grid_for(R * R * 64, 1024, ctx->sms * 8), 256, g64, (size_t)(R * R * 64), G_dev);
+        return LAB_OK;
+    }
+    return d_gram(ctx, ctx->What, ctx->wc.N, R, 0, R, Ghat, G_dev);
+}
+// ---- host-buffer forms over a resident witness ----
+extern "C" int lab_witness_load(lab_ctx *ctx, const lab_constants *c, const uint32_t *S_host) {
+    cudaSetDevice(ctx->device);
+    TRY(check_consts(ctx, c, false));
+    if (!S_host) FAIL(LAB_ERR_PARAMS, "null witness");
+    const size_t bytes = c->R * c->N * 64 * sizeof(uint32_t);
+    if (bytes > ctx->S_own_bytes) {
+        if (ctx->S_own) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->S_own); }
+        ctx->S_own = nullptr; ctx->S_own_bytes = 0;
+        CK(cudaMalloc(&ctx->S_own, bytes));
+        ctx->S_own_bytes = bytes;
+    }
+    CK(cudaMemcpyAsync(ctx->S_own, S_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return lab_witness_load_dev(ctx, c, ctx->S_own);
+}
+extern "C" int lab_commit_inner_resident(lab_ctx *ctx, const uint8_t seed[32], uint64_t row0, uint64_t nrows, uint32_t *T_host) {
+    NEED_WITNESS();
+    if (row0 + nrows > ctx->wc.KAPPA) FAIL(LAB_ERR_SHAPE, "row range exceeds KAPPA");
+    if (!nrows) return LAB_OK;
+    if (!T_host) FAIL(LAB_ERR_PARAMS, "null destination");
+    arena_reset(ctx);
+    uint32_t *dT;
+    TRY(arena_alloc(ctx, ctx->wc.R * nrows * 64, &dT));
+    bool host_done = false;
+    TRY(d_commit_inner(ctx, make_seed(seed), ctx->What, ctx->wc.N, ctx->wc.R, row0, nrows, dT, 0, 0, T_host, &host_done));
+    if (!host_done) TRY(download(ctx, T_host, dT, ctx->wc.R * nrows * 64));
+    return lab_sync(ctx);
 }
 extern "C" int lab_amortize_z_dev(lab_ctx *ctx, const uint32_t *ch_dev, uint64_t i0, uint64_t ni, uint32_t *z_dev) {
     NEED_WITNESS();

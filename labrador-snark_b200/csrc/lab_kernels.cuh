@@ -12,7 +12,7 @@
 //                                                      TMA-fed IMAD consumers; shapes < 2^22 polynomials  INT32 ALU
 //   k_crs_matvec<FILL_CACHE> + k_finish_rows (K_MV)    CRS gen + warp NTT + mat-vec (optionally write-through) INT32 ALU
 //   k_cached_matvec                                    the same mat-vec from the CRS cache     HBM
-//   k_fwd_hat / k_inv_hat / k_decomp_fwd / k_ip_hat / k_pointwise / k_jl / k_piT_omega / ...   HBM / L2
+//   k_fwd_hat / k_inv_hat / k_decomp_fwd / k_ip_hat / k_pointwise / ...   HBM / L2  (k_jl2, k_piT_omega2: lab_jl.cuh)
 // lab_umma.cuh: k_gen_planes (ChaCha20 -> int8 limb planes, INT32 ALU) + k_umma_commit (tcgen05 contraction, HBM) --
 // the large-shape inner commitment; lab_gen.cuh: device-side challenge / witness / statement generation.
 #pragma once
@@ -276,11 +276,11 @@ __global__ void k_sigma_inv(const uint32_t *__restrict__ in, uint32_t *__restric
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_ip_hat(const uint32_t *__restrict__ X, size_t x_sn, size_t x_si,
                                                 const uint32_t *__restrict__ Y, size_t y_sn, size_t y_si,
-                                                size_t len, size_t nby, uint32_t scale, int mode, uint32_t *__restrict__ out) {
+                                                size_t len, size_t nby, uint32_t scale, int mode, uint32_t *__restrict__ out, size_t xi0 = 0) {
     __shared__ uint32_t sre[8][32], sim[8][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const size_t b = blockIdx.x;
-    const size_t xi = mode == 2 ? b : b / nby, yi = mode == 2 ? b : b % nby;
+    const size_t xi = mode == 2 ? b : b / nby + xi0, yi = mode == 2 ? b : b % nby;       // xi0: first row of a row shard (out stays local)
     uint32_t accr = 0, acci = 0;
     int pending = 0;
     for (size_t n = w; n < len; n += 8) {
@@ -818,65 +818,8 @@ __global__ void __launch_bounds__(256) k_finish_rows(const uint32_t *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
-// JL projection p_j = sum_i sum_c Pi_i[j][c] * s_i[c], exact (proofgen.rs:429-457, util.rs:511-526).
-// CTA = one chunk of JL_CH coefficients of one witness vector x all 256 rows.  The witness chunk is
-// staged in shared memory once; warp w streams rows j = w, w+8, ... with 16-byte coalesced loads of
-// the int8 matrix (HBM bound on Pi), int32 partials per lane, shuffle reduction, int64 atomics.
+// JL projection and Pi^T omega: lab_jl.cuh (2-bit packed matrices, table-lookup projection)
 // ------------------------------------------------------------------------------------------------
-constexpr int JL_CH = 4096;
-
-__global__ void __launch_bounds__(256) k_jl(const int8_t *__restrict__ Pi, const uint32_t *__restrict__ S, size_t ND, size_t i0,
-                                            unsigned long long *__restrict__ p) {
-    __shared__ uint32_t ssm[JL_CH];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const size_t chunks_per_i = (ND + JL_CH - 1) / JL_CH;
-    const size_t i = i0 + blockIdx.x / chunks_per_i;            // absolute witness vector
-    const size_t li = blockIdx.x / chunks_per_i;                // index into Pi (which starts at i0)
-    const size_t c0 = (blockIdx.x % chunks_per_i) * JL_CH;
-    const size_t len = min((size_t)JL_CH, ND - c0);
-    for (size_t t = threadIdx.x; t < JL_CH; t += 256) ssm[t] = t < len ? S[i * ND + c0 + t] : 0u;
-    __syncthreads();
-    for (int j = w; j < 256; j += 8) {
-        const int8_t *row = Pi + (li * 256 + (size_t)j) * ND + c0;
-        int acc = 0;
-        for (size_t t = (size_t)lane * 16; t < len; t += 512) {
-            if (t + 16 <= len && ((reinterpret_cast<uintptr_t>(row + t) & 15) == 0)) {
-                int4 v = __ldg(reinterpret_cast<const int4 *>(row + t));
-                const int words[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        int tri = (int)(signed char)((words[q] >> (8 * e)) & 0xff);
-                        acc += tri * (int)ssm[t + q * 4 + e];
-                    }
-            } else {
-                for (size_t e = t; e < min(t + 16, len); e++) acc += (int)row[e] * (int)ssm[e];
-            }
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0 && acc) atomicAdd(p + j, (unsigned long long)(long long)acc);
-    }
-}
-
-// v[i][c] = sum_j omega_j * Pi_i[j][c] mod Q   (first half of phi'', proofgen.rs:244-253)
-__global__ void __launch_bounds__(256) k_piT_omega(const int8_t *__restrict__ Pi, const uint32_t *__restrict__ omega, size_t total /* R*ND */,
-                                                   size_t ND, uint32_t *__restrict__ v) {
-    __shared__ int som[256];
-    som[threadIdx.x] = (int)lab_canon(omega[threadIdx.x]);
-    __syncthreads();
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const size_t i = idx / ND, c = idx % ND;
-    const int8_t *col = Pi + i * 256 * ND + c;
-    int acc = 0;
-#pragma unroll 8
-    for (int j = 0; j < 256; j++) acc += (int)col[(size_t)j * ND] * som[j];
-    // |acc| <= 256 * 8190 < 2^21; bring into [0, Q)
-    int m = acc % (int)LABQ;
-    v[idx] = (uint32_t)(m < 0 ? m + (int)LABQ : m);
-}
 // phi''[i][n][d] = psi * phi[i][n][d] + sigma_inv(v_poly)[d]   (proofgen.rs:234-255)
 __global__ void k_phi_pp(const uint32_t *__restrict__ phi, const uint32_t *__restrict__ v, uint32_t psi, size_t n_coeffs, uint32_t *__restrict__ out) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -39,7 +39,8 @@ class CState(C.Structure):
 
 class CChallenges(C.Structure):
     _fields_ = [("pi", C.c_void_p), ("n_attempts", C.c_int), ("psi", C.c_uint32),
-                ("omega", C.c_void_p), ("alpha", C.c_void_p), ("beta", C.c_void_p), ("c", C.c_void_p)]
+                ("omega", C.c_void_p), ("alpha", C.c_void_p), ("beta", C.c_void_p), ("c", C.c_void_p),
+                ("pi2", C.c_void_p)]          # optional 2-bit packed twin of pi (include/labrador_b200.h)
 
 
 class CTranscript(C.Structure):
@@ -63,6 +64,10 @@ SYMBOLS = [
     "lab_synth_zq_dev", "lab_synth_pi_dev", "lab_bench_alu_peak",
     "lab_comm_unique_id", "lab_comm_init", "lab_comm_destroy", "lab_transcript_bincode", "lab_crs_cache_configure", "lab_crs_cache_stats",
     "lab_sample_challenge_polys_dev", "lab_generate_witness_dev", "lab_generate_state_dev",
+    "lab_comm_allreduce_i64_dev", "lab_comm_allgather_dev", "lab_comm_rank", "lab_comm_shard",
+    "lab_pi_pack", "lab_pi_unpack", "lab_pi_pack_dev", "lab_jl_project2", "lab_jl_project2_part", "lab_aggregate_phi2",
+    "lab_gram_part", "lab_amortize_z_part", "lab_jl_project2_dev", "lab_jl_project_sharded_dev", "lab_amortize_z_sharded_dev",
+    "lab_gram_sharded_dev", "lab_witness_load", "lab_commit_inner_resident", "lab_synth_pi2_dev",
 ]
 
 _lib = None

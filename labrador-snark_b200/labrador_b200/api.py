@@ -22,6 +22,47 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def pack_pi(pi):
+    """int8 JL entries {-1,0,1} -> 2-bit packed words (bit k = +1, bit 16 + k = -1 of the word of 16 entries); same leading
+    shape, last axis / 16.  Host-side marshalling (lab_pi_pack)."""
+    pi = np.ascontiguousarray(pi, dtype=np.int8)
+    if pi.shape[-1] % 16:
+        raise ValueError("row length must be a multiple of 16")
+    out = np.empty(pi.shape[:-1] + (pi.shape[-1] // 16,), np.uint32)
+    rc = _lib.lib().lab_pi_pack(_p(pi), C.c_size_t(pi.size), _p(out))
+    if rc != 0:
+        raise LabError(rc, "lab_pi_pack: entries must be in {-1,0,1}")
+    return out
+
+
+def unpack_pi(pi2):
+    pi2 = np.ascontiguousarray(pi2, dtype=np.uint32)
+    out = np.empty(pi2.shape[:-1] + (pi2.shape[-1] * 16,), np.int8)
+    rc = _lib.lib().lab_pi_unpack(_p(pi2), C.c_size_t(out.size), _p(out))
+    if rc != 0:
+        raise LabError(rc, "lab_pi_unpack failed")
+    return out
+
+
+def _chal(ch, keep):
+    """CChallenges from a challenges dict; uses ch["pi2"] (packed) when present, else ch["pi"] (int8)."""
+    pi = pi2 = None
+    if ch.get("pi2") is not None:
+        pi2 = np.ascontiguousarray(ch["pi2"], dtype=np.uint32)
+        if pi2.ndim == 3:
+            pi2 = pi2[None]
+        n_att = pi2.shape[0]
+    if ch.get("pi") is not None and pi2 is None:
+        pi = np.ascontiguousarray(ch["pi"], dtype=np.int8)
+        if pi.ndim == 3:
+            pi = pi[None]
+        n_att = pi.shape[0]
+    omega, alpha, beta, cc = _u32(ch["omega"]), _u32(ch["alpha"]), _u32(ch["beta"]), _u32(ch["c"])
+    keep.extend([pi, pi2, omega, alpha, beta, cc])
+    return _lib.CChallenges(_p(pi) if pi is not None else None, n_att, int(ch["psi"]), _p(omega), _p(alpha), _p(beta), _p(cc),
+                            _p(pi2) if pi2 is not None else None)
+
+
 def _seed_buf(seed):
     s = np.frombuffer(bytes(seed), dtype=np.uint8).copy()
     if s.size != 32:
@@ -199,6 +240,41 @@ class Context:
     def jl_project_dev(self, dpi, i0, ni, dp):
         self._ck(self.L.lab_jl_project_dev(self._h, C.c_void_p(dpi), C.c_uint64(i0), C.c_uint64(ni), C.c_void_p(dp)))
 
+    def jl_project2_dev(self, dpi2, i0, ni, dp):
+        self._ck(self.L.lab_jl_project2_dev(self._h, C.c_void_p(dpi2), C.c_uint64(i0), C.c_uint64(ni), C.c_void_p(dp)))
+
+    def pi_pack_dev(self, dpi, n_entries, dpi2):
+        self._ck(self.L.lab_pi_pack_dev(self._h, C.c_void_p(dpi), C.c_size_t(n_entries), C.c_void_p(dpi2)))
+
+    def synth_pi2_dev(self, seed, attempt, first_entry, total, dout):
+        self._ck(self.L.lab_synth_pi2_dev(self._h, C.c_uint64(seed), C.c_uint64(attempt), C.c_uint64(first_entry), C.c_size_t(total), C.c_void_p(dout)))
+
+    # ---- stage calls sharded over the library's communicator (all ranks call them) ----
+    def comm_shard(self, total):
+        x0, nx = C.c_uint64(0), C.c_uint64(0)
+        self._ck(self.L.lab_comm_shard(self._h, C.c_uint64(total), C.byref(x0), C.byref(nx)))
+        return x0.value, nx.value
+
+    def comm_allreduce_i64_dev(self, dbuf, n):
+        self._ck(self.L.lab_comm_allreduce_i64_dev(self._h, C.c_void_p(dbuf), C.c_size_t(n)))
+
+    def comm_allgather_dev(self, dbuf, bytes_per_rank):
+        self._ck(self.L.lab_comm_allgather_dev(self._h, C.c_void_p(dbuf), C.c_size_t(bytes_per_rank)))
+
+    def jl_project_sharded_dev(self, dpi2_part, dp):
+        self._ck(self.L.lab_jl_project_sharded_dev(self._h, C.c_void_p(dpi2_part), C.c_void_p(dp)))
+
+    def amortize_z_sharded_dev(self, dch, dz):
+        self._ck(self.L.lab_amortize_z_sharded_dev(self._h, C.c_void_p(dch), C.c_void_p(dz)))
+
+    def gram_sharded_dev(self, dG):
+        self._ck(self.L.lab_gram_sharded_dev(self._h, C.c_void_p(dG)))
+
+    def witness_load(self, c, S):
+        S = _u32(S)
+        self._ck(self.L.lab_witness_load(self._h, C.byref(c), _p(S)))
+        self.sync()
+
     def amortize_z_dev(self, dch, i0, ni, dz):
         self._ck(self.L.lab_amortize_z_dev(self._h, C.c_void_p(dch), C.c_uint64(i0), C.c_uint64(ni), C.c_void_p(dz)))
 
@@ -302,6 +378,40 @@ class Context:
         self._ck(self.L.lab_jl_project(self._h, C.byref(c), _p(S), _p(pi), _p(p), C.byref(acc)))
         return p, bool(acc.value)
 
+    def jl_project2(self, c, S, pi2):
+        S = _u32(S)
+        pi2 = np.ascontiguousarray(pi2, dtype=np.uint32)
+        p = np.empty(JL_ROWS, np.int64)
+        acc = C.c_int(0)
+        self._ck(self.L.lab_jl_project2(self._h, C.byref(c), _p(S), _p(pi2), _p(p), C.byref(acc)))
+        return p, bool(acc.value)
+
+    def jl_project2_part(self, c, S, pi2_part, i0, ni):
+        S = _u32(S)
+        pi2_part = np.ascontiguousarray(pi2_part, dtype=np.uint32)
+        p = np.empty(JL_ROWS, np.int64)
+        self._ck(self.L.lab_jl_project2_part(self._h, C.byref(c), _p(S), _p(pi2_part), C.c_uint64(i0), C.c_uint64(ni), _p(p)))
+        return p
+
+    def aggregate_phi2(self, c, phi, pi2, psi, omega):
+        phi, omega = _u32(phi), _u32(omega)
+        pi2 = np.ascontiguousarray(pi2, dtype=np.uint32)
+        out = np.empty((c.R, c.N, D), np.uint32)
+        self._ck(self.L.lab_aggregate_phi2(self._h, C.byref(c), _p(phi), _p(pi2), C.c_uint32(psi), _p(omega), _p(out)))
+        return out
+
+    def gram_part(self, c, S, i0, ni):
+        S = _u32(S)
+        G = np.empty((ni, c.R, D), np.uint32)
+        self._ck(self.L.lab_gram_part(self._h, C.byref(c), _p(S), C.c_uint64(i0), C.c_uint64(ni), _p(G)))
+        return G
+
+    def amortize_z_part(self, c, S, ch, i0, ni):
+        S, ch = _u32(S), _u32(ch)
+        z = np.empty((c.N, D), np.uint32)
+        self._ck(self.L.lab_amortize_z_part(self._h, C.byref(c), _p(S), _p(ch), C.c_uint64(i0), C.c_uint64(ni), _p(z)))
+        return z
+
     def jl_project_part(self, c, S, pi_part, i0, ni):
         S = _u32(S)
         pi_part = np.ascontiguousarray(pi_part, dtype=np.int8)
@@ -346,14 +456,11 @@ class Context:
         """tr: dict with u_1, projection_int, projection, b_prime_prime, u_2, z, t, g, h, jl_attempt (oracle layout).
         Returns (accepted, failed_check, norm_sum) like the reference's Verifier::verify (verification.rs:25-438)."""
         phi, a, b = _u32(phi), _u32(a), _u32(b)
-        pi = np.ascontiguousarray(ch["pi"], dtype=np.int8)
-        if pi.ndim == 3:
-            pi = pi[None]
-        omega, alpha, beta, cc = _u32(ch["omega"]), _u32(ch["alpha"]), _u32(ch["beta"]), _u32(ch["c"])
+        alive = []
+        cch = _chal(ch, alive)
         keep = {k: _u32(tr[k]) for k in ("u_1", "projection", "b_prime_prime", "u_2", "z", "t", "g", "h")}
         pint = np.ascontiguousarray(tr["projection_int"], dtype=np.int64)
         cst = _lib.CState(_p(phi), _p(a), _p(b))
-        cch = _lib.CChallenges(_p(pi), pi.shape[0], int(ch["psi"]), _p(omega), _p(alpha), _p(beta), _p(cc))
         ctr = _lib.CTranscript(_p(keep["u_1"]), int(tr.get("jl_attempt", 0)), _p(pint), _p(keep["projection"]), _p(keep["b_prime_prime"]),
                                _p(keep["u_2"]), _p(keep["z"]), _p(keep["t"]), _p(keep["g"]), _p(keep["h"]), None, 0)
         acc, fc, ns = C.c_int(0), C.c_int(0), C.c_uint64(0)
@@ -373,13 +480,10 @@ class Context:
         keep, outs = [], []
         for i in range(B):
             ch = challenges[i]
-            pi = np.ascontiguousarray(ch["pi"], dtype=np.int8)
-            if pi.ndim == 3:
-                pi = pi[None]
-            arrs = [pi, _u32(ch["omega"]), _u32(ch["alpha"]), _u32(ch["beta"]), _u32(ch["c"])]
+            arrs = []
+            chs[i] = _chal(ch, arrs)
             keep.append(arrs)
             sts[i] = _lib.CState(_p(phi[i]), _p(a[i]), _p(b[i]))
-            chs[i] = _lib.CChallenges(_p(arrs[0]), pi.shape[0], int(ch["psi"]), _p(arrs[1]), _p(arrs[2]), _p(arrs[3]), _p(arrs[4]))
             o = {"u_1": np.zeros((c.KAPPA_1, D), np.uint32), "projection_int": np.zeros(JL_ROWS, np.int64), "projection": np.zeros(JL_ROWS, np.uint32),
                  "b_prime_prime": np.zeros(D, np.uint32), "u_2": np.zeros((c.KAPPA_2, D), np.uint32), "z": np.zeros((c.N, D), np.uint32),
                  "t": np.zeros((c.R, c.KAPPA, D), np.uint32), "g": np.zeros((c.R, c.R, D), np.uint32), "h": np.zeros((c.R, c.R, D), np.uint32),
@@ -401,13 +505,10 @@ class Context:
 def transcript_bincode(c, tr, ch, jl_attempt=None):
     """tr: oracle-layout transcript dict; ch: challenges dict (pi [attempts][R][256][N*64]).  Host-only: needs no GPU."""
     L = _lib.lib()
-    pi = np.ascontiguousarray(ch["pi"], dtype=np.int8)
-    if pi.ndim == 3:
-        pi = pi[None]
-    omega, alpha, beta, cc = _u32(ch["omega"]), _u32(ch["alpha"]), _u32(ch["beta"]), _u32(ch["c"])
+    alive = []
+    cch = _chal(ch, alive)
     keep = {k: _u32(tr[k]) for k in ("u_1", "projection", "b_prime_prime", "u_2", "z", "t", "g", "h")}
     att = int(tr.get("jl_attempt", 0)) if jl_attempt is None else jl_attempt
-    cch = _lib.CChallenges(_p(pi), pi.shape[0], int(ch["psi"]), _p(omega), _p(alpha), _p(beta), _p(cc))
     ctr = _lib.CTranscript(_p(keep["u_1"]), att, None, _p(keep["projection"]), _p(keep["b_prime_prime"]),
                            _p(keep["u_2"]), _p(keep["z"]), _p(keep["t"]), _p(keep["g"]), _p(keep["h"]), None, 0)
     size = C.c_size_t(0)
@@ -576,13 +677,11 @@ class Prover:
     def proof_gen(self, st, crs):
         """Prover::proof_gen (proofgen.rs:30-427) -> Transcript."""
         c, ctx, ch = self.constants, self.ctx, self.verifier.challenges
-        pi = np.ascontiguousarray(ch["pi"], dtype=np.int8)
-        if pi.ndim == 3:
-            pi = pi[None]
-        omega, alpha, beta, cc = _u32(ch["omega"]), _u32(ch["alpha"]), _u32(ch["beta"]), _u32(ch["c"])
+        alive = []
+        cch = _chal(ch, alive)
+        pi, pi2, omega, alpha, beta, cc = alive
         phi, a, b = st.phi_k[0], st.a_k[0], st.b_k[0]
         cst = _lib.CState(_p(phi), _p(a), _p(b))
-        cch = _lib.CChallenges(_p(pi), pi.shape[0], int(ch["psi"]), _p(omega), _p(alpha), _p(beta), _p(cc))
         out = {
             "u_1": np.zeros((c.KAPPA_1, D), np.uint32), "projection_int": np.zeros(JL_ROWS, np.int64),
             "projection": np.zeros(JL_ROWS, np.uint32), "b_prime_prime": np.zeros(D, np.uint32),
@@ -597,7 +696,8 @@ class Prover:
         if rc == 1:
             raise LabError(rc, "failed JL...")                                     # proofgen.rs:176
         ctx._ck(rc)
-        return Transcript(u_1=out["u_1"], pi_accepted=pi[tr.jl_attempt], jl_attempt=tr.jl_attempt,
+        pi_acc = pi[tr.jl_attempt] if pi is not None else unpack_pi(pi2[tr.jl_attempt])
+        return Transcript(u_1=out["u_1"], pi_accepted=pi_acc, jl_attempt=tr.jl_attempt,
                           projection_int=out["projection_int"], projection=out["projection"],
                           psi=[[int(ch["psi"])]], omega=[omega], b_prime_prime=[out["b_prime_prime"]],
                           alpha=[alpha], beta=[beta], u_2=out["u_2"], c=cc, z=out["z"], t_i_all=out["t"],

@@ -1,0 +1,58 @@
+#!/usr/bin/env python3
+"""JL stage microbenchmark (BASELINE cfg 3 shape by default): k_jl2 on 2-bit packed matrices, the int8 -> packed kernel,
+and Pi^T omega.  Prints one JSON line per measurement; roofline = packed bytes / measured HBM copy bandwidth."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(ROOT, "labrador-snark_b200"))
+import labrador_b200 as lb  # noqa: E402
+
+N, R = int(os.environ.get("JLB_N", 4096)), int(os.environ.get("JLB_R", 64))
+ND = N * 64
+ctx = lb.Context(0)
+c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
+try:
+    hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    hbm = 6650.0
+dS = ctx.malloc(R * ND * 4)
+ctx.synth_zq_dev(lb.synth.SEED, 1, 0, R * ND, dS)
+ctx.witness_load_dev(c, dS)
+entries = R * 256 * ND
+dpi2, dp = ctx.malloc(entries // 4), ctx.malloc(256 * 8)
+ctx.synth_pi2_dev(lb.synth.SEED, 0, 0, entries, dpi2)
+ctx.sync()
+
+
+def timed(fn, reps=10):
+    for _ in range(3):
+        fn()
+    ctx.sync()
+    ts = []
+    for _ in range(reps):
+        ctx.timer_start(); fn(); ts.append(ctx.timer_stop())
+    return sorted(ts)[len(ts) // 2], min(ts)
+
+
+med, best = timed(lambda: ctx.jl_project2_dev(dpi2, 0, R, dp))
+p = np.empty(256, np.int64)
+ctx.d2h(p, dp); ctx.sync()
+alg = entries / 4 + R * ND * 4
+print(json.dumps({"kernel": "k_jl2", "N": N, "R": R, "ms_median": med, "ms_best": best, "algorithmic_bytes": alg, "GBps": alg / (med * 1e-3) / 1e9,
+                  "hbm_peak_GBps": hbm, "frac": alg / (med * 1e-3) / 1e9 / hbm, "sum_p2": int((p.astype(object) ** 2).sum())}), flush=True)
+if os.environ.get("JLB_PACK", "1") == "1":
+    dpi8 = ctx.malloc(entries)
+    ctx.synth_pi_dev(lb.synth.SEED, 0, 0, entries, dpi8)
+    ctx.sync()
+    med, best = timed(lambda: ctx.pi_pack_dev(dpi8, entries, dpi2), reps=5)
+    alg = entries + entries / 4
+    print(json.dumps({"kernel": "k_pi_pack", "ms_median": med, "algorithmic_bytes": alg, "GBps": alg / (med * 1e-3) / 1e9, "frac": alg / (med * 1e-3) / 1e9 / hbm}), flush=True)
+    med, best = timed(lambda: ctx.jl_project_dev(dpi8, 0, R, dp), reps=5)
+    p2 = np.empty(256, np.int64)
+    ctx.d2h(p2, dp); ctx.sync()
+    print(json.dumps({"kernel": "lab_jl_project_dev (int8: pack + k_jl2)", "ms_median": med, "same_projection": bool(np.array_equal(p, p2))}), flush=True)
+ctx.close()

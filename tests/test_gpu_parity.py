@@ -522,3 +522,275 @@ def test_generate_then_contract_counter_boundaries(ctx, orc, low, monkeypatch):
     co, _ = orc.constants(N, R)
     S = synth.uniform_witness(N, R, seed=9)
     assert np.array_equal(ctx.commit_inner(c, seed, S, 0, 8), orc.commit_inner_rows(co, seed, S, 0, 8))
+
+
+# ---- round 2: 2-bit packed JL matrices (lab_jl.cuh), sharded stage forms, BASELINE shapes, larger / non-square proofs ----
+@pytest.mark.parametrize("N,R", [(1, 1), (2, 3), (7, 3), (8, 2), (9, 2), (33, 5), (70, 2)])
+def test_packed_jl_matches_int8_and_oracle(ctx, orc, N, R):
+    """lab_jl_project2 / lab_aggregate_phi2 on the packed matrices == the int8 entry points == the oracle (proofgen.rs:429-457,
+    :244-253).  N = 7, 9, 33, 70 leave the last 512-coefficient unit of the table kernel ragged."""
+    c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
+    co, _ = orc.constants(N, R)
+    S = synth.uniform_witness(N, R, seed=31 * N + R)
+    pi = synth.sample_pi(N, R, seed=9)
+    pi2 = lb.api.pack_pi(pi)
+    assert pi2.shape == (R, 256, N * 4)
+    assert np.array_equal(lb.api.unpack_pi(pi2), pi)
+    ref = orc.jl_project(co, S, pi)
+    p8, acc8 = ctx.jl_project(c, S, pi)
+    p2, acc2 = ctx.jl_project2(c, S, pi2)
+    assert np.array_equal(p8, ref) and np.array_equal(p2, ref)
+    assert acc8 == acc2 == orc.valid_projection(co, ref)
+    h = R // 2
+    parts = ctx.jl_project2_part(c, S, pi2[:h], 0, h) + ctx.jl_project2_part(c, S, pi2[h:], h, R - h)
+    assert np.array_equal(parts, ref)
+    # phi'' (S5): psi phi + sigma_inv(Pi^T omega), reference value from the definition in numpy
+    phi = rand_polys(R * N, 12).reshape(R, N, D)
+    omega = synth.prg_zq(5, 7, 256)
+    psi = 4097
+    v = (np.einsum("j,ijc->ic", omega.astype(np.int64), pi.astype(np.int64)) % Q).reshape(R, N, D)
+    conj = np.empty_like(v)
+    conj[..., 0] = v[..., 0]
+    conj[..., 1:] = (Q - v[..., :0:-1]) % Q
+    want = ((phi.astype(np.int64) * psi + conj) % Q).astype(np.uint32)
+    assert np.array_equal(ctx.aggregate_phi(c, phi, pi, psi, omega), want)
+    assert np.array_equal(ctx.aggregate_phi2(c, phi, pi2, psi, omega), want)
+
+
+def test_packed_jl_extreme_values(ctx, orc):
+    """All-plus / all-minus rows against a witness of maximal coefficients: the largest table entries (8 x 8190) and the
+    largest per-lane sums; a non-canonical witness is reduced before it is projected (Zq values are canonical in the
+    reference, algebraic.rs:30-38)."""
+    N, R = 16, 2
+    c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
+    co, _ = orc.constants(N, R)
+    S = np.full((R, N, D), Q - 1, np.uint32)
+    pi = np.zeros((R, 256, N * D), np.int8)
+    pi[:, 0::3, :] = 1
+    pi[:, 1::3, :] = -1
+    pi[1, 5, 100:] = 0
+    ref = orc.jl_project(co, S, pi)
+    assert np.array_equal(ctx.jl_project2(c, S, lb.api.pack_pi(pi))[0], ref)
+    assert abs(int(ref[0])) == R * N * D * (Q - 1)
+    Snc = S + np.uint32(3 * Q)                                # same residues, non-canonical representatives
+    assert np.array_equal(ctx.jl_project(c, Snc, pi)[0], ref)
+    with pytest.raises(lb.LabError):
+        lb.api.pack_pi(np.full((1, 256, 64), 2, np.int8))
+
+
+def test_full_proof_with_packed_pi(ctx, orc):
+    """lab_prove / lab_verify / the bincode writer take the JL attempts 2-bit packed (lab_challenges.pi2): same transcript."""
+    N, R = 2, 3
+    co, S, phi, a, b, ch = full_case(orc, N, R, seed=515, n_attempts=3)
+    c = lb.RuntimeConstants.new(N, R)
+    rc, ref = orc.prove(co, SEED32, S, phi, a, b, ch, ntt=True, nthreads=8)
+    assert rc == 0
+    ch2 = dict(ch); ch2["pi2"] = lb.api.pack_pi(ch["pi"]); ch2["pi"] = None
+    st = lb.State(phi, a, b)
+    tr = lb.Prover.new(S, lb.Verifier.new(st.b_prime_k, c, challenges=ch2), c, ctx).proof_gen(st, lb.CRS.from_seed(c, SEED32, ctx))
+    got = tr.as_oracle_dict()
+    for k in ("t", "g", "u_1", "projection_int", "projection", "b_prime_prime", "phi_final", "h", "u_2", "z"):
+        assert np.array_equal(got[k], ref[k]), k
+    assert np.array_equal(tr.pi_accepted, ch["pi"][ref["jl_attempt"]])
+    assert ctx.verify(c, SEED32, phi, a, b, ch2, got)[:2] == (True, 0)
+    assert lb.api.transcript_bincode(c, got, ch2) == lb.api.transcript_bincode(c, got, ch)
+
+
+def test_stage_shards_add_up(ctx, orc):
+    """lab_gram_part / lab_amortize_z_part: the (i, .) tiles of g and the per-shard partial sums of z."""
+    N, R = 5, 7
+    c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
+    co, _ = orc.constants(N, R)
+    S = synth.uniform_witness(N, R, seed=55)
+    ch = rand_polys(R, 13)
+    G = orc.gram(co, S)
+    assert np.array_equal(np.concatenate([ctx.gram_part(c, S, 0, 3), ctx.gram_part(c, S, 3, 4)]), G)
+    z = sum(ctx.amortize_z_part(c, S, ch, i0, ni).astype(np.uint64) for i0, ni in ((0, 2), (2, 0), (2, 5))) % Q
+    assert np.array_equal(z.astype(np.uint32), orc.amortize_z(co, S, ch))
+
+
+def test_resident_witness_host_forms(ctx, orc, monkeypatch):
+    """lab_witness_load + lab_commit_inner_resident (host destination, rows streamed out per chunk) + the sharded device
+    calls without a communicator (they then compute everything locally)."""
+    monkeypatch.setenv("LAB_GEN_CONTRACT_MIN_POLYS", "1")
+    monkeypatch.setenv("LAB_GC_CHUNK_MB", "1")
+    N, R = 33, 6
+    c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
+    co, _ = orc.constants(N, R)
+    S = synth.uniform_witness(N, R, seed=8)
+    c2 = lb.Context(0)
+    try:
+        c2.witness_load(c, S)
+        T = np.empty((R, 200, D), np.uint32)
+        import ctypes as C
+        c2._ck(c2.L.lab_commit_inner_resident(c2._h, lb.api._p(lb.api._seed_buf(SEED32)), C.c_uint64(5), C.c_uint64(200), lb.api._p(T)))
+        assert np.array_equal(T, orc.commit_inner_rows(co, SEED32, S, 5, 200, ntt=True, nthreads=8))
+        pi = synth.sample_pi(N, R, seed=2)
+        pi2 = lb.api.pack_pi(pi)
+        dpi, dp, dG, dz, dch = c2.malloc(pi2.nbytes), c2.malloc(256 * 8), c2.malloc(R * R * 256), c2.malloc(N * 256), c2.malloc(R * 256)
+        chal = rand_polys(R, 14)
+        c2.h2d(dpi, pi2); c2.h2d(dch, chal)
+        assert c2.comm_shard(R) == (0, R)
+        c2.jl_project_sharded_dev(dpi, dp)
+        c2.gram_sharded_dev(dG)
+        c2.amortize_z_sharded_dev(dch, dz)
+        p, G, z = np.empty(256, np.int64), np.empty((R, R, D), np.uint32), np.empty((N, D), np.uint32)
+        c2.d2h(p, dp); c2.d2h(G, dG); c2.d2h(z, dz); c2.sync()
+        assert np.array_equal(p, orc.jl_project(co, S, pi))
+        assert np.array_equal(G, orc.gram(co, S))
+        assert np.array_equal(z, orc.amortize_z(co, S, chal))
+        for d in (dpi, dp, dG, dz, dch):
+            c2.free(d)
+    finally:
+        c2.close()
+
+
+@pytest.mark.parametrize("N,R", [(8, 8), (2, 4), (4, 8)])
+def test_full_proof_larger_and_non_square_shapes(ctx, orc, N, R):
+    """labrador_perf shapes beyond (4,4) (benches/labrador_perf.rs:22-28 doubles n and r alternately from (1,2)): (8,8) has
+    T_1 = 5, (2,4) and (4,8) are the non-square steps.  Transcript equal field by field, oracle verifier accepts."""
+    co, S, phi, a, b, ch = full_case(orc, N, R, seed=2000 + 10 * N + R, n_attempts=3)
+    c = lb.RuntimeConstants.new(N, R)
+    nth = orc.num_threads()
+    rc, ref = orc.prove(co, SEED32, S, phi, a, b, ch, ntt=True, nthreads=nth)
+    assert rc == 0
+    st = lb.State(phi, a, b)
+    tr = lb.Prover.new(S, lb.Verifier.new(st.b_prime_k, c, challenges=ch), c, ctx).proof_gen(st, lb.CRS.from_seed(c, SEED32, ctx))
+    got = tr.as_oracle_dict()
+    for k in ("t", "g", "u_1", "projection_int", "projection", "b_prime_prime", "phi_final", "h", "u_2", "z"):
+        assert np.array_equal(got[k], ref[k]), k
+    assert got["jl_attempt"] == ref["jl_attempt"]
+    ok, failed, norm_sum = orc.verify(co, SEED32, phi, a, b, ch, got, ntt=True, nthreads=nth)
+    assert ok and failed == 0 and tr.norm_sum == norm_sum
+    assert ctx.verify(c, SEED32, phi, a, b, ch, got) == (True, 0, norm_sum)
+
+
+@pytest.mark.parametrize("N,R", [(1, 2), (2, 2), (2, 4)])
+def test_full_proof_against_schoolbook_oracle(ctx, orc, N, R):
+    """The same comparison with the oracle multiplying by the reference's classic path (schoolbook product + sign-folding
+    reduction, algebraic.rs:352-376,402: NTT_ENABLED = false) -- the checker then shares no transform with the device."""
+    co, S, phi, a, b, ch = full_case(orc, N, R, seed=3000 + 10 * N + R, n_attempts=3)
+    c = lb.RuntimeConstants.new(N, R)
+    nth = orc.num_threads()
+    rc, ref = orc.prove(co, SEED32, S, phi, a, b, ch, ntt=False, nthreads=nth)
+    assert rc == 0
+    st = lb.State(phi, a, b)
+    got = lb.Prover.new(S, lb.Verifier.new(st.b_prime_k, c, challenges=ch), c, ctx).proof_gen(st, lb.CRS.from_seed(c, SEED32, ctx)).as_oracle_dict()
+    for k in ("t", "g", "u_1", "projection_int", "projection", "b_prime_prime", "phi_final", "h", "u_2", "z"):
+        assert np.array_equal(got[k], ref[k]), k
+    ok, failed, _ = orc.verify(co, SEED32, phi, a, b, ch, got, ntt=False, nthreads=nth)
+    assert ok and failed == 0
+
+
+def test_rejected_proof_then_other_shape_on_same_ctx(ctx, orc):
+    """A proof that ends with LAB_ERR_JL_REJECTED leaves its forked strand (inner commitment, g, u_1 on the second stream)
+    behind; the next call on the same ctx -- another shape, so other arena offsets -- must not run into it."""
+    N, R = 16, 16
+    co, _ = orc.constants(N, R)
+    c = lb.RuntimeConstants.new(N, R)
+    S_big = synth.uniform_witness(N, R, seed=3)              # not short: every projection is rejected
+    phi, a = synth.generate_statement_inputs(N, R, 5)
+    st = lb.State(phi, a, np.zeros(D, np.uint32))
+    ch = {"pi": np.stack([synth.sample_pi(N, R, 7, t) for t in range(6)]), "psi": 1, "omega": synth.prg_zq(7, 7, 256), "alpha": synth.prg_zq(7, 8, D),
+          "beta": synth.prg_zq(7, 9, D), "c": rand_polys(R, 15)}
+    c2 = lb.Context(0)
+    try:
+        with pytest.raises(lb.LabError) as e:
+            lb.Prover.new(S_big, lb.Verifier.new(st.b_prime_k, c, challenges=ch), c, c2).proof_gen(st, lb.CRS.from_seed(c, SEED32, c2))
+        assert e.value.status == 1
+        # immediately afterwards: a small proof of a different shape on the same context, checked against the oracle
+        n2, r2 = 2, 3
+        co2, S2, phi2, a2, b2, ch2 = full_case(orc, n2, r2, seed=808)
+        cc2 = lb.RuntimeConstants.new(n2, r2)
+        rc, ref = orc.prove(co2, SEED32, S2, phi2, a2, b2, ch2, ntt=True, nthreads=8)
+        assert rc == 0
+        st2 = lb.State(phi2, a2, b2)
+        got = lb.Prover.new(S2, lb.Verifier.new(st2.b_prime_k, cc2, challenges=ch2), cc2, c2).proof_gen(st2, lb.CRS.from_seed(cc2, SEED32, c2)).as_oracle_dict()
+        for k in ("t", "g", "u_1", "h", "u_2", "z"):
+            assert np.array_equal(got[k], ref[k]), k
+    finally:
+        c2.close()
+
+
+def test_baseline_cfg3_shape_against_oracle(ctx, orc):
+    """BASELINE config 3 at its full size, (N, R) = (4096, 64), kappa = 262144, through the default code paths (no environment
+    overrides): the whole JL projection (4.3e9 entries) against the oracle's literal loop, the amortised opening z, 64
+    sampled garbage polynomials g_ij, and rows of T around the first 4 GB chunk boundary of the generate-then-contract
+    path (8191 / 8192 / 8193), rows 0, 1 and the last row kappa - 1.  One of the rows is also checked with the oracle's
+    schoolbook multiplication."""
+    N, R = 4096, 64
+    c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
+    co, _ = orc.constants(N, R)
+    ND, kappa = N * D, c.KAPPA
+    nth = orc.num_threads()
+    c2 = lb.Context(0)
+    try:
+        dS = c2.malloc(R * ND * 4)
+        c2.synth_zq_dev(synth.SEED, 1, 0, R * ND, dS)
+        c2.witness_load_dev(c, dS)
+        S = np.empty((R, N, D), np.uint32)
+        c2.d2h(S, dS); c2.sync()
+        assert np.array_equal(S[5, 9], synth.prg_zq(synth.SEED, 1, D, start=(5 * N + 9) * D))
+        # ---- G4: full projection, packed on the device from the int8 stream and generated packed directly ----
+        dpi8, dpi2, dpi2b, dp = c2.malloc(R * 256 * ND), c2.malloc(R * 256 * ND // 4), c2.malloc(R * 256 * ND // 4), c2.malloc(256 * 8)
+        c2.synth_pi_dev(synth.SEED, 0, 0, R * 256 * ND, dpi8)
+        c2.synth_pi2_dev(synth.SEED, 0, 0, R * 256 * ND, dpi2b)
+        c2.pi_pack_dev(dpi8, R * 256 * ND, dpi2)
+        pi = np.empty((R, 256, ND), np.int8)
+        c2.d2h(pi, dpi8)
+        a2, b2 = np.empty(R * 256 * ND // 16, np.uint32), np.empty(R * 256 * ND // 16, np.uint32)
+        c2.d2h(a2, dpi2); c2.d2h(b2, dpi2b); c2.sync()
+        assert np.array_equal(a2, b2)
+        del a2, b2
+        p = np.empty(256, np.int64)
+        c2.jl_project2_dev(dpi2, 0, R, dp)
+        c2.d2h(p, dp); c2.sync()
+        ref_p = orc.jl_project(co, S, pi)
+        assert np.array_equal(p, ref_p)
+        h = 24                                               # two unequal shards of witness vectors: partial sums add up
+        c2.jl_project2_dev(dpi2, 0, h, dp); p0 = np.empty(256, np.int64); c2.d2h(p0, dp); c2.sync()
+        c2.jl_project2_dev(dpi2 + h * 256 * ND // 4, h, R - h, dp); p1 = np.empty(256, np.int64); c2.d2h(p1, dp); c2.sync()
+        assert np.array_equal(p0 + p1, ref_p)
+        c2.jl_project_dev(dpi8, 0, R, dp); c2.d2h(p0, dp); c2.sync()          # int8 entry point (packs first)
+        assert np.array_equal(p0, ref_p)
+        del pi
+        for d in (dpi8, dpi2, dpi2b):
+            c2.free(d)
+        # ---- G9: z ----
+        chal = rand_polys(R, 16)
+        dch, dz = c2.malloc(R * 256), c2.malloc(N * 256)
+        c2.h2d(dch, chal)
+        c2.amortize_z_dev(dch, 0, R, dz)
+        z = np.empty((N, D), np.uint32)
+        c2.d2h(z, dz); c2.sync()
+        assert np.array_equal(z, orc.amortize_z(co, S, chal))
+        # ---- G2: sampled g_ij ----
+        dG = c2.malloc(R * R * 256)
+        c2.gram_dev(0, R, dG)
+        G = np.empty((R, R, D), np.uint32)
+        c2.d2h(G, dG); c2.sync()
+        assert np.array_equal(G, G.transpose(1, 0, 2))
+        rng = np.random.default_rng(3)
+        for i, j in [(0, 0), (63, 63), (0, 63)] + [tuple(rng.integers(0, R, 2)) for _ in range(61)]:
+            assert np.array_equal(G[i, j], orc.inner_product(S[i], S[j])), (i, j)
+        # ---- G1: rows of T around the chunk boundary and at both ends (default generate-then-contract path) ----
+        n0 = 8448
+        dT = c2.malloc(R * n0 * 256)
+        c2.commit_inner_dev(SEED32, 0, n0, dT)
+        T = np.empty((R, n0, D), np.uint32)
+        c2.d2h(T, dT); c2.sync()
+        for row in (0, 1, 8191, 8192, 8193, n0 - 1):
+            ref = orc.commit_inner_rows(co, SEED32, S, row, 1, ntt=True, nthreads=nth)
+            assert np.array_equal(T[:, row:row + 1], ref), row
+        assert np.array_equal(T[:, 8192:8193], orc.commit_inner_rows(co, SEED32, S, 8192, 1, ntt=False, nthreads=nth))
+        n1 = 1024
+        c2.commit_inner_dev(SEED32, kappa - n1, n1, dT)
+        T1 = np.empty((R, n1, D), np.uint32)
+        c2.d2h(T1, dT); c2.sync()
+        for row in (kappa - n1, kappa - 1):
+            ref = orc.commit_inner_rows(co, SEED32, S, row, 1, ntt=True, nthreads=nth)
+            assert np.array_equal(T1[:, row - (kappa - n1):row - (kappa - n1) + 1], ref), row
+        for d in (dS, dp, dch, dz, dG, dT):
+            c2.free(d)
+    finally:
+        c2.close()

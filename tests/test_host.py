@@ -376,3 +376,18 @@ def test_trimmed_chacha20_equals_the_full_block_on_words_0_to_3(orc):
             assert [int(v) for v in full[:4]] == w
     # operation count the roofline uses: 20 rounds x 4 quarter rounds x 4 (xor + rotate) = 640; hoisted 28, dead tail 16
     assert 640 - 28 - 16 == 596
+
+
+def test_pi_pack_roundtrip_on_host():
+    """lab_pi_pack / lab_pi_unpack are host-side marshalling (no ctx): bit k = +1, bit 16 + k = -1 of the word of 16 entries."""
+    pi = synth.sample_pi(2, 3, seed=4)
+    pi2 = lb.api.pack_pi(pi)
+    assert pi2.dtype == np.uint32 and pi2.shape == (3, 256, 8)
+    w = 5
+    row = pi[1, 7, 16 * w:16 * w + 16]
+    want = sum(1 << k for k in range(16) if row[k] == 1) | sum(1 << (16 + k) for k in range(16) if row[k] == -1)
+    assert int(pi2[1, 7, w]) == want
+    assert np.array_equal(lb.api.unpack_pi(pi2), pi)
+    assert (pi2 & (pi2 >> 16) & 0xFFFF).max() == 0          # an entry is never +1 and -1
+    with pytest.raises(lb.LabError):
+        lb.api.pack_pi(np.full((1, 16), 3, np.int8))
