@@ -830,6 +830,18 @@ __global__ void k_phi_pp(const uint32_t *__restrict__ phi, const uint32_t *__res
     uint32_t conj = d == 0 ? sv : (sv ? LABQ - sv : 0u);
     out[idx] = lab_canon(lab_canon(phi[idx]) * psi + conj);
 }
+// the same with psi read from device memory (whole-proof CUDA graph: psi changes per proof, kernel arguments do not)
+__global__ void k_phi_pp_dev(const uint32_t *__restrict__ phi, const uint32_t *__restrict__ v, const uint32_t *__restrict__ psi_dev, size_t n_coeffs,
+                             uint32_t *__restrict__ out) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_coeffs) return;
+    const uint32_t psi = lab_canon(*psi_dev);
+    const size_t p = idx >> 6;
+    const int d = (int)(idx & 63);
+    uint32_t sv = v[p * 64 + ((64 - d) & 63)];
+    uint32_t conj = d == 0 ? sv : (sv ? LABQ - sv : 0u);
+    out[idx] = lab_canon(lab_canon(phi[idx]) * psi + conj);
+}
 // int64 projection -> mod Q lift (proofgen.rs:186) is done on the host (256 values)
 
 

@@ -55,4 +55,15 @@ if os.environ.get("JLB_PACK", "1") == "1":
     p2 = np.empty(256, np.int64)
     ctx.d2h(p2, dp); ctx.sync()
     print(json.dumps({"kernel": "lab_jl_project_dev (int8: pack + k_jl2)", "ms_median": med, "same_projection": bool(np.array_equal(p, p2))}), flush=True)
+if os.environ.get("JLB_PHI", "1") == "1":          # Pi^T omega + phi'' through the host entry point at a smaller shape (its kernels are what ncu looks at)
+    n2, r2 = 1024, 16
+    c2 = lb.RuntimeConstants.new(n2, r2, allow_degenerate=True)
+    d2 = ctx.malloc(r2 * 256 * n2 * 64 // 4)
+    ctx.synth_pi2_dev(lb.synth.SEED, 1, 0, r2 * 256 * n2 * 64, d2)
+    pi2 = np.empty((r2, 256, n2 * 4), np.uint32)
+    ctx.d2h(pi2, d2); ctx.sync()
+    phi = lb.synth.prg_zq(3, 4, r2 * n2 * 64).reshape(r2, n2, 64)
+    omega = lb.synth.prg_zq(3, 7, 256)
+    out = ctx.aggregate_phi2(c2, phi, pi2, 77, omega)
+    print(json.dumps({"kernel": "lab_aggregate_phi2 (k_piT_omega2 + k_phi_pp)", "N": n2, "R": r2, "checksum": int(out.astype(np.uint64).sum())}), flush=True)
 ctx.close()

@@ -794,3 +794,51 @@ def test_baseline_cfg3_shape_against_oracle(ctx, orc):
             c2.free(d)
     finally:
         c2.close()
+
+
+def test_graph_path_matches_plain_path(orc, monkeypatch):
+    """Small shapes replay the whole proof as one CUDA graph from the second proof of a shape on (lab_api.cu, prove_graph): new
+    CRS seed, statement, challenges and psi per replay, int8 and packed matrices (separate graphs), a rejected first JL
+    attempt (the graph is replayed with the next matrices), and the same proofs again with LAB_NO_GRAPH on a fresh context."""
+    N, R = 2, 2
+    c = lb.RuntimeConstants.new(N, R)
+    cases = []
+    for k in range(5):
+        co, S, phi, a, b, ch = full_case(orc, N, R, seed=9000 + k, n_attempts=3)
+        if k == 3:                                   # attempt 0 = all-ones rows: p_j = sum of the coefficients for every j -> rejected
+            ch["pi"] = ch["pi"].copy(); ch["pi"][0] = 1
+            assert not orc.valid_projection(co, orc.jl_project(co, S, ch["pi"][0]))
+        seed32 = bytes([k + 1]) * 32
+        rc, ref = orc.prove(co, seed32, S, phi, a, b, ch, ntt=True, nthreads=8)
+        assert rc == 0
+        cases.append((seed32, S, phi, a, b, ch, ref))
+    assert cases[3][6]["jl_attempt"] == 1
+
+    def run_all(cx, packed):
+        launches = []
+        for seed32, S, phi, a, b, ch, ref in cases:
+            chx = dict(ch)
+            if packed:
+                chx["pi2"] = lb.api.pack_pi(ch["pi"]); chx["pi"] = None
+            st = lb.State(phi, a, b)
+            l0 = cx.kernel_launches
+            tr = lb.Prover.new(S, lb.Verifier.new(st.b_prime_k, c, challenges=chx), c, cx).proof_gen(st, lb.CRS.from_seed(c, seed32, cx))
+            launches.append(cx.kernel_launches - l0)
+            got = tr.as_oracle_dict()
+            for k in ("t", "g", "u_1", "projection_int", "projection", "b_prime_prime", "phi_final", "h", "u_2", "z"):
+                assert np.array_equal(got[k], ref[k]), (packed, k)
+            assert got["jl_attempt"] == ref["jl_attempt"]
+            assert tr.norm_sum == orc.verify(orc.constants(N, R)[0], seed32, phi, a, b, ch, got, ntt=True, nthreads=8)[2]
+        return launches
+    c2 = lb.Context(0)
+    try:
+        run_all(c2, False)
+        run_all(c2, True)
+    finally:
+        c2.close()
+    monkeypatch.setenv("LAB_NO_GRAPH", "1")
+    c3 = lb.Context(0)
+    try:
+        run_all(c3, False)
+    finally:
+        c3.close()
