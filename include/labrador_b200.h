@@ -261,6 +261,48 @@ int lab_crs_cache_stats(const lab_ctx *ctx, size_t *bytes_used, uint64_t *hits, 
 int lab_transcript_bincode(const lab_constants *c, const lab_transcript *tr, const lab_challenges *ch,
                            uint8_t *out, size_t cap, size_t *size);
 
+/* Transcript::size_in_bytes (structs.rs:211-221): the bincode bytes above through gzip at best compression (main.rs:111-114
+ * prints it in KB).  zlib level 9 in a gzip container; the reference's flate2 uses the miniz_oxide backend, whose output for
+ * the same input may differ by a few bytes -- a size METRIC, not a byte-parity claim.  Host code, no ctx. */
+int lab_transcript_size_in_bytes(const lab_constants *c, const lab_transcript *tr, const lab_challenges *ch, size_t *gzip_bytes, size_t *bincode_bytes);
+
+/* Compact wire format of the same 14 fields: 13 bits per Z_q coefficient (little-endian bit stream), 2 bits per
+ * entry of the accepted JL matrices (the packed words as they are), 3 bits per challenge coefficient when every c_i has the
+ * reference's shape {0, +-1, +-2} (13 bits otherwise), the upper triangle of the symmetric g and h (an asymmetric g or h --
+ * which Checks 8 / 9 would reject -- is refused with LAB_ERR_PARAMS).  32-byte header: "LB2C", version, N, R, jl_attempt, psi.
+ * At (2,2): 0.08 MB against 1.2 MB of bincode.  lab_transcript_unpack fills caller-allocated buffers (projection_int is not
+ * part of the reference's transcript and is left untouched; phi_final likewise).  Host code, no ctx. */
+typedef struct {                 /* writable twin of lab_challenges for one (the accepted) JL attempt */
+    uint32_t *pi2;               /* [R][256][N*4] */
+    uint32_t psi;
+    uint32_t *omega;             /* [256] */
+    uint32_t *alpha, *beta;      /* [64] each */
+    uint32_t *c;                 /* [R][64] */
+} lab_challenges_buf;
+int lab_transcript_pack(const lab_constants *c, const lab_transcript *tr, const lab_challenges *ch, uint8_t *out, size_t cap, size_t *size);
+int lab_transcript_unpack(const lab_constants *c, const uint8_t *in, size_t size, lab_transcript *tr, lab_challenges_buf *ch);
+
+/* ---- Fiat-Shamir (the reference's README lists it as TODO, README.md:12) ----
+ * The verifier's randomness is derived from the transcript prefix instead of being injected: a running SHA-256 state absorbs
+ * the statement and every prover message in the order of SURVEY A.1, and 64-bit seeds squeezed from it drive the seeded
+ * samplers of this library (lab_synth_pi2_dev, the uniform Z_q stream, lab_sample_challenge_polys_dev):
+ *     state  = SHA256("LaBRADOR-B200-FS-v1" | crs_seed | N | R | phi | a | b)                      lab_fs_init
+ *     absorb : state = SHA256(state | label | data)                                                 lab_fs_absorb
+ *     squeeze: seed  = first 8 bytes (LE) of SHA256(state | label | index as u32 LE)               lab_fs_squeeze
+ *   absorb "u_1"; Pi of attempt t <- squeeze("pi", t) (PRG stream 5 + (0 << 8) of that seed); absorb "proj" (t, p as 256 x i64);
+ *   psi, omega <- squeeze("agg", 0) (streams 6, 7); absorb "bpp"; alpha, beta <- squeeze("ab", 0) (streams 8, 9);
+ *   absorb "u_2"; c_i <- squeeze("c", 0) (lab_sample_challenge_polys_dev, index i).
+ * lab_prove_fs runs Prover::proof_gen against this derived verifier and also returns the challenges it derived (ch_out, accepted
+ * JL attempt packed); lab_verify_fs re-derives them from the transcript and runs Verifier::verify.  Integers are little-endian,
+ * polynomials dense uint32[64]. */
+int lab_fs_init(const lab_constants *c, const uint8_t crs_seed[32], const lab_state *st, uint8_t state[32]);
+int lab_fs_absorb(uint8_t state[32], const char *label, const void *data, size_t bytes);
+int lab_fs_squeeze(const uint8_t state[32], const char *label, uint32_t index, uint64_t *seed);
+int lab_prove_fs(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], const uint32_t *S, const lab_state *st,
+                 lab_transcript *out, lab_challenges_buf *ch_out);
+int lab_verify_fs(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], const lab_state *st, const lab_transcript *tr,
+                  int *accepted, int *failed_check, uint64_t *norm_sum);
+
 /* ---- device-resident stage API (inputs already in HBM; used for sharded / pipelined proving) ---- */
 /* S_dev: uint32_t[R][N][64] on device.  Prepares the transformed witness inside ctx. */
 int lab_witness_load_dev(lab_ctx *ctx, const lab_constants *c, const uint32_t *S_dev);

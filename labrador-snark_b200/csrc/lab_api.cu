@@ -6,6 +6,7 @@
 #include "lab_gen.cuh"
 #include "lab_umma.cuh"
 #include "lab_jl.cuh"
+#include "lab_wire.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -896,9 +897,9 @@ static int d_jl(lab_ctx *ctx, const uint32_t *dPi2, const uint32_t *dS, uint64_t
     if (!ni) return LAB_OK;
     if (ND / 16 >= (1ull << 26) || i0 + ni >= (1ull << 32)) FAIL(LAB_ERR_PARAMS, "JL: shape exceeds 32-bit word indexing");
     const uint64_t upv = (ND + JL2_UNIT - 1) / JL2_UNIT, total = ni * upv;
-    // persistent CTAs, three per SM (64 KB of tables each); a lane's int32 row accumulators take 2^13 units of at most 2^18 each
+    // persistent CTAs, three per SM (64 KB of tables each); a lane's int32 row accumulators take 2^14 units of at most 2^17 each
     uint64_t grid = std::min<uint64_t>(total, (uint64_t)ctx->sms * 3);
-    grid = std::max<uint64_t>(grid, (total + 4095) / 4096);
+    grid = std::max<uint64_t>(grid, (total + 8191) / 8192);
     LAUNCH_SMEM(k_jl2, (unsigned)grid, JL2_THREADS, JL2_SMEM, dPi2, dS, ND, (uint32_t)(ND / 16), (uint32_t)i0, (uint32_t)upv, total, dp);
     return LAB_OK;
 }
@@ -1752,9 +1753,9 @@ static int dev_equal(lab_ctx *ctx, const uint32_t *x, const uint32_t *y, size_t 
     *equal = h == 0;
     return LAB_OK;
 }
-extern "C" int lab_verify(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_bytes[32], const lab_state *st, const lab_challenges *ch,
-                          const lab_transcript *tr, int *accepted, int *failed_check, uint64_t *norm_sum) {
-    CallScope cs(ctx);
+// dPi2_ready (optional): the accepted JL matrices already on the device, packed (lab_verify_fs regenerates them there)
+static int verify_core(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_bytes[32], const lab_state *st, const lab_challenges *ch,
+                       const lab_transcript *tr, const uint32_t *dPi2_ready, int *accepted, int *failed_check, uint64_t *norm_sum) {
     TRY(check_consts(ctx, c, true));
     if (!st || !ch || !tr || !accepted) FAIL(LAB_ERR_PARAMS, "null argument");
     const uint64_t R = c->R, N = c->N, K = c->KAPPA, K1 = c->KAPPA_1, K2 = c->KAPPA_2, ND = N * LAB_D;
@@ -1763,7 +1764,7 @@ extern "C" int lab_verify(lab_ctx *ctx, const lab_constants *c, const uint8_t se
     const uint32_t psi = ch->psi % LAB_Q;
     int fc = 0;
     *accepted = 0;
-    if (tr->jl_attempt < 0 || tr->jl_attempt >= ch->n_attempts) FAIL(LAB_ERR_PARAMS, "jl_attempt out of range");
+    if (!dPi2_ready && (tr->jl_attempt < 0 || tr->jl_attempt >= ch->n_attempts)) FAIL(LAB_ERR_PARAMS, "jl_attempt out of range");
     // checks 8, 9: g and h symmetric (verification.rs:157-178)
     for (uint64_t i = 0; i < R && !fc; i++)
         for (uint64_t j = 0; j < R; j++)
@@ -1784,10 +1785,11 @@ extern "C" int lab_verify(lab_ctx *ctx, const lab_constants *c, const uint8_t se
     TRY(upload(ctx, ch->omega, (size_t)LAB_JL_ROWS, &dom));
     TRY(upload(ctx, st->a, R * R * 64, &da));
     TRY(upload(ctx, ch->c, R * 64, &dc));
-    if (!ch->pi && !ch->pi2) FAIL(LAB_ERR_PARAMS, "no JL matrix given (pi or pi2)");
-    TRY(arena_alloc(ctx, R * LAB_JL_ROWS * ND / 16, &dPi2));
-    if (!ch->pi2) TRY(arena_alloc(ctx, R * LAB_JL_ROWS * ND, &dPi8));
-    {
+    if (dPi2_ready) dPi2 = const_cast<uint32_t *>(dPi2_ready);
+    else {
+        if (!ch->pi && !ch->pi2) FAIL(LAB_ERR_PARAMS, "no JL matrix given (pi or pi2)");
+        TRY(arena_alloc(ctx, R * LAB_JL_ROWS * ND / 16, &dPi2));
+        if (!ch->pi2) TRY(arena_alloc(ctx, R * LAB_JL_ROWS * ND, &dPi8));
         const size_t first = (size_t)tr->jl_attempt * R * LAB_JL_ROWS * ND;
         TRY(upload_pi2(ctx, ch->pi2 ? nullptr : ch->pi + first, ch->pi2 ? ch->pi2 + first / 16 : nullptr, R, ND, dPi2, dPi8));
     }
@@ -1935,6 +1937,11 @@ extern "C" int lab_verify(lab_ctx *ctx, const lab_constants *c, const uint8_t se
     return LAB_OK;
 }
 
+extern "C" int lab_verify(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_bytes[32], const lab_state *st, const lab_challenges *ch,
+                          const lab_transcript *tr, int *accepted, int *failed_check, uint64_t *norm_sum) {
+    CallScope cs(ctx);
+    return verify_core(ctx, c, seed_bytes, st, ch, tr, nullptr, accepted, failed_check, norm_sum);
+}
 extern "C" int lab_prove_batch(lab_ctx *ctx, const lab_constants *c, size_t n_statements, const uint8_t *seeds, int shared_crs, const uint32_t *S,
                                const lab_state *st, const lab_challenges *ch, lab_transcript *out) {
     TRY(check_consts(ctx, c, true));
@@ -2069,6 +2076,363 @@ extern "C" int lab_transcript_bincode(const lab_constants *c, const lab_transcri
     *size = w.pos;
     if (out && w.pos > cap) return LAB_ERR_SHAPE;
     return LAB_OK;
+}
+
+// Transcript::size_in_bytes (structs.rs:211-221): gzip at best compression of the bincode bytes
+extern "C" int lab_transcript_size_in_bytes(const lab_constants *c, const lab_transcript *tr, const lab_challenges *ch, size_t *gzip_bytes, size_t *bincode_bytes) {
+    size_t n = 0;
+    int rc = lab_transcript_bincode(c, tr, ch, nullptr, 0, &n);
+    if (rc != LAB_OK) return rc;
+    std::vector<uint8_t> buf(n);
+    rc = lab_transcript_bincode(c, tr, ch, buf.data(), n, &n);
+    if (rc != LAB_OK) return rc;
+    if (bincode_bytes) *bincode_bytes = n;
+    size_t gz = 0;
+    if (labwire::gzip_size(buf.data(), n, &gz) != 0) return LAB_ERR_PARAMS;
+    if (gzip_bytes) *gzip_bytes = gz;
+    return LAB_OK;
+}
+
+// ---- compact wire format (include/labrador_b200.h): 13-bit coefficients, 2-bit JL entries ----
+namespace {
+constexpr uint32_t LB2C_MAGIC = 0x4332424Cu;      // "LB2C"
+bool challenge_shaped(const uint32_t *c, uint64_t n) {                  // every coefficient in {0, 1, 2, q - 1, q - 2}
+    for (uint64_t e = 0; e < n; e++) {
+        const uint32_t v = c[e] % LAB_Q;
+        if (!(v <= 2 || v >= LAB_Q - 2)) return false;
+    }
+    return true;
+}
+void put13(labwire::BitWriter &w, const uint32_t *p, uint64_t n) { for (uint64_t e = 0; e < n; e++) w.put(p[e] % LAB_Q, 13); w.align(); }
+void get13(labwire::BitReader &r, uint32_t *p, uint64_t n) { for (uint64_t e = 0; e < n; e++) p[e] = r.get(13); r.align(); }
+}  // namespace
+extern "C" int lab_transcript_pack(const lab_constants *c, const lab_transcript *tr, const lab_challenges *ch, uint8_t *out, size_t cap, size_t *size) {
+    if (!c || !tr || !ch || !size) return LAB_ERR_PARAMS;
+    if (!tr->u_1 || !tr->projection || !tr->b_prime_prime || !tr->u_2 || !tr->z || !tr->t || !tr->g || !tr->h || (!ch->pi && !ch->pi2) || !ch->omega || !ch->alpha ||
+        !ch->beta || !ch->c || tr->jl_attempt < 0 || tr->jl_attempt >= ch->n_attempts)
+        return LAB_ERR_PARAMS;
+    const uint64_t R = c->R, N = c->N, K = c->KAPPA, ND = N * LAB_D;
+    for (uint64_t i = 0; i < R; i++)                                     // only symmetric g, h have a compact form (Checks 8, 9 reject the others)
+        for (uint64_t j = i + 1; j < R; j++)
+            if (std::memcmp(tr->g + (i * R + j) * 64, tr->g + (j * R + i) * 64, 256) || std::memcmp(tr->h + (i * R + j) * 64, tr->h + (j * R + i) * 64, 256)) return LAB_ERR_PARAMS;
+    labwire::BitWriter w{out, out ? cap : 0};
+    const uint32_t hdr[8] = {LB2C_MAGIC, 1u, (uint32_t)N, (uint32_t)(N >> 32), (uint32_t)R, (uint32_t)(R >> 32), (uint32_t)tr->jl_attempt, ch->psi % LAB_Q};
+    w.raw(hdr, sizeof hdr);
+    put13(w, tr->u_1, c->KAPPA_1 * 64);
+    // pi_i_all: the accepted attempt as packed words
+    const size_t first = (size_t)tr->jl_attempt * R * LAB_JL_ROWS * ND;
+    if (ch->pi2) w.raw(ch->pi2 + first / 16, R * LAB_JL_ROWS * ND / 4);
+    else {
+        std::vector<uint32_t> tmp(R * LAB_JL_ROWS * ND / 16);
+        if (lab_pi_pack(ch->pi + first, R * LAB_JL_ROWS * ND, tmp.data()) != LAB_OK) return LAB_ERR_PARAMS;
+        w.raw(tmp.data(), tmp.size() * 4);
+    }
+    put13(w, tr->projection, LAB_JL_ROWS);
+    put13(w, ch->omega, LAB_JL_ROWS);
+    put13(w, tr->b_prime_prime, 64);
+    put13(w, ch->alpha, 64);
+    put13(w, ch->beta, 64);
+    put13(w, tr->u_2, c->KAPPA_2 * 64);
+    const bool shaped = challenge_shaped(ch->c, R * 64);
+    w.put(shaped ? 1u : 0u, 8);
+    if (shaped) {
+        for (uint64_t e = 0; e < R * 64; e++) { const uint32_t v = ch->c[e] % LAB_Q; w.put(v <= 2 ? v : (v == LAB_Q - 1 ? 3u : 4u), 3); }
+        w.align();
+    } else put13(w, ch->c, R * 64);
+    put13(w, tr->z, N * 64);
+    put13(w, tr->t, R * K * 64);
+    for (uint64_t i = 0; i < R; i++) for (uint64_t j = i; j < R; j++) put13(w, tr->g + (i * R + j) * 64, 64);
+    for (uint64_t i = 0; i < R; i++) for (uint64_t j = i; j < R; j++) put13(w, tr->h + (i * R + j) * 64, 64);
+    w.align();
+    *size = w.pos;
+    if (out && w.pos > cap) return LAB_ERR_SHAPE;
+    return LAB_OK;
+}
+extern "C" int lab_transcript_unpack(const lab_constants *c, const uint8_t *in, size_t size, lab_transcript *tr, lab_challenges_buf *ch) {
+    if (!c || !in || !tr || !ch) return LAB_ERR_PARAMS;
+    if (!tr->u_1 || !tr->projection || !tr->b_prime_prime || !tr->u_2 || !tr->z || !tr->t || !tr->g || !tr->h || !ch->pi2 || !ch->omega || !ch->alpha || !ch->beta || !ch->c)
+        return LAB_ERR_PARAMS;
+    const uint64_t R = c->R, N = c->N, K = c->KAPPA, ND = N * LAB_D;
+    labwire::BitReader r{in, size};
+    uint32_t hdr[8];
+    r.raw(hdr, sizeof hdr);
+    if (r.bad || hdr[0] != LB2C_MAGIC || hdr[1] != 1u || (((uint64_t)hdr[3] << 32) | hdr[2]) != N || (((uint64_t)hdr[5] << 32) | hdr[4]) != R) return LAB_ERR_SHAPE;
+    tr->jl_attempt = (int)hdr[6];
+    ch->psi = hdr[7];
+    get13(r, tr->u_1, c->KAPPA_1 * 64);
+    r.raw(ch->pi2, R * LAB_JL_ROWS * ND / 4);
+    get13(r, tr->projection, LAB_JL_ROWS);
+    get13(r, ch->omega, LAB_JL_ROWS);
+    get13(r, tr->b_prime_prime, 64);
+    get13(r, ch->alpha, 64);
+    get13(r, ch->beta, 64);
+    get13(r, tr->u_2, c->KAPPA_2 * 64);
+    const uint32_t shaped = r.get(8);
+    if (shaped) {
+        static const uint32_t dec[8] = {0, 1, 2, LAB_Q - 1, LAB_Q - 2, 0, 0, 0};
+        for (uint64_t e = 0; e < R * 64; e++) ch->c[e] = dec[r.get(3)];
+        r.align();
+    } else get13(r, ch->c, R * 64);
+    get13(r, tr->z, N * 64);
+    get13(r, tr->t, R * K * 64);
+    for (uint64_t i = 0; i < R; i++)
+        for (uint64_t j = i; j < R; j++) {
+            get13(r, tr->g + (i * R + j) * 64, 64);
+            if (j != i) std::memcpy(tr->g + (j * R + i) * 64, tr->g + (i * R + j) * 64, 256);
+        }
+    for (uint64_t i = 0; i < R; i++)
+        for (uint64_t j = i; j < R; j++) {
+            get13(r, tr->h + (i * R + j) * 64, 64);
+            if (j != i) std::memcpy(tr->h + (j * R + i) * 64, tr->h + (i * R + j) * 64, 256);
+        }
+    return r.bad ? LAB_ERR_SHAPE : LAB_OK;
+}
+
+// ---- Fiat-Shamir seed chain (include/labrador_b200.h) ----
+static const char FS_DOMAIN[] = "LaBRADOR-B200-FS-v1";
+extern "C" int lab_fs_init(const lab_constants *c, const uint8_t crs_seed[32], const lab_state *st, uint8_t state[32]) {
+    if (!c || !crs_seed || !st || !st->phi || !st->a || !st->b || !state) return LAB_ERR_PARAMS;
+    labwire::Sha256 h;
+    h.update(FS_DOMAIN, sizeof FS_DOMAIN - 1);
+    h.update(crs_seed, 32);
+    const uint64_t nr[2] = {c->N, c->R};
+    h.update(nr, sizeof nr);
+    h.update(st->phi, c->R * c->N * 256);
+    h.update(st->a, c->R * c->R * 256);
+    h.update(st->b, 256);
+    h.final(state);
+    return LAB_OK;
+}
+extern "C" int lab_fs_absorb(uint8_t state[32], const char *label, const void *data, size_t bytes) {
+    if (!state || !label || (!data && bytes)) return LAB_ERR_PARAMS;
+    labwire::Sha256 h;
+    h.update(state, 32);
+    h.update(label, std::strlen(label));
+    if (bytes) h.update(data, bytes);
+    h.final(state);
+    return LAB_OK;
+}
+extern "C" int lab_fs_squeeze(const uint8_t state[32], const char *label, uint32_t index, uint64_t *seed) {
+    if (!state || !label || !seed) return LAB_ERR_PARAMS;
+    labwire::Sha256 h;
+    h.update(state, 32);
+    h.update(label, std::strlen(label));
+    h.update(&index, 4);
+    uint8_t d[32];
+    h.final(d);
+    uint64_t v = 0;
+    for (int b = 7; b >= 0; b--) v = (v << 8) | d[b];
+    *seed = v;
+    return LAB_OK;
+}
+
+// uniform Z_q value idx of PRG stream `stream` (the SplitMix64 counter PRG of k_synth_zq / labrador_b200/synth.py)
+static uint64_t prg_base(uint64_t seed, uint64_t stream);
+static uint32_t host_prg_zq(uint64_t seed, uint64_t stream, uint64_t idx) {
+    uint64_t z = prg_base(seed, stream) + (idx + 1ull) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (uint32_t)(((u128)z * LAB_Q) >> 64);
+}
+// the derived verifier's answers (SURVEY A.1 order): Pi of attempt t on the device, psi / omega / alpha / beta on the host
+static int fs_pi(lab_ctx *ctx, const uint8_t state[32], uint32_t attempt, size_t entries, uint32_t *dPi2) {
+    uint64_t sd;
+    lab_fs_squeeze(state, "pi", attempt, &sd);
+    return lab_synth_pi2_dev(ctx, sd, 0, 0, entries, dPi2);
+}
+static void fs_agg(const uint8_t state[32], uint32_t *psi, uint32_t omega[LAB_JL_ROWS]) {
+    uint64_t sd;
+    lab_fs_squeeze(state, "agg", 0, &sd);
+    *psi = host_prg_zq(sd, 6, 0);
+    for (int j = 0; j < LAB_JL_ROWS; j++) omega[j] = host_prg_zq(sd, 7, (uint64_t)j);
+}
+static void fs_ab(const uint8_t state[32], uint32_t ab[128]) {
+    uint64_t sd;
+    lab_fs_squeeze(state, "ab", 0, &sd);
+    for (int d = 0; d < 64; d++) { ab[d] = host_prg_zq(sd, 8, (uint64_t)d); ab[64 + d] = host_prg_zq(sd, 9, (uint64_t)d); }
+}
+static void fs_absorb_proj(uint8_t state[32], int attempt, const int64_t *p) {
+    uint8_t buf[4 + LAB_JL_ROWS * 8];
+    const uint32_t a = (uint32_t)attempt;
+    std::memcpy(buf, &a, 4);
+    std::memcpy(buf + 4, p, LAB_JL_ROWS * 8);
+    lab_fs_absorb(state, "proj", buf, sizeof buf);
+}
+
+// Prover::proof_gen against the Fiat-Shamir verifier: the stages run strictly in protocol order, because every challenge
+// depends on the prover messages before it (u_1 before Pi, p before psi / omega, b'' before alpha / beta, u_2 before c).
+extern "C" int lab_prove_fs(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_bytes[32], const uint32_t *S, const lab_state *st,
+                            lab_transcript *out, lab_challenges_buf *cho) {
+    CallScope cs(ctx);
+    TRY(check_consts(ctx, c, true));
+    if (!S || !st || !out || !cho || !st->phi || !st->a || !st->b || !cho->pi2 || !cho->omega || !cho->alpha || !cho->beta || !cho->c) FAIL(LAB_ERR_PARAMS, "null argument");
+    const uint64_t R = c->R, N = c->N, K = c->KAPPA, K1 = c->KAPPA_1, K2 = c->KAPPA_2, ND = N * LAB_D;
+    const uint64_t T1 = (uint64_t)c->T_1, T2 = (uint64_t)c->T_2;
+    const LabSeed seed = make_seed(seed_bytes);
+    uint8_t fs[32];
+    TRY(lab_fs_init(c, seed_bytes, st, fs));
+    uint32_t *dS, *What, *dphi, *da;
+    TRY(load_witness(ctx, c, S, &dS, &What));
+    TRY(upload(ctx, st->phi, R * ND, &dphi));
+    TRY(upload(ctx, st->a, R * R * 64, &da));
+    // ---- round 1: t, g, u_1 ----
+    uint32_t *dT, *Ghat, *dG, *du1;
+    TRY(arena_alloc(ctx, R * K * 64, &dT));
+    TRY(arena_alloc(ctx, R * R * 32, &Ghat));
+    TRY(arena_alloc(ctx, R * R * 64, &dG));
+    TRY(arena_alloc(ctx, K1 * 64, &du1));
+    TRY(d_commit_inner(ctx, seed, What, N, R, 0, K, dT, K, 0));
+    TRY(d_gram(ctx, What, N, R, 0, R, Ghat, dG));
+    TRY(d_outer_u1(ctx, c, seed, dT, dG, du1));
+    TRY(download(ctx, out->u_1, du1, K1 * 64));
+    TRY(lab_sync(ctx));
+    TRY(lab_fs_absorb(fs, "u_1", out->u_1, K1 * 256));
+    // ---- round 2: JL with the reference's retry rule (proofgen.rs:161-186) ----
+    uint32_t *dPi2;
+    unsigned long long *dp;
+    TRY(arena_alloc(ctx, R * LAB_JL_ROWS * ND / 16, &dPi2));
+    TRY(arena_alloc(ctx, (size_t)LAB_JL_ROWS, &dp));
+    int att = 0;
+    for (;;) {
+        TRY(fs_pi(ctx, fs, (uint32_t)att, R * LAB_JL_ROWS * ND, dPi2));
+        TRY(d_jl(ctx, dPi2, dS, ND, 0, R, dp));
+        CK(cudaMemcpyAsync(out->projection_int, dp, LAB_JL_ROWS * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        TRY(lab_sync(ctx));
+        if (valid_projection(c, out->projection_int)) break;
+        if (++att > 5) FAIL(LAB_ERR_JL_REJECTED, "failed JL... (proofgen.rs:175-176)");
+    }
+    out->jl_attempt = att;
+    CK(cudaMemcpyAsync(cho->pi2, dPi2, R * LAB_JL_ROWS * ND / 4, cudaMemcpyDeviceToHost, ctx->stream));
+    fs_absorb_proj(fs, att, out->projection_int);
+    // ---- round 3: psi, omega -> phi'', b'' ----
+    fs_agg(fs, &cho->psi, cho->omega);
+    const uint32_t psi = cho->psi;
+    uint32_t *dom, *dpp, *Phihat, *PPhat, *Ahat, *AG, *diag, *sums, *dsums;
+    TRY(upload(ctx, cho->omega, (size_t)LAB_JL_ROWS, &dom));
+    TRY(arena_alloc(ctx, R * ND, &dpp));
+    TRY(arena_alloc(ctx, R * N * 32, &Phihat));
+    TRY(arena_alloc(ctx, R * N * 32, &PPhat));
+    TRY(arena_alloc(ctx, R * R * 32, &Ahat));
+    TRY(arena_alloc(ctx, R * R * 32, &AG));
+    TRY(arena_alloc(ctx, R * 32, &diag));
+    TRY(arena_alloc(ctx, (size_t)2 * 32, &sums));
+    TRY(arena_alloc(ctx, (size_t)2 * 64, &dsums));
+    TRY(d_fwd_hat(ctx, dphi, Phihat, R * N, N, R));
+    TRY(d_fwd_hat(ctx, da, Ahat, R * R, 0, 0));
+    LAUNCH(k_pointwise, grid_for(R * R * 32, 256, ctx->sms * 16), 256, Ahat, (size_t)1, (size_t)(R * R), Ghat, (const uint32_t *)nullptr, (size_t)1,
+           (size_t)0, (const uint32_t *)nullptr, AG, (size_t)(R * R));
+    LAUNCH(k_sum_hats, 1, 32, AG, (size_t)(R * R), (size_t)1, sums, (size_t)1);
+    TRY(d_aggregate_phi(ctx, c, dphi, dPi2, psi, dom, dpp));
+    TRY(d_fwd_hat(ctx, dpp, PPhat, R * N, N, R));
+    LAUNCH(k_ip_hat, (unsigned)R, 256, PPhat, (size_t)R, (size_t)1, What, (size_t)R, (size_t)1, (size_t)N, (size_t)0, 1u, 2, diag);
+    LAUNCH(k_sum_hats, 1, 32, diag, (size_t)R, (size_t)1, sums + 32, (size_t)1);
+    TRY(d_inv_hat(ctx, sums, dsums, 2));
+    uint32_t hs[128];
+    TRY(download(ctx, hs, dsums, (size_t)128));
+    TRY(lab_sync(ctx));
+    for (int d = 0; d < 64; d++) out->b_prime_prime[d] = (uint32_t)(((uint64_t)hs[d] * psi + hs[64 + d]) % LAB_Q);
+    TRY(lab_fs_absorb(fs, "bpp", out->b_prime_prime, 256));
+    // ---- round 4: alpha, beta -> phi, h, u_2 ----
+    uint32_t ab[128];
+    fs_ab(fs, ab);
+    std::memcpy(cho->alpha, ab, 256);
+    std::memcpy(cho->beta, ab + 64, 256);
+    uint32_t *dab, *ABhat, *PFhat, *Hhat, *dH, *du2, *pf_tmp = nullptr;
+    TRY(upload(ctx, ab, (size_t)128, &dab));
+    TRY(arena_alloc(ctx, (size_t)64, &ABhat));
+    TRY(arena_alloc(ctx, R * N * 32, &PFhat));
+    TRY(arena_alloc(ctx, R * R * 32, &Hhat));
+    TRY(arena_alloc(ctx, R * R * 64, &dH));
+    TRY(arena_alloc(ctx, K2 * 64, &du2));
+    TRY(d_fwd_hat(ctx, dab, ABhat, 2, 0, 0));
+    LAUNCH(k_pointwise, grid_for(R * N * 32, 256, ctx->sms * 16), 256, ABhat, (size_t)1, (size_t)0, Phihat, ABhat + 32, (size_t)1, (size_t)0, PPhat,
+           PFhat, (size_t)(R * N));
+    TRY(d_h_gram(ctx, PFhat, What, N, R, Hhat, dH));
+    TRY(d_outer_u2(ctx, c, seed, dH, du2));
+    TRY(download(ctx, out->u_2, du2, K2 * 64));
+    TRY(lab_sync(ctx));
+    TRY(lab_fs_absorb(fs, "u_2", out->u_2, K2 * 256));
+    // ---- round 5: c_i (fetch_challenge with the operator-norm rejection, on the device) -> z ----
+    uint64_t sc;
+    lab_fs_squeeze(fs, "c", 0, &sc);
+    uint32_t *dc, *Chat, *zhat, *dz;
+    unsigned long long *dnorm;
+    TRY(arena_alloc(ctx, R * 64, &dc));
+    TRY(arena_alloc(ctx, R * 32, &Chat));
+    TRY(arena_alloc(ctx, N * 32, &zhat));
+    TRY(arena_alloc(ctx, N * 64, &dz));
+    TRY(arena_alloc(ctx, (size_t)1, &dnorm));
+    TRY(lab_sample_challenge_polys_dev(ctx, sc, 0, (uint32_t)R, dc, nullptr));
+    TRY(d_fwd_hat(ctx, dc, Chat, R, 0, 0));
+    TRY(d_amortize(ctx, Chat, What, N, R, 0, R, zhat, dz));
+    CK(cudaMemsetAsync(dnorm, 0, sizeof *dnorm, ctx->stream));
+    LAUNCH(k_digit_norm_sq, grid_for(N * 64, 2048, ctx->sms * 8), 256, dz, (size_t)(N * 64), (uint32_t)c->B, 2, dnorm);
+    LAUNCH(k_digit_norm_sq, grid_for(R * K * 64, 2048, ctx->sms * 8), 256, dT, (size_t)(R * K * 64), (uint32_t)c->B_1, (int)T1, dnorm);
+    LAUNCH(k_digit_norm_sq, grid_for(R * R * 64, 2048, ctx->sms * 8), 256, dG, (size_t)(R * R * 64), (uint32_t)c->B_2, (int)T2, dnorm);
+    LAUNCH(k_digit_norm_sq, grid_for(R * R * 64, 2048, ctx->sms * 8), 256, dH, (size_t)(R * R * 64), (uint32_t)c->B_1, (int)T1, dnorm);
+    if (out->phi_final) {
+        TRY(arena_alloc(ctx, R * N * 64, &pf_tmp));
+        TRY(d_inv_hat(ctx, PFhat, pf_tmp, R * N));
+        for (uint64_t i = 0; i < R; i++)
+            CK(cudaMemcpy2DAsync(out->phi_final + i * N * 64, 64 * sizeof(uint32_t), pf_tmp + i * 64, R * 64 * sizeof(uint32_t), 64 * sizeof(uint32_t), N,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    unsigned long long hnorm = 0;
+    TRY(download(ctx, cho->c, dc, R * 64));
+    TRY(download(ctx, out->z, dz, N * 64));
+    TRY(download(ctx, out->t, dT, R * K * 64));
+    TRY(download(ctx, out->g, dG, R * R * 64));
+    TRY(download(ctx, out->h, dH, R * R * 64));
+    CK(cudaMemcpyAsync(&hnorm, dnorm, sizeof hnorm, cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(lab_sync(ctx));
+    out->norm_sum = hnorm;
+    lab_challenges chv{};
+    chv.psi = psi; chv.omega = cho->omega;
+    return finish_transcript(ctx, st, &chv, psi, hs, out);
+}
+
+// Verifier::verify against the same derived challenges: everything the interactive verifier would have sent is recomputed
+// from the transcript prefix; the projection-norm test the prover ran interactively (valid_projection, proofgen.rs:170) becomes
+// a verifier check (reported as check 7, before the reference's Checks 8-20).
+extern "C" int lab_verify_fs(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_bytes[32], const lab_state *st, const lab_transcript *tr,
+                             int *accepted, int *failed_check, uint64_t *norm_sum) {
+    CallScope cs(ctx);
+    TRY(check_consts(ctx, c, true));
+    if (!st || !tr || !accepted || !st->phi || !st->a || !st->b || !tr->u_1 || !tr->projection_int || !tr->projection || !tr->b_prime_prime || !tr->u_2)
+        FAIL(LAB_ERR_PARAMS, "null argument");
+    const uint64_t R = c->R, ND = c->N * LAB_D;
+    *accepted = 0;
+    if (failed_check) *failed_check = 0;
+    if (tr->jl_attempt < 0 || tr->jl_attempt > 5) FAIL(LAB_ERR_PARAMS, "jl_attempt out of range");
+    bool proj_ok = valid_projection(c, tr->projection_int);
+    for (int j = 0; j < LAB_JL_ROWS && proj_ok; j++) {
+        int64_t m = tr->projection_int[j] % (int64_t)LAB_Q;
+        proj_ok = tr->projection[j] % LAB_Q == (uint32_t)(m < 0 ? m + (int64_t)LAB_Q : m);
+    }
+    if (!proj_ok) { if (failed_check) *failed_check = 7; return LAB_OK; }
+    uint8_t fs[32];
+    TRY(lab_fs_init(c, seed_bytes, st, fs));
+    TRY(lab_fs_absorb(fs, "u_1", tr->u_1, c->KAPPA_1 * 256));
+    uint32_t *dPi2, *dc;
+    TRY(arena_alloc(ctx, R * LAB_JL_ROWS * ND / 16, &dPi2));
+    TRY(arena_alloc(ctx, R * 64, &dc));
+    TRY(fs_pi(ctx, fs, (uint32_t)tr->jl_attempt, R * LAB_JL_ROWS * ND, dPi2));
+    fs_absorb_proj(fs, tr->jl_attempt, tr->projection_int);
+    uint32_t psi, omega[LAB_JL_ROWS], ab[128];
+    fs_agg(fs, &psi, omega);
+    TRY(lab_fs_absorb(fs, "bpp", tr->b_prime_prime, 256));
+    fs_ab(fs, ab);
+    TRY(lab_fs_absorb(fs, "u_2", tr->u_2, c->KAPPA_2 * 256));
+    uint64_t sc;
+    lab_fs_squeeze(fs, "c", 0, &sc);
+    TRY(lab_sample_challenge_polys_dev(ctx, sc, 0, (uint32_t)R, dc, nullptr));
+    std::vector<uint32_t> hc(R * 64);
+    TRY(download(ctx, hc.data(), dc, R * 64));
+    TRY(lab_sync(ctx));
+    lab_challenges chv{};
+    chv.n_attempts = tr->jl_attempt + 1; chv.psi = psi; chv.omega = omega; chv.alpha = ab; chv.beta = ab + 64; chv.c = hc.data();
+    return verify_core(ctx, c, seed_bytes, st, &chv, tr, dPi2, accepted, failed_check, norm_sum);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -4,17 +4,18 @@
 // 32-bit word:   bit k = (entry == +1),  bit 16 + k = (entry == -1).   A row of N*64 entries is N*4 words (2 bits per entry,
 // a quarter of the int8 form), rows and witness vectors follow each other like in the int8 layout: pi2[R][256][N*4].
 //
-// k_jl2 -- p_j = sum_c Pi[j][c] s[c] by table lookup ("Four Russians"): a CTA takes one unit of 1024 coefficients of one
-// witness vector, builds in shared memory, for each of its 128 groups of 8 coefficients, the 256 subset sums
-// tab[g][m] = sum_{b in m} s[8 g + b] (16 bits: at most 8 * 8190), and then every row of Pi costs one lookup per byte of
-// its masks: plus-byte lookups are added, minus-byte lookups subtracted.  Lane l owns groups 4 l .. 4 l + 3 and shared-memory
-// bank l: entry (m, group q of the lane) sits at byte m * 256 + (q >> 1) * 128 + 4 l + 2 (q & 1), so neither the lookups
-// (random m per lane) nor the table stores ever conflict, the address of an entry is one byte-permute of the mask word,
-// and the table is written as 32-bit words holding two groups' sums, updated with one packed add per Gray-code step.
-// The 256 rows are split over 8 warps x 32 rows; a lane keeps 32 row accumulators across all the units its CTA processes
-// (persistent grid) and one butterfly of 31 shuffles at the very end turns them into per-row totals (lane l = row l),
-// which go to the global int64 sums with one atomic per row and CTA.  Per entry the kernel does 1/8 lookup + 1/32 table
-// store: it leans on the shared-memory pipe (ncu: LSU data pipe 77 % busy), at about half the rate HBM delivers the bytes.
+// k_jl2 -- p_j = sum_c Pi[j][c] s[c] by table lookup ("Four Russians"): a CTA takes one unit of 512 coefficients of one
+// witness vector, builds in shared memory, for each of its 64 groups of 8 coefficients, the 256 subset sums
+// tab[g][m] = sum_{b in m} s[8 g + b], and then every row of Pi costs one lookup per byte of its masks: plus-byte lookups
+// are added, minus-byte lookups subtracted.  Layout tab[m][g & 1][g >> 1]: lane l owns groups 2 l, 2 l + 1 and
+// shared-memory bank l, so neither the lookups (random m per lane) nor the table stores ever conflict, and the byte address
+// m * 256 + (g & 1) * 128 + 4 l of an entry is one byte-permute of the mask word.  The 256 rows are
+// split over 8 warps x 32 rows; a lane keeps 32 row accumulators across all the units its CTA processes (persistent grid)
+// and one butterfly of 31 shuffles at the very end turns them into per-row totals (lane l = row l), which go to the global
+// int64 sums with one atomic per row and CTA.  Per entry the kernel does 1/8 lookup + 1/16 table store: the shared-memory
+// pipe, not the ALU pipe, is what it leans on (ncu: LSU data pipe 77 % busy), at half the rate HBM delivers the packed bytes.
+// (A variant with 16-bit sums, 1024-coefficient units and 8-byte row loads -- 25 % fewer shared-memory wavefronts on paper --
+// measured 3 % slower on a B200 and was dropped.)
 //
 // k_piT_omega2 -- v[c] = sum_j omega_j Pi[j][c] mod q (first half of phi'', proofgen.rs:244-253) from the same words: a
 // thread owns one word (16 coefficients), walks the 256 rows (coalesced across threads) and accumulates omega split into
@@ -26,7 +27,7 @@
 
 namespace lab {
 
-constexpr int JL2_UNIT = 1024;                     // coefficients per table unit (128 groups of 8; 16-bit subset sums)
+constexpr int JL2_UNIT = 512;                      // coefficients per table
 constexpr int JL2_THREADS = 256;                   // 8 warps x 32 rows = the 256 JL rows (verification.rs:559)
 constexpr size_t JL2_SMEM = 2 * 256 * 32 * sizeof(uint32_t);   // 64 KB: three CTAs per SM
 
@@ -71,67 +72,60 @@ __global__ void __launch_bounds__(256) k_pi_unpack(const uint32_t *__restrict__ 
     }
 }
 
-// Shared-memory byte address of table entry (group q of the lane, subset m): m * 256 + (q >> 1) * 128 + lane * 4 + (q & 1) * 2, formed
-// by ONE byte permute: result byte 0 = byte 0 of `off` (the lane's constant part, < 256), byte 1 = byte BYTE of the mask word.
+// Shared-memory byte address of table entry (group parity b, subset m) for this lane: m * 256 + b * 128 + lane * 4, formed by ONE
+// byte permute: result byte 0 = byte 0 of `off` (= b * 128 + lane * 4 < 256), byte 1 = byte BYTE of the mask word, rest zero.
 template <int BYTE>
 __device__ __forceinline__ uint32_t jl2_addr(uint32_t x, uint32_t off) {
     uint32_t r;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(off), "n"(0x7704 | (BYTE << 4)));   // selectors: [3]=off.b3 (0) [2]=off.b3 (0) [1]=x.bBYTE [0]=off.b0
     return r;
 }
-__device__ __forceinline__ int jl2_lds16(uint32_t saddr) {
-    uint32_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr));
-    return (int)v;
+__device__ __forceinline__ int jl2_lds(uint32_t saddr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
 }
 
 // pi2: rows of this call's witness vectors, [ni][256][W] with W = ND / 16 words per row; S: the full witness [R][ND] (device);
 // vector li of pi2 is witness vector i0 + li.  p: int64[256], accumulated with atomics (zero it first).
 __global__ void __launch_bounds__(JL2_THREADS, 3) k_jl2(const uint32_t *__restrict__ pi2, const uint32_t *__restrict__ S, uint64_t ND, uint32_t W,
                                                          uint32_t i0, uint32_t units_per_vec, uint64_t total_units, unsigned long long *__restrict__ p) {
-    extern __shared__ __align__(256) uint32_t tab[];            // [m][group pair][32 lanes] words of two 16-bit subset sums: 256 bytes per subset m
+    extern __shared__ __align__(256) uint32_t tab[];            // [m][group parity][32 lanes]: 256 bytes per subset m
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(tab);
-    const uint32_t off0 = (uint32_t)lane * 4u, off1 = off0 + 2u, off2 = off0 + 128u, off3 = off0 + 130u;
+    const uint32_t off0 = (uint32_t)lane * 4u, off1 = off0 + 128u;
     int acc[32];
 #pragma unroll
     for (int r = 0; r < 32; r++) acc[r] = 0;
     for (uint64_t unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
         const uint32_t li = (uint32_t)(unit / units_per_vec), u = (uint32_t)(unit % units_per_vec);
-        // ---- the lane's 32 coefficients = groups 0..3 of the lane, canonical, as packed pairs: svp[p][k] = s[16 p + k] | s[16 p + 8 + k] << 16
-        //      (bit k of group 2 p in the low half, of group 2 p + 1 in the high half); past the end of the vector: zero ----
-        uint32_t svp[2][8];
+        // ---- the lane's 16 coefficients (groups 2 lane, 2 lane + 1), canonical; past the end of the vector: zero ----
+        uint32_t sv[16];
         {
-            const uint64_t c0 = (uint64_t)u * JL2_UNIT + (uint64_t)lane * 32;
-            const bool in = c0 < ND;                                    // ND is a multiple of 64: all 32 or none
+            const uint64_t c0 = (uint64_t)u * JL2_UNIT + (uint64_t)lane * 16;
+            const bool in = c0 < ND;                                    // ND is a multiple of 64: all 16 or none
             const uint4 *src = reinterpret_cast<const uint4 *>(S + (uint64_t)(i0 + li) * ND + (in ? c0 : 0));
 #pragma unroll
-            for (int pp = 0; pp < 2; pp++) {
-                uint4 v[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) v[q] = in ? __ldg(src + 4 * pp + q) : make_uint4(0, 0, 0, 0);
-                svp[pp][0] = lab_canon(v[0].x) | lab_canon(v[2].x) << 16; svp[pp][1] = lab_canon(v[0].y) | lab_canon(v[2].y) << 16;
-                svp[pp][2] = lab_canon(v[0].z) | lab_canon(v[2].z) << 16; svp[pp][3] = lab_canon(v[0].w) | lab_canon(v[2].w) << 16;
-                svp[pp][4] = lab_canon(v[1].x) | lab_canon(v[3].x) << 16; svp[pp][5] = lab_canon(v[1].y) | lab_canon(v[3].y) << 16;
-                svp[pp][6] = lab_canon(v[1].z) | lab_canon(v[3].z) << 16; svp[pp][7] = lab_canon(v[1].w) | lab_canon(v[3].w) << 16;
+            for (int q = 0; q < 4; q++) {
+                uint4 v = in ? __ldg(src + q) : make_uint4(0, 0, 0, 0);
+                sv[4 * q] = lab_canon(v.x); sv[4 * q + 1] = lab_canon(v.y); sv[4 * q + 2] = lab_canon(v.z); sv[4 * q + 3] = lab_canon(v.w);
             }
         }
-        // The unit's two words (32 entries) of rows 32 w .. 32 w + 7 are requested before the table is built.  A lane outside the
-        // row (ragged last unit) reads the first words of the unit instead and masks them: no predicated address arithmetic.
-        const bool win = (uint64_t)u * (JL2_UNIT / 16) + 2 * lane < W;
-        const uint2 *row = reinterpret_cast<const uint2 *>(pi2 + ((uint64_t)li * 256 + (uint64_t)w * 32) * W + (uint64_t)u * (JL2_UNIT / 16) + (win ? 2 * lane : 0));
-        const uint32_t keep = win ? 0xFFFFFFFFu : 0u, W2 = W / 2;
-        uint2 wd[8];
+        // the unit's words of rows 32 w .. 32 w + 15 are requested before the table is built.  A lane outside the row (ragged
+        // last unit) reads word 0 of the unit instead and masks it: no predicated address arithmetic in the unrolled loads.
+        const bool win = (uint64_t)u * (JL2_UNIT / 16) + lane < W;
+        const uint32_t *row = pi2 + ((uint64_t)li * 256 + (uint64_t)w * 32) * W + (uint64_t)u * (JL2_UNIT / 16) + (win ? lane : 0);
+        const uint32_t keep = win ? 0xFFFFFFFFu : 0u;
+        uint32_t wd[16];
 #pragma unroll
-        for (int r = 0; r < 8; r++) wd[r] = __ldg(row + (uint32_t)r * W2);
+        for (int r = 0; r < 16; r++) wd[r] = __ldg(row + (uint32_t)r * W);
         __syncthreads();                                                // every warp is done with the previous table
-        // ---- subset sums: warp w fills m = 32 w + k (k in Gray-code order: one packed add or subtract per pair of entries; a field
-        //      never leaves [0, 8 * 8190], so the two 16-bit halves never borrow from each other) ----
+        // ---- subset sums: warp w fills m = 32 w + k (k in Gray-code order: one add or subtract per entry) ----
 #pragma unroll
-        for (int pp = 0; pp < 2; pp++) {
-            const uint32_t *s8 = svp[pp];
+        for (int b = 0; b < 2; b++) {
+            const uint32_t *s8 = sv + 8 * b;
             uint32_t val = ((w & 1) ? s8[5] : 0u) + ((w & 2) ? s8[6] : 0u) + ((w & 4) ? s8[7] : 0u);
-            uint32_t *t = tab + (size_t)(w * 32) * 64 + pp * 32 + lane;
+            uint32_t *t = tab + (size_t)(w * 32) * 64 + b * 32 + lane;
             t[0] = val;
             int idx = 0;
 #pragma unroll
@@ -144,30 +138,26 @@ __global__ void __launch_bounds__(JL2_THREADS, 3) k_jl2(const uint32_t *__restri
             }
         }
         __syncthreads();
-        // ---- lookups: rows 32 w .. 32 w + 31 in four quarters of 8 rows; the next quarter's words are in flight meanwhile ----
+        // ---- lookups: rows 32 w .. 32 w + 31, two halves of 16 rows ----
 #pragma unroll
-        for (int qr = 0; qr < 4; qr++) {
-            uint2 nx[8];
-            if (qr < 3) {
+        for (int half = 0; half < 2; half++) {
+            uint32_t nx[16];
+            if (half == 0) {                                            // second half of the rows: in flight during the first half's lookups
 #pragma unroll
-                for (int r = 0; r < 8; r++) nx[r] = __ldg(row + (uint32_t)(8 * (qr + 1) + r) * W2);
+                for (int r = 0; r < 16; r++) nx[r] = __ldg(row + (uint32_t)(16 + r) * W);
             }
 #pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const uint32_t x = wd[r].x & keep, y = wd[r].y & keep;
-                const int a0 = jl2_lds16(tab_s + jl2_addr<0>(x, off0));   // plus masks: groups 0, 1 (word x), 2, 3 (word y)
-                const int a1 = jl2_lds16(tab_s + jl2_addr<1>(x, off1));
-                const int a2 = jl2_lds16(tab_s + jl2_addr<0>(y, off2));
-                const int a3 = jl2_lds16(tab_s + jl2_addr<1>(y, off3));
-                const int m0 = jl2_lds16(tab_s + jl2_addr<2>(x, off0));   // minus masks
-                const int m1 = jl2_lds16(tab_s + jl2_addr<3>(x, off1));
-                const int m2 = jl2_lds16(tab_s + jl2_addr<2>(y, off2));
-                const int m3 = jl2_lds16(tab_s + jl2_addr<3>(y, off3));
-                acc[8 * qr + r] += ((a0 - m0) + (a1 - m1)) + ((a2 - m2) + (a3 - m3));
+            for (int r = 0; r < 16; r++) {
+                const uint32_t x = wd[r] & keep;
+                const int a0 = jl2_lds(tab_s + jl2_addr<0>(x, off0));   // plus mask, group 2 lane
+                const int a1 = jl2_lds(tab_s + jl2_addr<1>(x, off1));   // plus mask, group 2 lane + 1
+                const int m0 = jl2_lds(tab_s + jl2_addr<2>(x, off0));   // minus mask, group 2 lane
+                const int m1 = jl2_lds(tab_s + jl2_addr<3>(x, off1));   // minus mask, group 2 lane + 1
+                acc[16 * half + r] += (a0 - m0) + (a1 - m1);
             }
-            if (qr < 3) {
+            if (half == 0) {
 #pragma unroll
-                for (int r = 0; r < 8; r++) wd[r] = nx[r];
+                for (int r = 0; r < 16; r++) wd[r] = nx[r];
             }
         }
     }

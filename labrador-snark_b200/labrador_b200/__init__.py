@@ -2,4 +2,4 @@
 from ._lib import Constants, D, JL_ROWS, LabError, Q, SO_PATH, SYMBOLS  # noqa: F401
 from .api import (CRS, Context, Prover, RuntimeConstants, State, Transcript, Verifier,  # noqa: F401
                   default_context, generate_witness)
-from . import shard, synth  # noqa: F401
+from . import api, fs, shard, synth  # noqa: F401

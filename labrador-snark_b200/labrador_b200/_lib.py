@@ -43,6 +43,11 @@ class CChallenges(C.Structure):
                 ("pi2", C.c_void_p)]          # optional 2-bit packed twin of pi (include/labrador_b200.h)
 
 
+class CChallengesBuf(C.Structure):
+    """lab_challenges_buf: writable challenges of one (the accepted) JL attempt."""
+    _fields_ = [("pi2", C.c_void_p), ("psi", C.c_uint32), ("omega", C.c_void_p), ("alpha", C.c_void_p), ("beta", C.c_void_p), ("c", C.c_void_p)]
+
+
 class CTranscript(C.Structure):
     _fields_ = [("u_1", C.c_void_p), ("jl_attempt", C.c_int), ("projection_int", C.c_void_p),
                 ("projection", C.c_void_p), ("b_prime_prime", C.c_void_p), ("u_2", C.c_void_p),
@@ -68,6 +73,8 @@ SYMBOLS = [
     "lab_pi_pack", "lab_pi_unpack", "lab_pi_pack_dev", "lab_jl_project2", "lab_jl_project2_part", "lab_aggregate_phi2",
     "lab_gram_part", "lab_amortize_z_part", "lab_jl_project2_dev", "lab_jl_project_sharded_dev", "lab_amortize_z_sharded_dev",
     "lab_gram_sharded_dev", "lab_witness_load", "lab_commit_inner_resident", "lab_synth_pi2_dev",
+    "lab_transcript_size_in_bytes", "lab_transcript_pack", "lab_transcript_unpack", "lab_fs_init", "lab_fs_absorb", "lab_fs_squeeze",
+    "lab_prove_fs", "lab_verify_fs",
 ]
 
 _lib = None

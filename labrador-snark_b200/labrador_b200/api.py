@@ -468,6 +468,34 @@ class Context:
                                    C.byref(acc), C.byref(fc), C.byref(ns)))
         return bool(acc.value), fc.value, ns.value
 
+    # ---- Fiat-Shamir: the verifier's randomness derived from the transcript (lab_prove_fs / lab_verify_fs) ----
+    def prove_fs(self, c, seed, S, phi, a, b):
+        """Returns (transcript dict, challenges dict as derived: accepted attempt packed in pi2[1], jl_attempt = tries before it)."""
+        S, phi, a, b = _u32(S), _u32(phi), _u32(a), _u32(b)
+        o = _alloc_out(c)
+        ctr = _ctr(o)
+        bufs, cb = _alloc_chbuf(c)
+        cst = _lib.CState(_p(phi), _p(a), _p(b))
+        rc = self.L.lab_prove_fs(self._h, C.byref(c), _p(_seed_buf(seed)), _p(S), C.byref(cst), C.byref(ctr), C.byref(cb))
+        if rc == 1:
+            raise LabError(rc, "failed JL...")
+        self._ck(rc)
+        o["jl_attempt"] = ctr.jl_attempt
+        o["norm_sum"] = int(ctr.norm_sum)
+        ch = {"pi": None, "pi2": bufs["pi2"][None], "psi": int(cb.psi), "omega": bufs["omega"], "alpha": bufs["alpha"], "beta": bufs["beta"], "c": bufs["c"]}
+        return o, ch
+
+    def verify_fs(self, c, seed, phi, a, b, tr):
+        phi, a, b = _u32(phi), _u32(a), _u32(b)
+        keep = {k: _u32(tr[k]) for k in ("u_1", "projection", "b_prime_prime", "u_2", "z", "t", "g", "h")}
+        pint = np.ascontiguousarray(tr["projection_int"], dtype=np.int64)
+        cst = _lib.CState(_p(phi), _p(a), _p(b))
+        ctr = _lib.CTranscript(_p(keep["u_1"]), int(tr.get("jl_attempt", 0)), _p(pint), _p(keep["projection"]), _p(keep["b_prime_prime"]),
+                               _p(keep["u_2"]), _p(keep["z"]), _p(keep["t"]), _p(keep["g"]), _p(keep["h"]), None, 0)
+        acc, fc, ns = C.c_int(0), C.c_int(0), C.c_uint64(0)
+        self._ck(self.L.lab_verify_fs(self._h, C.byref(c), _p(_seed_buf(seed)), C.byref(cst), C.byref(ctr), C.byref(acc), C.byref(fc), C.byref(ns)))
+        return bool(acc.value), fc.value, ns.value
+
     def prove_batch(self, c, seeds, shared_crs, S, phi, a, b, challenges):
         """lab_prove_batch: S [B][R][N][64], phi [B][R][N][64], a [B][R][R][64], b [B][64]; challenges: list of dicts.
         Returns a list of oracle-layout transcript dicts."""
@@ -520,6 +548,71 @@ def transcript_bincode(c, tr, ch, jl_attempt=None):
     if rc != 0:
         raise LabError(rc, "lab_transcript_bincode failed")
     return buf.tobytes()
+
+
+def transcript_size_in_bytes(c, tr, ch):
+    """Transcript::size_in_bytes (structs.rs:211-221): (gzip-compressed size, bincode size) in bytes."""
+    alive = []
+    cch = _chal(ch, alive)
+    keep = {k: _u32(tr[k]) for k in ("u_1", "projection", "b_prime_prime", "u_2", "z", "t", "g", "h")}
+    ctr = _lib.CTranscript(_p(keep["u_1"]), int(tr.get("jl_attempt", 0)), None, _p(keep["projection"]), _p(keep["b_prime_prime"]),
+                           _p(keep["u_2"]), _p(keep["z"]), _p(keep["t"]), _p(keep["g"]), _p(keep["h"]), None, 0)
+    gz, raw = C.c_size_t(0), C.c_size_t(0)
+    rc = _lib.lib().lab_transcript_size_in_bytes(C.byref(c), C.byref(ctr), C.byref(cch), C.byref(gz), C.byref(raw))
+    if rc != 0:
+        raise LabError(rc, "lab_transcript_size_in_bytes failed")
+    return gz.value, raw.value
+
+
+def transcript_pack(c, tr, ch):
+    """Compact wire format (13-bit coefficients, 2-bit JL entries): bytes."""
+    L = _lib.lib()
+    alive = []
+    cch = _chal(ch, alive)
+    keep = {k: _u32(tr[k]) for k in ("u_1", "projection", "b_prime_prime", "u_2", "z", "t", "g", "h")}
+    ctr = _lib.CTranscript(_p(keep["u_1"]), int(tr.get("jl_attempt", 0)), None, _p(keep["projection"]), _p(keep["b_prime_prime"]),
+                           _p(keep["u_2"]), _p(keep["z"]), _p(keep["t"]), _p(keep["g"]), _p(keep["h"]), None, 0)
+    size = C.c_size_t(0)
+    rc = L.lab_transcript_pack(C.byref(c), C.byref(ctr), C.byref(cch), None, C.c_size_t(0), C.byref(size))
+    if rc != 0:
+        raise LabError(rc, "lab_transcript_pack: bad arguments (g and h must be symmetric)")
+    buf = np.empty(size.value, np.uint8)
+    rc = L.lab_transcript_pack(C.byref(c), C.byref(ctr), C.byref(cch), _p(buf), C.c_size_t(buf.size), C.byref(size))
+    if rc != 0:
+        raise LabError(rc, "lab_transcript_pack failed")
+    return buf.tobytes()
+
+
+def _alloc_out(c):
+    return {"u_1": np.zeros((c.KAPPA_1, D), np.uint32), "projection_int": np.zeros(JL_ROWS, np.int64), "projection": np.zeros(JL_ROWS, np.uint32),
+            "b_prime_prime": np.zeros(D, np.uint32), "u_2": np.zeros((c.KAPPA_2, D), np.uint32), "z": np.zeros((c.N, D), np.uint32),
+            "t": np.zeros((c.R, c.KAPPA, D), np.uint32), "g": np.zeros((c.R, c.R, D), np.uint32), "h": np.zeros((c.R, c.R, D), np.uint32),
+            "phi_final": np.zeros((c.R, c.N, D), np.uint32)}
+
+
+def _ctr(o, jl_attempt=0):
+    return _lib.CTranscript(_p(o["u_1"]), jl_attempt, _p(o["projection_int"]), _p(o["projection"]), _p(o["b_prime_prime"]), _p(o["u_2"]),
+                            _p(o["z"]), _p(o["t"]), _p(o["g"]), _p(o["h"]), _p(o["phi_final"]), 0)
+
+
+def _alloc_chbuf(c):
+    b = {"pi2": np.zeros((c.R, JL_ROWS, c.N * 4), np.uint32), "omega": np.zeros(JL_ROWS, np.uint32), "alpha": np.zeros(D, np.uint32),
+         "beta": np.zeros(D, np.uint32), "c": np.zeros((c.R, D), np.uint32)}
+    return b, _lib.CChallengesBuf(_p(b["pi2"]), 0, _p(b["omega"]), _p(b["alpha"]), _p(b["beta"]), _p(b["c"]))
+
+
+def transcript_unpack(c, blob):
+    """Inverse of transcript_pack -> (transcript dict, challenges dict with the accepted attempt as pi2[1][R][256][N*4])."""
+    data = np.frombuffer(bytes(blob), dtype=np.uint8).copy()
+    o = _alloc_out(c)
+    ctr = _ctr(o)
+    b, cb = _alloc_chbuf(c)
+    rc = _lib.lib().lab_transcript_unpack(C.byref(c), _p(data), C.c_size_t(data.size), C.byref(ctr), C.byref(cb))
+    if rc != 0:
+        raise LabError(rc, "lab_transcript_unpack: malformed input")
+    o["jl_attempt"] = ctr.jl_attempt
+    ch = {"pi": None, "pi2": b["pi2"][None], "psi": int(cb.psi), "omega": b["omega"], "alpha": b["alpha"], "beta": b["beta"], "c": b["c"]}
+    return o, ch
 
 
 _default_ctx = None

@@ -842,3 +842,40 @@ def test_graph_path_matches_plain_path(orc, monkeypatch):
         run_all(c3, False)
     finally:
         c3.close()
+
+
+@pytest.mark.parametrize("N,R", [(1, 2), (2, 2), (2, 3)])
+def test_fiat_shamir_proof_matches_oracle(ctx, orc, N, R):
+    """lab_prove_fs: the challenges come from the SHA-256 chain over the transcript prefix (include/labrador_b200.h).  The
+    independent restatement of the chain (labrador_b200/fs.py: hashlib + the host samplers) derives the same challenges from
+    the GPU transcript; the CPU oracle, given them by injection, reproduces every field; the oracle's verifier and lab_verify_fs
+    accept; a tampered transcript is rejected (the derived challenges no longer fit, or a check fails)."""
+    co, rc = orc.constants(N, R)
+    c = lb.RuntimeConstants.new(N, R)
+    S = orc.generate_witness(co, 600 + N + R)
+    phi, a, b = orc.generate_state(co, S, 600 + N + R)
+    tr, chg = ctx.prove_fs(c, SEED32, S, phi, a, b)
+    ch = lb.fs.derive_challenges(N, R, SEED32, phi, a, b, tr)
+    att = tr["jl_attempt"]
+    assert chg["psi"] == ch["psi"]
+    for k in ("omega", "alpha", "beta", "c"):
+        assert np.array_equal(chg[k], ch[k]), k
+    assert np.array_equal(lb.api.unpack_pi(chg["pi2"][0]), ch["pi"][att])
+    rc, ref = orc.prove(co, SEED32, S, phi, a, b, ch, ntt=True, nthreads=8)
+    assert rc == 0 and ref["jl_attempt"] == att
+    for k in ("t", "g", "u_1", "projection_int", "projection", "b_prime_prime", "phi_final", "h", "u_2", "z"):
+        assert np.array_equal(tr[k], ref[k]), k
+    ok, failed, norm_sum = orc.verify(co, SEED32, phi, a, b, ch, tr, ntt=True, nthreads=8)
+    assert ok and norm_sum == tr["norm_sum"]
+    assert ctx.verify_fs(c, SEED32, phi, a, b, tr) == (True, 0, norm_sum)
+    for field, idx in (("u_1", (0, 0)), ("z", (0, 3)), ("u_2", (1, 1)), ("b_prime_prime", (5,)), ("t", (0, 2, 2))):
+        bad = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in tr.items()}
+        bad[field][idx] = (int(bad[field][idx]) + 1) % Q
+        assert ctx.verify_fs(c, SEED32, phi, a, b, bad)[0] is False, field
+    bad = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in tr.items()}
+    bad["projection_int"][0] += 10 ** 6                              # breaks the norm bound the verifier now checks itself
+    assert ctx.verify_fs(c, SEED32, phi, a, b, bad)[:2] == (False, 7)
+    # the compact wire format carries exactly what the non-interactive verifier needs besides the statement
+    got, _ = lb.api.transcript_unpack(c, lb.api.transcript_pack(c, tr, chg))
+    got["projection_int"] = tr["projection_int"]
+    assert ctx.verify_fs(c, SEED32, phi, a, b, got)[0] is True

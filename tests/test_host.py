@@ -391,3 +391,94 @@ def test_pi_pack_roundtrip_on_host():
     assert (pi2 & (pi2 >> 16) & 0xFFFF).max() == 0          # an entry is never +1 and -1
     with pytest.raises(lb.LabError):
         lb.api.pack_pi(np.full((1, 16), 3, np.int8))
+
+
+def _small_transcript(orc, N=1, R=2, seed=12):
+    c, _ = orc.constants(N, R)
+    S = orc.generate_witness(c, seed)
+    phi, a, b = orc.generate_state(c, S, seed)
+    ch = orc.sample_challenges(c, seed, 2)
+    rc, tr = orc.prove(c, bytes(range(32)), S, phi, a, b, ch, ntt=True, nthreads=4)
+    assert rc == 0
+    return lb.RuntimeConstants.new(N, R), (S, phi, a, b), ch, tr
+
+
+def test_compact_wire_format_roundtrip(orc):
+    """lab_transcript_pack / lab_transcript_unpack (13-bit coefficients, 2-bit JL entries, 3-bit challenge coefficients): every
+    field of the reference's Transcript (structs.rs:192-209) comes back; int8 and packed matrices give the same bytes."""
+    c, _, ch, tr = _small_transcript(orc)
+    blob = lb.api.transcript_pack(c, tr, ch)
+    ch2 = dict(ch); ch2["pi2"] = lb.api.pack_pi(ch["pi"]); ch2["pi"] = None
+    assert lb.api.transcript_pack(c, tr, ch2) == blob
+    assert blob[:4] == b"LB2C"
+    raw = len(lb.api.transcript_bincode(c, tr, ch))
+    assert len(blob) * 10 < raw                                     # 16-byte i128 per coefficient / JL entry vs 13 / 2 bits
+    got, gch = lb.api.transcript_unpack(c, blob)
+    for k in ("u_1", "projection", "b_prime_prime", "u_2", "z", "t", "g", "h"):
+        assert np.array_equal(got[k], tr[k]), k
+    assert got["jl_attempt"] == tr["jl_attempt"]
+    assert gch["psi"] == ch["psi"]
+    for k in ("omega", "alpha", "beta", "c"):
+        assert np.array_equal(gch[k], ch[k]), k
+    assert np.array_equal(lb.api.unpack_pi(gch["pi2"][0]), ch["pi"][tr["jl_attempt"]])
+    # arbitrary (non challenge-shaped) c falls back to 13 bits; an asymmetric g is refused; truncated input is detected
+    ch3 = dict(ch); ch3["c"] = synth.prg_zq(1, 2, 2 * 64).reshape(2, 64)
+    _, gch3 = lb.api.transcript_unpack(c, lb.api.transcript_pack(c, tr, ch3))
+    assert np.array_equal(gch3["c"], ch3["c"])
+    bad = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in tr.items()}
+    bad["g"][0, 1, 0] = (int(bad["g"][0, 1, 0]) + 1) % Q
+    with pytest.raises(lb.LabError):
+        lb.api.transcript_pack(c, bad, ch)
+    with pytest.raises(lb.LabError):
+        lb.api.transcript_unpack(c, blob[:-5])
+
+
+def test_transcript_gzip_size_metric(orc):
+    """lab_transcript_size_in_bytes = Transcript::size_in_bytes (structs.rs:211-221): gzip(best) of the bincode bytes."""
+    import gzip
+    import zlib
+    c, _, ch, tr = _small_transcript(orc)
+    raw = lb.api.transcript_bincode(c, tr, ch)
+    gz, n = lb.api.transcript_size_in_bytes(c, tr, ch)
+    assert n == len(raw)
+    co = zlib.compressobj(9, zlib.DEFLATED, 31)
+    assert gz == len(co.compress(raw) + co.flush())
+    assert abs(gz - len(gzip.compress(raw, 9, mtime=0))) <= 16      # same deflate stream, header fields aside
+    assert gz < n // 8                                              # 16-byte encodings of 13-bit values compress well
+
+
+def test_fiat_shamir_chain_matches_hashlib():
+    """lab_fs_init / absorb / squeeze against labrador_b200/fs.py (hashlib); SHA-256 itself against the FIPS 180-4 'abc' vector
+    through the chain's primitives (absorb of an all-zero state is SHA256(zeros | label | data))."""
+    import hashlib
+    L = lb._lib.lib()
+    N, R = 2, 3
+    c = lb.RuntimeConstants.new(N, R)
+    phi, a = synth.generate_statement_inputs(N, R, 5)
+    b = synth.prg_zq(5, 99, 64)
+    seed32 = bytes(range(32))
+    st = (ctypes.c_uint8 * 32)()
+    cst = lb._lib.CState(phi.ctypes.data_as(ctypes.c_void_p), a.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p))
+    sb = (ctypes.c_uint8 * 32).from_buffer_copy(seed32)
+    assert L.lab_fs_init(ctypes.byref(c), sb, ctypes.byref(cst), st) == 0
+    want = lb.fs.init(N, R, seed32, phi, a, b)
+    assert bytes(st) == want
+    data = bytes(range(200)) * 3
+    buf = (ctypes.c_uint8 * len(data)).from_buffer_copy(data)
+    assert L.lab_fs_absorb(st, b"u_1", buf, ctypes.c_size_t(len(data))) == 0
+    want = lb.fs.absorb(want, "u_1", data)
+    assert bytes(st) == want
+    for label, idx in (("pi", 0), ("pi", 5), ("agg", 0), ("c", 0)):
+        sd = ctypes.c_uint64(0)
+        assert L.lab_fs_squeeze(st, label.encode(), ctypes.c_uint32(idx), ctypes.byref(sd)) == 0
+        assert sd.value == lb.fs.squeeze(want, label, idx)
+    z = (ctypes.c_uint8 * 32)()
+    m = (ctypes.c_uint8 * 3).from_buffer_copy(b"abc")
+    assert L.lab_fs_absorb(z, b"", m, ctypes.c_size_t(3)) == 0
+    assert bytes(z) == hashlib.sha256(bytes(32) + b"abc").digest()
+    long = bytes(1000)                                              # crosses several 64-byte blocks and the padding boundary cases
+    for n in (0, 1, 23, 24, 55, 56, 63, 64, 119, 120, 1000):
+        z = (ctypes.c_uint8 * 32)()
+        mm = (ctypes.c_uint8 * max(n, 1)).from_buffer_copy(long[:max(n, 1)])
+        assert L.lab_fs_absorb(z, b"", mm, ctypes.c_size_t(n)) == 0
+        assert bytes(z) == hashlib.sha256(bytes(32) + long[:n]).digest(), n
