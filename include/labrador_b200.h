@@ -117,6 +117,9 @@ int lab_ntt_fwd_batch_dev(lab_ctx *ctx, const uint32_t *in, uint32_t *out, size_
 int lab_ntt_inv_batch_dev(lab_ctx *ctx, const uint32_t *in, uint32_t *out, size_t n_polys);
 int lab_polymul_batch_dev(lab_ctx *ctx, const uint32_t *a, const uint32_t *b, uint32_t *c, size_t n_polys);
 void lab_ntt_slot_exponents(int out[32]);
+/* &Rq + &Rq, &Rq - &Rq (algebraic.rs:441-515): coefficientwise mod q on dense polynomials, batched */
+int lab_rq_add_batch(lab_ctx *ctx, const uint32_t *a, const uint32_t *b, uint32_t *c, size_t n_polys);
+int lab_rq_sub_batch(lab_ctx *ctx, const uint32_t *a, const uint32_t *b, uint32_t *c, size_t n_polys);
 /* polynomial_vec_inner_product (util.rs:496-509), batched: out[b] = <v1[b][0..len), v2[b][0..len)> */
 int lab_inner_product_batch(lab_ctx *ctx, const uint32_t *v1, const uint32_t *v2, size_t n_vecs, size_t len, uint32_t *out);
 /* decompose_polynomial (util.rs:389-442): out[k][p][64], k < exp */

@@ -81,11 +81,20 @@ struct State {
 // verifier randomness in consumption order
 struct Challenges {
     std::vector<std::int8_t> pi;      // [n_attempts][R][256][N*64]
+    std::vector<std::uint32_t> pi2;   // the same 2-bit packed, [n_attempts][R][256][N*4]; used instead of pi when not empty
     int n_attempts = 1;
     std::uint32_t psi = 0;
     std::array<std::uint32_t, LAB_JL_ROWS> omega{};
     Poly alpha{}, beta{};
     std::vector<std::uint32_t> c;     // [R][64]
+    lab_challenges raw() const {
+        return lab_challenges{pi2.empty() ? pi.data() : nullptr, n_attempts, psi, omega.data(), alpha.data(), beta.data(), c.data(), pi2.empty() ? nullptr : pi2.data()};
+    }
+    // int8 entries {-1,0,1} -> packed words (lab_pi_pack)
+    void pack() {
+        pi2.resize(pi.size() / 16);
+        if (int rc = lab_pi_pack(pi.data(), pi.size(), pi2.data()); rc != LAB_OK) throw Error(rc, "lab_pi_pack: entries must be in {-1,0,1}");
+    }
 };
 
 // Transcript (structs.rs:192-209)
@@ -110,7 +119,7 @@ class Prover {
         tr.u_1.resize(K * D); tr.u_2.resize(K * D); tr.z.resize(N * D); tr.t_i_all.resize(R * K * D);
         tr.g_mat.resize(R * R * D); tr.h_mat.resize(R * R * D); tr.phi_final.resize(R * N * D);
         lab_state cst{st.phi.data(), st.a.data(), st.b.data()};
-        lab_challenges cch{ch.pi.data(), ch.n_attempts, ch.psi, ch.omega.data(), ch.alpha.data(), ch.beta.data(), ch.c.data()};
+        lab_challenges cch = ch.raw();
         lab_transcript out{tr.u_1.data(), 0, tr.projection_int.data(), tr.projection.data(), tr.b_prime_prime.data(), tr.u_2.data(),
                            tr.z.data(), tr.t_i_all.data(), tr.g_mat.data(), tr.h_mat.data(), tr.phi_final.data(), 0};
         int rc = lab_prove(ctx.get(), &c_, crs.base_seed.data(), witness_.data(), &cst, &cch, &out);
@@ -124,7 +133,7 @@ class Prover {
     // Verifier::verify (verification.rs:25-438): returns the reference's check number that failed, 0 = accepted
     int verify(const Context &ctx, const State &st, const CRS &crs, const Challenges &ch, Transcript &tr) const {
         lab_state cst{st.phi.data(), st.a.data(), st.b.data()};
-        lab_challenges cch{ch.pi.data(), ch.n_attempts, ch.psi, ch.omega.data(), ch.alpha.data(), ch.beta.data(), ch.c.data()};
+        lab_challenges cch = ch.raw();
         lab_transcript in{tr.u_1.data(), tr.jl_attempt, tr.projection_int.data(), tr.projection.data(), tr.b_prime_prime.data(), tr.u_2.data(),
                           tr.z.data(), tr.t_i_all.data(), tr.g_mat.data(), tr.h_mat.data(), nullptr, 0};
         int accepted = 0, failed = 0;
@@ -132,9 +141,18 @@ class Prover {
         ctx.check(lab_verify(ctx.get(), &c_, crs.base_seed.data(), &cst, &cch, &in, &accepted, &failed, &norm));
         return accepted ? 0 : failed;
     }
+    // Transcript::size_in_bytes (structs.rs:211-221): gzip(best) of the bincode bytes
+    std::size_t size_in_bytes(const Challenges &ch, Transcript &tr) const {
+        lab_challenges cch = ch.raw();
+        lab_transcript in{tr.u_1.data(), tr.jl_attempt, tr.projection_int.data(), tr.projection.data(), tr.b_prime_prime.data(), tr.u_2.data(),
+                          tr.z.data(), tr.t_i_all.data(), tr.g_mat.data(), tr.h_mat.data(), nullptr, 0};
+        std::size_t gz = 0, raw = 0;
+        if (int rc = lab_transcript_size_in_bytes(&c_, &in, &cch, &gz, &raw); rc != LAB_OK) throw Error(rc, "lab_transcript_size_in_bytes");
+        return gz;
+    }
     // bincode::serialize(&Transcript) (structs.rs:192-221)
     std::vector<std::uint8_t> to_bincode(const Challenges &ch, Transcript &tr) const {
-        lab_challenges cch{ch.pi.data(), ch.n_attempts, ch.psi, ch.omega.data(), ch.alpha.data(), ch.beta.data(), ch.c.data()};
+        lab_challenges cch = ch.raw();
         lab_transcript in{tr.u_1.data(), tr.jl_attempt, tr.projection_int.data(), tr.projection.data(), tr.b_prime_prime.data(), tr.u_2.data(),
                           tr.z.data(), tr.t_i_all.data(), tr.g_mat.data(), tr.h_mat.data(), nullptr, 0};
         std::size_t size = 0;

@@ -896,6 +896,11 @@ static int d_jl(lab_ctx *ctx, const uint32_t *dPi2, const uint32_t *dS, uint64_t
     CK(cudaMemsetAsync(dp, 0, LAB_JL_ROWS * sizeof(unsigned long long), ctx->stream));
     if (!ni) return LAB_OK;
     if (ND / 16 >= (1ull << 26) || i0 + ni >= (1ull << 32)) FAIL(LAB_ERR_PARAMS, "JL: shape exceeds 32-bit word indexing");
+    if (ni * ND <= ((uint64_t)1 << 14)) {            // small proofs (up to (16,16)): thread-per-row kernel without tables
+        const uint64_t cpv = (ND + JL2S_CH - 1) / JL2S_CH;
+        LAUNCH(k_jl2_small, (unsigned)(ni * cpv), 256, dPi2, dS, ND, (uint32_t)(ND / 16), (uint32_t)i0, (uint32_t)cpv, dp);
+        return LAB_OK;
+    }
     const uint64_t upv = (ND + JL2_UNIT - 1) / JL2_UNIT, total = ni * upv;
     // persistent CTAs, three per SM (64 KB of tables each); a lane's int32 row accumulators take 2^14 units of at most 2^17 each
     uint64_t grid = std::min<uint64_t>(total, (uint64_t)ctx->sms * 3);
@@ -980,6 +985,19 @@ extern "C" int lab_polymul_batch(lab_ctx *ctx, const uint32_t *a, const uint32_t
     TRY(download(ctx, c, dc, n * 64));
     return lab_sync(ctx);
 }
+static int rq_addsub(lab_ctx *ctx, const uint32_t *a, const uint32_t *b, uint32_t *c, size_t n, int sub) {
+    CallScope cs(ctx);
+    if (!n) return LAB_OK;
+    uint32_t *da, *db, *dc;
+    TRY(upload(ctx, a, n * 64, &da));
+    TRY(upload(ctx, b, n * 64, &db));
+    TRY(arena_alloc(ctx, n * 64, &dc));
+    LAUNCH(k_rq_addsub, grid_for(n * 64, 1024, ctx->sms * 16), 256, da, db, dc, n * 64, sub);
+    TRY(download(ctx, c, dc, n * 64));
+    return lab_sync(ctx);
+}
+extern "C" int lab_rq_add_batch(lab_ctx *ctx, const uint32_t *a, const uint32_t *b, uint32_t *c, size_t n) { return rq_addsub(ctx, a, b, c, n, 0); }
+extern "C" int lab_rq_sub_batch(lab_ctx *ctx, const uint32_t *a, const uint32_t *b, uint32_t *c, size_t n) { return rq_addsub(ctx, a, b, c, n, 1); }
 extern "C" int lab_inner_product_batch(lab_ctx *ctx, const uint32_t *v1, const uint32_t *v2, size_t n_vecs, size_t len, uint32_t *out) {
     CallScope cs(ctx);
     if (!n_vecs) return LAB_OK;

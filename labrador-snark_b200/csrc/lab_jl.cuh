@@ -175,6 +175,32 @@ __global__ void __launch_bounds__(JL2_THREADS, 3) k_jl2(const uint32_t *__restri
     if (acc[0]) atomicAdd(p + w * 32 + lane, (unsigned long long)(long long)acc[0]);
 }
 
+// Small shapes (a default-size proof has 2 x 256 x 128 entries): the table machinery above would be all set-up.  One CTA per
+// (vector, chunk of 1024 coefficients), thread = row; the chunk of s sits in 4 KB of static shared memory (every thread reads
+// the same coefficient at the same time: a broadcast), the row's words come straight from global memory.
+constexpr int JL2S_CH = 1024;
+__global__ void __launch_bounds__(256) k_jl2_small(const uint32_t *__restrict__ pi2, const uint32_t *__restrict__ S, uint64_t ND, uint32_t W, uint32_t i0,
+                                                   uint32_t chunks_per_vec, unsigned long long *__restrict__ p) {
+    __shared__ uint32_t ss[JL2S_CH];
+    const uint32_t li = blockIdx.x / chunks_per_vec, ch = blockIdx.x % chunks_per_vec;
+    const uint64_t c0 = (uint64_t)ch * JL2S_CH;
+    const uint32_t len = (uint32_t)min((uint64_t)JL2S_CH, ND - c0);            // multiple of 64
+    for (uint32_t t = threadIdx.x; t < len; t += 256) ss[t] = lab_canon(S[(uint64_t)(i0 + li) * ND + c0 + t]);
+    __syncthreads();
+    const uint32_t *row = pi2 + ((uint64_t)li * 256 + threadIdx.x) * W + c0 / 16;
+    int acc = 0;
+    for (uint32_t wq = 0; wq < len / 16; wq++) {
+        const uint32_t x = __ldg(row + wq);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int sv = (int)ss[wq * 16 + k];
+            acc += ((x >> k) & 1u) ? sv : 0;
+            acc -= ((x >> (16 + k)) & 1u) ? sv : 0;
+        }
+    }
+    if (acc) atomicAdd(p + threadIdx.x, (unsigned long long)(long long)acc);
+}
+
 // v[i][c] = sum_j omega_j Pi_i[j][c] mod q from packed words.  total_words = R * W.
 __global__ void __launch_bounds__(256) k_piT_omega2(const uint32_t *__restrict__ pi2, const uint32_t *__restrict__ omega, uint64_t total_words, uint32_t W,
                                                     uint32_t *__restrict__ v) {

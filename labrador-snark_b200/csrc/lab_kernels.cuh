@@ -385,6 +385,15 @@ __global__ void k_addsub_hats(const uint32_t *__restrict__ X, const uint32_t *__
     out[idx] = lab_pack(lab_canon(r), lab_canon(i));
 }
 
+// c = a + b or a - b, coefficientwise mod Q (algebraic.rs:441-515)
+__global__ void k_rq_addsub(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b, uint32_t *__restrict__ c, size_t n, int sub) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; idx < n; idx += stride) {
+        const uint32_t x = lab_canon(a[idx]), y = lab_canon(b[idx]);
+        c[idx] = lab_csub(sub ? x + LABQ - y : x + y);
+    }
+}
 // exact sum of squares of canonical representatives (util.rs:195-202)
 __global__ void __launch_bounds__(256) k_norm_sq(const uint32_t *__restrict__ in, size_t n, unsigned long long *out) {
     unsigned long long acc = 0;

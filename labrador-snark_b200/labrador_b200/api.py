@@ -321,6 +321,16 @@ class Context:
         self._ck(self.L.lab_polymul_batch(self._h, _p(a), _p(b), _p(out), C.c_size_t(a.shape[0])))
         return out
 
+    def rq_add_batch(self, a, b, sub=False):
+        """&Rq + &Rq / &Rq - &Rq (algebraic.rs:441-515), batched."""
+        a, b = _u32(a).reshape(-1, D), _u32(b).reshape(-1, D)
+        if a.shape != b.shape:
+            raise LabError(3, "rq_add_batch: shape mismatch")
+        out = np.empty_like(a)
+        f = self.L.lab_rq_sub_batch if sub else self.L.lab_rq_add_batch
+        self._ck(f(self._h, _p(a), _p(b), _p(out), C.c_size_t(a.shape[0])))
+        return out
+
     def inner_product_batch(self, v1, v2):
         """polynomial_vec_inner_product (util.rs:496-509) for a batch: v1, v2 [B][len][64] -> [B][64]."""
         v1, v2 = _u32(v1), _u32(v2)

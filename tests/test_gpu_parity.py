@@ -525,10 +525,11 @@ def test_generate_then_contract_counter_boundaries(ctx, orc, low, monkeypatch):
 
 
 # ---- round 2: 2-bit packed JL matrices (lab_jl.cuh), sharded stage forms, BASELINE shapes, larger / non-square proofs ----
-@pytest.mark.parametrize("N,R", [(1, 1), (2, 3), (7, 3), (8, 2), (9, 2), (33, 5), (70, 2)])
+@pytest.mark.parametrize("N,R", [(1, 1), (2, 3), (7, 3), (8, 2), (9, 2), (33, 5), (70, 2), (33, 9), (70, 4), (129, 3), (256, 2)])
 def test_packed_jl_matches_int8_and_oracle(ctx, orc, N, R):
     """lab_jl_project2 / lab_aggregate_phi2 on the packed matrices == the int8 entry points == the oracle (proofgen.rs:429-457,
-    :244-253).  N = 7, 9, 33, 70 leave the last 512-coefficient unit of the table kernel ragged."""
+    :244-253).  Up to 2^14 coefficients the thread-per-row kernel runs, above it the table kernel: N = 33, 70, 129 leave its
+    last 512-coefficient unit ragged, (256, 2) fills its units exactly."""
     c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
     co, _ = orc.constants(N, R)
     S = synth.uniform_witness(N, R, seed=31 * N + R)
@@ -879,3 +880,43 @@ def test_fiat_shamir_proof_matches_oracle(ctx, orc, N, R):
     got, _ = lb.api.transcript_unpack(c, lb.api.transcript_pack(c, tr, chg))
     got["projection_int"] = tr["projection_int"]
     assert ctx.verify_fs(c, SEED32, phi, a, b, got)[0] is True
+
+
+def test_rq_add_sub(ctx):
+    """&Rq + &Rq and &Rq - &Rq (algebraic.rs:441-515): coefficientwise mod q, also on non-canonical input."""
+    a = np.concatenate([rand_polys(200, 21), edge_polys()])
+    b = np.concatenate([rand_polys(200, 22), edge_polys()[::-1]])
+    assert np.array_equal(ctx.rq_add_batch(a, b), ((a.astype(np.uint64) + b) % Q).astype(np.uint32))
+    assert np.array_equal(ctx.rq_add_batch(a, b, sub=True), ((a.astype(np.int64) - b) % Q).astype(np.uint32))
+    assert np.array_equal(ctx.rq_add_batch(a + np.uint32(5 * Q), b), ((a.astype(np.uint64) + b) % Q).astype(np.uint32))
+
+
+def test_cpp_header_runs_a_proof(ctx, orc, tmp_path):
+    """tests/cpp/test_labrador_hpp.cpp: Prover::proof_gen / verify / to_bincode / size_in_bytes through cpp/labrador.hpp (compiled
+    here with g++) against the oracle's transcript of the same inputs, int8 and packed challenges, a tampered u_2 -> check 20."""
+    from test_host import build_cpp_test
+    exe = build_cpp_test(tmp_path)
+    N, R = 2, 2
+    co, S, phi, a, b, ch = full_case(orc, N, R, seed=7100, n_attempts=2)
+    c = lb.RuntimeConstants.new(N, R)
+    rc, ref = orc.prove(co, SEED32, S, phi, a, b, ch, ntt=True, nthreads=8)
+    assert rc == 0
+    blob = lb.api.transcript_bincode(c, ref, ch)
+    case = tmp_path / "case.bin"
+    with open(case, "wb") as f:
+        f.write(np.array([N, R, 2, ref["jl_attempt"]], np.uint64).tobytes())
+        f.write(SEED32)
+        for arr in (S, phi, a, b):
+            f.write(np.ascontiguousarray(arr, np.uint32).tobytes())
+        f.write(np.ascontiguousarray(ch["pi"], np.int8).tobytes())
+        f.write(np.array([ch["psi"]], np.uint32).tobytes())
+        for k in ("omega", "alpha", "beta", "c"):
+            f.write(np.ascontiguousarray(ch[k], np.uint32).tobytes())
+        for k in ("u_1", "u_2", "z", "t", "g", "h"):
+            f.write(np.ascontiguousarray(ref[k], np.uint32).tobytes())
+        f.write(np.ascontiguousarray(ref["projection_int"], np.int64).tobytes())
+        f.write(np.ascontiguousarray(ref["b_prime_prime"], np.uint32).tobytes())
+        f.write(np.array([len(blob)], np.uint64).tobytes())
+    import subprocess
+    out = subprocess.run([exe, str(case)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr

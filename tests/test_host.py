@@ -482,3 +482,42 @@ def test_fiat_shamir_chain_matches_hashlib():
         mm = (ctypes.c_uint8 * max(n, 1)).from_buffer_copy(long[:max(n, 1)])
         assert L.lab_fs_absorb(z, b"", mm, ctypes.c_size_t(n)) == 0
         assert bytes(z) == hashlib.sha256(bytes(32) + long[:n]).digest(), n
+
+
+def build_cpp_test(tmpdir):
+    """g++ -std=c++17 of tests/cpp/test_labrador_hpp.cpp against cpp/labrador.hpp and the product library."""
+    exe = os.path.join(str(tmpdir), "test_labrador_hpp")
+    libdir = os.path.dirname(os.path.abspath(lb.SO_PATH))
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_labrador_hpp.cpp"),
+                           f"-L{libdir}", "-llabrador_b200", f"-Wl,-rpath,{libdir}"])
+    return exe
+
+
+def test_cpp_header_compiles_and_host_checks_pass(tmp_path):
+    """cpp/labrador.hpp (C++ host mirror of the reference API) compiles warning-free against the C ABI; the checks that need no
+    GPU (RuntimeConstants, degenerate shapes refused, lab_pi_pack) run here, the proof itself in the GPU suite."""
+    exe = build_cpp_test(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_rust_sys_crate_matches_the_header():
+    """rust/labrador-b200-sys/src/lib.rs is generated from include/labrador_b200.h (tools/gen_rust_sys.py): stale output fails."""
+    subprocess.check_call([sys.executable, os.path.join(PKG, "tools", "gen_rust_sys.py"), "--check"])
+    src = open(os.path.join(PKG, "rust", "labrador-b200-sys", "src", "lib.rs")).read()
+    for sym in lb.SYMBOLS:
+        assert re.search(rf"\bpub fn {sym}\(", src), sym
+    wrapper = open(os.path.join(PKG, "rust", "labrador-b200", "src", "lib.rs")).read()
+    for sig in ("pub fn new(witness: &'a Array2<Rq>, verifier: &'a Verifier<'a>, constants: &'a RuntimeConstants) -> Self",      # proofgen.rs:26
+                "pub fn proof_gen(&mut self, st: &State, crs: &mut CRS) -> Transcript",                                            # proofgen.rs:30
+                "pub fn jl_project(&mut self) -> (Vec<i128>, Vec<Array2<Zq>>)",                                                    # proofgen.rs:429
+                "pub fn generate_witness(constants: &RuntimeConstants) -> Array2<Rq>",                                             # proofgen.rs:460
+                "pub fn new(witness: &Array2<Rq>, constants: &RuntimeConstants) -> Self",                                          # structs.rs:352
+                "pub fn new(b_prime_k: Vec<Zq>, constants: &'a RuntimeConstants) -> Self",                                         # verification.rs:18
+                "pub fn verify(&self, st: &State, proof: &Transcript, crs: &mut CRS) -> bool",                                     # verification.rs:25
+                "pub fn polynomial_vec_inner_product(v1: &[Rq], v2: &[Rq]) -> Rq",                                                 # util.rs:496
+                "pub fn decompose_polynomial(p: &Rq, base: i128, exp: i128) -> Vec<Rq>",                                           # util.rs:389
+                "pub fn size_in_bytes(&self) -> usize"):                                                                           # structs.rs:212
+        assert sig in wrapper, sig
+    for f in re.findall(r"sys::(lab_[a-z0-9_]+)", wrapper):                     # every call of the wrapper exists in the sys crate
+        assert re.search(rf"\bpub fn {f}\(", src) or f in ("lab_ctx", "lab_constants", "lab_state", "lab_challenges", "lab_transcript"), f
