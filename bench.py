@@ -126,6 +126,44 @@ def cpu_sample(N, R, rows, nthreads):
     return dt, int(np.asarray(T, dtype=np.uint64).sum() & 0xFFFFFFFF)
 
 
+def measure_ntt(ctx, torch, dev, traffic_of):
+    """Batched R_q NTT / INTT / fused polymul on 2^22 polynomials (BASELINE config 2 at one size; `--workload cfg2` is the sweep).
+    Runs at the START of the default bench: measured after a minute of ChaCha20 at full power the same launch read 20 % lower in
+    a round-2 run (5272 GB/s against 6483 GB/s in `--workload cfg2` on the same box) -- its integer work is about as long as its
+    HBM time, so it is sensitive to the SM clock the power management leaves it."""
+    # batched R_q NTT (BASELINE config 2): 2^22 polys, 512 algorithmic bytes per poly
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    npoly = 1 << 22
+    a = torch.empty((npoly, D), dtype=torch.int32, device=dev)
+    b = torch.empty((npoly, D), dtype=torch.int32, device=dev)
+    o = torch.empty((npoly, D), dtype=torch.int32, device=dev)
+    ctx.synth_zq_dev(PRG_SEED, 20, 0, npoly * D, a.data_ptr())
+    ctx.synth_zq_dev(PRG_SEED, 21, 0, npoly * D, b.data_ptr())
+    res = {}
+    for name, fn, bpp in (("ntt_fwd", lambda: ctx.ntt_fwd_batch_dev(a.data_ptr(), o.data_ptr(), npoly), 512),
+                          ("ntt_inv", lambda: ctx.ntt_inv_batch_dev(a.data_ptr(), o.data_ptr(), npoly), 512),
+                          ("polymul", lambda: ctx.polymul_batch_dev(a.data_ptr(), b.data_ptr(), o.data_ptr(), npoly), 768)):
+        for _ in range(3):
+            fn()
+        ctx.sync()
+        tt = []
+        for _ in range(5):
+            ctx.timer_start(); fn(); tt.append(ctx.timer_stop())
+        t = sorted(tt)[len(tt) // 2]
+        res[name] = {"polys_per_s": npoly / (t * 1e-3), "GBps": npoly * bpp / (t * 1e-3) / 1e9, "ms": t}
+    roof_ntt = {"kernel": "k_ntt_fwd_regs", "bound": "hbm", "achieved": res["ntt_fwd"]["GBps"], "peak": hbm, "unit": "GB/s",
+                "frac": res["ntt_fwd"]["GBps"] / hbm, "traffic": traffic_of("k_ntt_fwd_regs", True),
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "log2_polys": 22, "operands_exceed_L2": True}
+    del a, b, o
+    return res, roof_ntt
+
+
 def sharded_prove_check(ctx, lb, rank, world, dev, dist):
     """One full Prover::proof_gen + Verifier::verify of the seeded (8, 8) statement of tests/golden/prove_8_8.json through
     lab_prove / lab_verify on `ctx`.  With a communicator attached (world > 1) the library shards rows of A / u_1 / u_2 and the
@@ -395,7 +433,7 @@ def run_cfg1(args, rank, world, local_rank):
             "roofline": {"kernel": "k_crs_matvec", "bound": "int32_alu", "achieved": first["chacha_blocks_per_s_prove"] * ALU_OPS_PER_BLOCK / 1e9, "peak": ctx.alu_peak() / 1e9,
                          "unit": "Gop/s", "frac": first["chacha_blocks_per_s_prove"] * ALU_OPS_PER_BLOCK / ctx.alu_peak(), "traffic": None,
                          "note": "whole-proof CRS coefficients x 596 ALU ops over the whole prove() wall time (launch latency included)"},
-            "cpu_baseline": cpu, "extra": {"sweep": tab}}
+            "cpu_baseline": cpu, "extra": {"sweep": tab, "proof_graphs": ctx.graph_stats()}}
     _finish_line(line, rank, world)
     ctx.close()
 
@@ -519,8 +557,9 @@ def run_cfg5(args, rank, world, local_rank):
 
     def run():
         for shared in (False, True):
-            for _ in range(max(1, args.warmup // 2)):
-                ctx.prove_batch(c, seeds, shared, Sb[:8], phib[:8], ab[:8], bb[:8], chs[:8])
+            ctx.prove_batch(c, seeds, shared, Sb[:8], phib[:8], ab[:8], bb[:8], chs[:8])      # first proof of the shape per worker: ordinary path, sizes the arena
+            for _ in range(max(1, args.warmup // 2)):                                        # then whole batches (graphs recorded, clocks up)
+                ctx.prove_batch(c, seeds, shared, Sb, phib, ab, bb, chs)
             ts, tw = [], []
             for _ in range(args.steps):
                 if world > 1:
@@ -533,7 +572,8 @@ def run_cfg5(args, rank, world, local_rank):
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             res["shared" if shared else "per_statement"] = {"s_per_batch": float(t[0].item()), "proofs_per_s": total / float(t[0].item()),
-                                                            "s_per_batch_incl_python_marshalling": float(t[1].item())}
+                                                            "s_per_batch_incl_python_marshalling": float(t[1].item()),
+                                                            "s_per_batch_each_step_this_rank": [round(x, 4) for x in ts]}
             res["out_shared" if shared else "out_per_statement"] = out
     _, clocks = _clock_wrap(local_rank, run)
     cpu = None
@@ -565,7 +605,7 @@ def run_cfg5(args, rank, world, local_rank):
             "e2e": {"value": per["proofs_per_s"], "unit": "proofs/s", "h2d_bytes_per_step": int(Sb.nbytes + phib.nbytes + ab.nbytes + bb.nbytes),
                     "d2h_bytes_per_step": nb * (128 * 2 + 128 * 2 + 16) * 256, "note": "lab_prove_batch takes host buffers: the timed C call is the end-to-end path (ctypes marshalling of 1024 structs excluded, reported in extra)"},
             "gpu_launches": None, "clocks": clocks, "roofline": None, "cpu_baseline": cpu,
-            "extra": {"shared_crs_seed_variant": res["shared"], "per_statement_seed_variant": per}}
+            "extra": {"shared_crs_seed_variant": res["shared"], "per_statement_seed_variant": per, "proof_graphs": ctx.graph_stats()}}
     _finish_line(line, rank, world)
     if world > 1:
         dist.destroy_process_group()
@@ -605,6 +645,13 @@ def main():
     N, R = workload_shape(args.workload)
     c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
     kappa, ND = c.KAPPA, N * D
+    ntt_res = roof_ntt = None
+    if rank == 0 and os.environ.get("LAB_BENCH_LIGHT") != "1":
+        try:
+            tdb = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
+        except Exception:
+            tdb = {}
+        ntt_res, roof_ntt = measure_ntt(ctx, torch, dev, lambda k, ok: (lambda d: d["dram_bytes_read_per_launch"] + d["dram_bytes_write_per_launch"] if d and ok else None)(tdb.get(k)))
 
     # ---- shards (strong scaling): rows of A / T, rows of g, witness vectors for JL and z ----
     pl = lb.shard.plan(kappa, R, world, rank)
@@ -613,6 +660,7 @@ def main():
     # measured on the first 1/rows_div of every rank's commitment rows and the step time is extrapolated linearly in the
     # rows (the commitment is 99.9 % of the step and exactly linear in them); SURVEY 8d asks for that labelling.
     rows_div = int(os.environ.get("LAB_BENCH_ROWS_DIV", "64" if args.workload == "cfg4" else "1"))
+    light = os.environ.get("LAB_BENCH_LIGHT") == "1"          # long shapes (cfg 4 on all rows): no re-runs of the commitment, no extras, warm-up as given
     nrows_full = nrows
     nrows = max(1, nrows // rows_div) if nrows else 0
     if args.workload == "cfg4":
@@ -667,7 +715,7 @@ def main():
             torch.cuda.synchronize()
 
     # ---- warm-up, then K timed steps (CUDA events on the library stream) ----
-    for _ in range(max(args.warmup, 1)):
+    for _ in range(args.warmup if light else max(args.warmup, 1)):
         step()
     barrier()
     sampler = ClockSampler(local_rank)
@@ -708,7 +756,7 @@ def main():
         sharded = {"error": repr(e), "matches_oracle": False}
 
     # ---- per-kernel numbers for the roofline (rank 0, kernel timed alone, same shard) ----
-    roof = roof_ntt = extra = None
+    roof = extra = None
     # DRAM bytes per launch from the committed ncu capture of this very command (profiles/ncu_traffic_r1.json);
     # only quoted when the launch shape is the captured one
     try:
@@ -721,13 +769,39 @@ def main():
         if not d or not ok:
             return None
         return d["dram_bytes_read_per_launch"] + d["dram_bytes_write_per_launch"]
+    # cfg 4: T stays sharded and is never gathered -- report the sum of all its coefficients mod 2^64 over all ranks (int64
+    # ncclSum inside the library) and check two rows of every rank's shard against the oracle
+    cfg4_checks = None
+    if args.workload == "cfg4":
+        stats.fill_(int(T.sum(dtype=torch.int64).item()))
+        torch.cuda.current_stream().synchronize()
+        ctx.comm_allreduce_i64_dev(stats.data_ptr(), 1)
+        ctx.sync()
+        cfg4_checks = {"T_checksum_mod_2_64": int(stats.item()) & 0xFFFFFFFFFFFFFFFF, "rows_summed": kappa if rows_div == 1 else f"first 1/{rows_div} of every rank's rows"}
+        if not args.no_cpu:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import oracle
+            co4 = oracle.constants(N, R)[0]
+            S_host = S.cpu().numpy().view(np.uint32)
+            okr = []
+            for rr in sorted({0, nrows - 1}):
+                ref = oracle.commit_inner_rows(co4, SEED32, S_host, row0 + rr, 1, ntt=True, nthreads=max(1, oracle.num_threads() // world))
+                okr.append(bool(np.array_equal(ref[:, 0], T[:, rr].cpu().numpy().view(np.uint32))))
+            flag = torch.tensor([int(all(okr))], dtype=torch.int64, device=dev)
+            stats.copy_(flag)
+            torch.cuda.current_stream().synchronize()
+            ctx.comm_allreduce_i64_dev(stats.data_ptr(), 1)
+            ctx.sync()
+            cfg4_checks["oracle_rows_checked_per_rank"] = len(okr)
+            cfg4_checks["ranks_whose_rows_match_the_oracle"] = int(stats.item())
+            del S_host
     if rank == 0:
         reps = []
-        for _ in range(2):
+        for _ in range(0 if light else 2):
             ctx.timer_start()
             ctx.commit_inner_dev(SEED32, row0, nrows, T.data_ptr())
             reps.append(ctx.timer_stop())
-        k_ms = min(reps)
+        k_ms = min(reps) if reps else ms_step_measured
         blocks = nrows * N * D
         alu_peak = ctx.alu_peak()                                            # lane-ops/s, LOP3 + SHF
         achieved = blocks * ALU_OPS_PER_BLOCK / (k_ms * 1e-3)
@@ -750,7 +824,7 @@ def main():
         # first commitment writes A through to HBM as int8 limb planes (137 GB at cfg 3); the next one under the same CRS is
         # the tcgen05 contraction of lab_umma.cuh, which streams A once
         crs_cached = None
-        if world == 1:
+        if world == 1 and not light:
             try:
                 ctx.crs_cache_configure(0)                       # releases the cold path's transient limb planes first
                 free_b, _tot = torch.cuda.mem_get_info(dev)
@@ -775,68 +849,43 @@ def main():
                 crs_cached = {"error": repr(e)}
             finally:
                 ctx.crs_cache_configure(0)
-        # batched R_q NTT (BASELINE config 2): 2^22 polys, 512 algorithmic bytes per poly
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm = float(peaks.get("hbm_gbs", 6650.0))
-        npoly = 1 << 22
-        a = torch.empty((npoly, D), dtype=torch.int32, device=dev)
-        b = torch.empty((npoly, D), dtype=torch.int32, device=dev)
-        o = torch.empty((npoly, D), dtype=torch.int32, device=dev)
-        ctx.synth_zq_dev(PRG_SEED, 20, 0, npoly * D, a.data_ptr())
-        ctx.synth_zq_dev(PRG_SEED, 21, 0, npoly * D, b.data_ptr())
-        res = {}
-        for name, fn, bpp in (("ntt_fwd", lambda: ctx.ntt_fwd_batch_dev(a.data_ptr(), o.data_ptr(), npoly), 512),
-                              ("ntt_inv", lambda: ctx.ntt_inv_batch_dev(a.data_ptr(), o.data_ptr(), npoly), 512),
-                              ("polymul", lambda: ctx.polymul_batch_dev(a.data_ptr(), b.data_ptr(), o.data_ptr(), npoly), 768)):
-            for _ in range(3):
-                fn()
-            ctx.sync()
-            tt = []
-            for _ in range(5):
-                ctx.timer_start(); fn(); tt.append(ctx.timer_stop())
-            t = sorted(tt)[len(tt) // 2]
-            res[name] = {"polys_per_s": npoly / (t * 1e-3), "GBps": npoly * bpp / (t * 1e-3) / 1e9, "ms": t}
-        roof_ntt = {"kernel": "k_ntt_fwd_regs", "bound": "hbm", "achieved": res["ntt_fwd"]["GBps"], "peak": hbm, "unit": "GB/s",
-                    "frac": res["ntt_fwd"]["GBps"] / hbm, "traffic": traffic_of("k_ntt_fwd_regs", True),
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                    "log2_polys": 22, "operands_exceed_L2": True}
-        extra = {"ntt": res, "crs_resident": crs_cached, "sharded_prove": sharded}
-        del a, b, o
-        # default-size full prove() (BASELINE config 1 shape), ms per proof through the host API
-        try:
-            from labrador_b200 import synth
-            c2 = lb.RuntimeConstants.new(2, 2)
-            S2 = synth.generate_witness(2, 2, c2.BETA_BOUND, PRG_SEED)
-            st2 = lb.State.new(S2, c2, PRG_SEED, ctx)
-            ver = lb.Verifier.new(st2.b_prime_k, c2, seed=PRG_SEED, n_attempts=6)
-            prover = lb.Prover.new(S2, ver, c2, ctx)
-            crs = lb.CRS.from_seed(c2, SEED32, ctx)
-            for _ in range(3):       # warm-up (the scratch arena is sized after the first call)
-                prover.proof_gen(st2, crs)
-            t0 = time.perf_counter()
-            for _ in range(5):
-                prover.proof_gen(st2, crs)
-            extra["prove_default_N2_R2_ms"] = (time.perf_counter() - t0) / 5 * 1e3
-            tr2 = prover.proof_gen(st2, crs)
-            t0 = time.perf_counter()
-            okv = ctx.verify(c2, SEED32, st2.phi_k[0], st2.a_k[0], st2.b_k[0], ver.challenges, tr2.as_oracle_dict())
-            extra["verify_default_N2_R2_ms"] = (time.perf_counter() - t0) * 1e3
-            extra["verify_default_accepts"] = bool(okv[0])
-            # BASELINE config 5 flavour: independent default-size statements on this GPU (per-statement CRS seeds)
-            nb = 128
-            Sb = np.stack([S2] * nb); phib = np.stack([st2.phi_k[0]] * nb); ab_ = np.stack([st2.a_k[0]] * nb); bb = np.stack([st2.b_k[0]] * nb)
-            seeds = [bytes([i]) * 32 for i in range(nb)]
-            ctx.prove_batch(c2, seeds, False, Sb[:8], phib[:8], ab_[:8], bb[:8], [ver.challenges] * 8)
-            ctx.prove_batch(c2, seeds, False, Sb[:8], phib[:8], ab_[:8], bb[:8], [ver.challenges] * 8)
-            t0 = time.perf_counter()
-            ctx.prove_batch(c2, seeds, False, Sb, phib, ab_, bb, [ver.challenges] * nb)
-            extra["batch_default_proofs_per_s_per_gpu"] = nb / (time.perf_counter() - t0)
-        except Exception as e:       # reported, never hidden
-            extra["prove_default_error"] = repr(e)
+        extra = {"sharded_prove": sharded}
+        if not light:
+            extra.update({"ntt": ntt_res, "crs_resident": crs_cached})
+            # default-size full prove() (BASELINE config 1 shape), ms per proof through the host API
+            try:
+                from labrador_b200 import synth
+                c2 = lb.RuntimeConstants.new(2, 2)
+                S2 = synth.generate_witness(2, 2, c2.BETA_BOUND, PRG_SEED)
+                st2 = lb.State.new(S2, c2, PRG_SEED, ctx)
+                ver = lb.Verifier.new(st2.b_prime_k, c2, seed=PRG_SEED, n_attempts=6)
+                prover = lb.Prover.new(S2, ver, c2, ctx)
+                crs = lb.CRS.from_seed(c2, SEED32, ctx)
+                for _ in range(3):       # warm-up (the scratch arena is sized after the first call)
+                    prover.proof_gen(st2, crs)
+                t0 = time.perf_counter()
+                for _ in range(5):
+                    prover.proof_gen(st2, crs)
+                extra["prove_default_N2_R2_ms"] = (time.perf_counter() - t0) / 5 * 1e3
+                tr2 = prover.proof_gen(st2, crs)
+                t0 = time.perf_counter()
+                okv = ctx.verify(c2, SEED32, st2.phi_k[0], st2.a_k[0], st2.b_k[0], ver.challenges, tr2.as_oracle_dict())
+                extra["verify_default_N2_R2_ms"] = (time.perf_counter() - t0) * 1e3
+                extra["verify_default_accepts"] = bool(okv[0])
+                # BASELINE config 5 flavour: independent default-size statements on this GPU (per-statement CRS seeds)
+                nb = 128
+                Sb = np.stack([S2] * nb); phib = np.stack([st2.phi_k[0]] * nb); ab_ = np.stack([st2.a_k[0]] * nb); bb = np.stack([st2.b_k[0]] * nb)
+                seeds = [bytes([i]) * 32 for i in range(nb)]
+                ctx.prove_batch(c2, seeds, False, Sb[:8], phib[:8], ab_[:8], bb[:8], [ver.challenges] * 8)
+                ctx.prove_batch(c2, seeds, False, Sb[:8], phib[:8], ab_[:8], bb[:8], [ver.challenges] * 8)
+                t0 = time.perf_counter()
+                ctx.prove_batch(c2, seeds, False, Sb, phib, ab_, bb, [ver.challenges] * nb)
+                extra["batch_default_proofs_per_s_per_gpu"] = nb / (time.perf_counter() - t0)
+            except Exception as e:       # reported, never hidden
+                extra["prove_default_error"] = repr(e)
+
+        if cfg4_checks is not None:
+            extra["cfg4_checks"] = cfg4_checks
 
     # ---- end to end through the host-buffer C ABI ----
     e2e = None

@@ -253,6 +253,12 @@ int lab_verify(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], con
  * between calls (lab_crs_cache_configure(ctx, 0) is the "give the memory back" call). */
 int lab_crs_cache_configure(lab_ctx *ctx, size_t max_bytes);
 int lab_crs_cache_stats(const lab_ctx *ctx, size_t *bytes_used, uint64_t *hits, uint64_t *misses);
+/* Small shapes (inputs + outputs of a proof within a few MB; (2,2) ... (8,8)) run lab_prove as ONE CUDA graph from the second
+ * proof of a shape on: one H2D copy of a pinned input block, every stage of one JL attempt with the outer commitment u_1 on a
+ * forked branch, one D2H copy of the output block; the CRS seed is patched into the recorded kernels per replay.  Same bits as
+ * the ordinary path.  LAB_NO_GRAPH=1 disables it.  Counters (this ctx and its batch workers): graphs built, replays, and
+ * whether a recording was abandoned (the ordinary path is used then). */
+int lab_graph_stats(const lab_ctx *ctx, uint64_t *graphs, uint64_t *replays, int *failed);
 
 /* ---- transcript wire format (structs.rs:192-221) ----
  * The bytes `bincode::serialize(&Transcript)` produces in the reference (bincode 1.3.3 defaults: fixed-width little-endian

@@ -86,6 +86,8 @@ struct lab_ctx {
     std::vector<std::unique_ptr<ProofGraph>> graphs;
     std::vector<std::array<uint64_t, 3>> graph_seen;
     bool graph_failed = false;
+    uint64_t graph_replays = 0;
+    std::string graph_fail_reason;
     // CRS cache (lab_crs_cache_configure): hats of the CRS polynomials a K_MV call generated, kept in HBM and re-used by
     // later calls with the same seed, item list and row range (the verifier right after the prover; further proofs under
     // the same CRS).  Bit-identical results; off by default so that a proof regenerates its CRS like the reference does.
@@ -1452,6 +1454,8 @@ static ProofGraph *graph_build(lab_ctx *ctx, const lab_constants *c, const LabSe
     g->launches = ctx->launches - l0;
     ctx->launches = l0;
     if (rc != LAB_OK || !graph || overflowed) {
+        ctx->graph_fail_reason = rc != LAB_OK ? "recording failed: " + ctx->err : (!graph ? "cudaStreamEndCapture failed" : "scratch did not fit the graph's arena");
+        if (g_trace) std::fprintf(stderr, "[lab] proof graph not built: %s\n", ctx->graph_fail_reason.c_str());
         if (graph) cudaGraphDestroy(graph);
         for (void *q : ctx->overflow) cudaFree(q);
         ctx->overflow.clear();
@@ -1507,6 +1511,7 @@ static int prove_graph(lab_ctx *ctx, ProofGraph &g, const lab_constants *c, cons
         std::memcpy(g.h_in + g.in.pi, src + (size_t)att * pi_bytes, pi_bytes);
         CK(cudaGraphLaunch(g.exec, ctx->stream));
         ctx->launches += g.launches;
+        ctx->graph_replays++;
         TRY(lab_sync(ctx));
         std::memcpy(out->projection_int, g.h_out + g.out.p, LAB_JL_ROWS * sizeof(int64_t));
         if (valid_projection(c, out->projection_int)) break;
@@ -2013,6 +2018,17 @@ extern "C" int lab_crs_cache_configure(lab_ctx *ctx, size_t max_bytes) {
         ctx->crs_cache_used = 0;
     }
     ctx->crs_cache_max = max_bytes;
+    return LAB_OK;
+}
+// whole-proof graphs of this ctx and of its batch workers: graphs built, replays so far, 1 if a recording was abandoned
+extern "C" int lab_graph_stats(const lab_ctx *ctx, uint64_t *graphs, uint64_t *replays, int *failed) {
+    if (!ctx) return LAB_ERR_PARAMS;
+    uint64_t g = ctx->graphs.size(), r = ctx->graph_replays;
+    int f = ctx->graph_failed ? 1 : 0;
+    for (const lab_ctx *w : ctx->workers) { g += w->graphs.size(); r += w->graph_replays; f |= w->graph_failed ? 1 : 0; }
+    if (graphs) *graphs = g;
+    if (replays) *replays = r;
+    if (failed) *failed = f;
     return LAB_OK;
 }
 extern "C" int lab_crs_cache_stats(const lab_ctx *ctx, size_t *bytes_used, uint64_t *hits, uint64_t *misses) {

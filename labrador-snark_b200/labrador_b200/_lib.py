@@ -74,7 +74,7 @@ SYMBOLS = [
     "lab_gram_part", "lab_amortize_z_part", "lab_jl_project2_dev", "lab_jl_project_sharded_dev", "lab_amortize_z_sharded_dev",
     "lab_gram_sharded_dev", "lab_witness_load", "lab_commit_inner_resident", "lab_synth_pi2_dev",
     "lab_transcript_size_in_bytes", "lab_transcript_pack", "lab_transcript_unpack", "lab_fs_init", "lab_fs_absorb", "lab_fs_squeeze",
-    "lab_prove_fs", "lab_verify_fs", "lab_rq_add_batch", "lab_rq_sub_batch",
+    "lab_prove_fs", "lab_verify_fs", "lab_rq_add_batch", "lab_rq_sub_batch", "lab_graph_stats",
 ]
 
 _lib = None

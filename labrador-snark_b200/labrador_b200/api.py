@@ -189,6 +189,11 @@ class Context:
         self._ck(self.L.lab_crs_cache_stats(self._h, C.byref(used), C.byref(hits), C.byref(misses)))
         return {"bytes": used.value, "hits": hits.value, "misses": misses.value}
 
+    def graph_stats(self):
+        g, r, f = C.c_uint64(0), C.c_uint64(0), C.c_int(0)
+        self._ck(self.L.lab_graph_stats(self._h, C.byref(g), C.byref(r), C.byref(f)))
+        return {"graphs": g.value, "replays": r.value, "failed": bool(f.value)}
+
     # ---- device-side generation (f2 challenges, f4 witness / statement) ----
     def sample_challenge_polys(self, seed, first_idx, count):
         """Verifier::fetch_challenge on the device -> ([count][64] canonical, candidates tried per polynomial)."""

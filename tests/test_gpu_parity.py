@@ -834,13 +834,16 @@ def test_graph_path_matches_plain_path(orc, monkeypatch):
     c2 = lb.Context(0)
     try:
         run_all(c2, False)
+        assert c2.graph_stats() == {"graphs": 1, "replays": 5, "failed": False}      # 4 proofs after the first + 1 replay for the rejected attempt
         run_all(c2, True)
+        assert c2.graph_stats() == {"graphs": 2, "replays": 10, "failed": False}
     finally:
         c2.close()
     monkeypatch.setenv("LAB_NO_GRAPH", "1")
     c3 = lb.Context(0)
     try:
         run_all(c3, False)
+        assert c3.graph_stats()["graphs"] == 0
     finally:
         c3.close()
 
