@@ -369,9 +369,12 @@ def run_cfg1(args, rank, world, local_rank):
                 tr = prover.proof_gen(st, crs)
             l0 = ctx.kernel_launches
             t0 = time.perf_counter()
+            tcs = []
             for _ in range(reps):
                 tr = prover.proof_gen(st, crs)
+                tcs.append(ctx.last_prove_seconds)
             tp = (time.perf_counter() - t0) / reps
+            tc_call = sum(tcs) / len(tcs)
             launches = (ctx.kernel_launches - l0) // reps
             d = tr.as_oracle_dict()
             ctx.verify(c, SEED32, st.phi_k[0], st.a_k[0], st.b_k[0], ver.challenges, d)
@@ -397,7 +400,7 @@ def run_cfg1(args, rank, world, local_rank):
                 cached["bit_identical_to_uncached"] = bool(okc[0]) and all(np.array_equal(dc[k], d[k]) for k in ("t", "g", "u_1", "h", "u_2", "z"))
             finally:
                 ctx.crs_cache_configure(0)
-            row = {"N": N, "R": R, "kappa": c.KAPPA, "T_1": c.T_1, "T_2": c.T_2, "prove_ms": tp * 1e3, "verify_ms": tv * 1e3, "verify_accepts": bool(okv[0]),
+            row = {"N": N, "R": R, "kappa": c.KAPPA, "T_1": c.T_1, "T_2": c.T_2, "prove_ms": tp * 1e3, "prove_c_call_ms": tc_call * 1e3, "verify_ms": tv * 1e3, "verify_accepts": bool(okv[0]),
                    "with_crs_cache": cached,
                    "launches_per_proof": launches, "crs_coefficients_per_proof": blocks, "chacha_blocks_per_s_prove": blocks / tp,
                    "witness_coeffs_per_s": N * R * D / tp, "jl_attempt": tr.jl_attempt}
@@ -853,14 +856,16 @@ def main():
         if not light:
             extra.update({"ntt": ntt_res, "crs_resident": crs_cached})
             # default-size full prove() (BASELINE config 1 shape), ms per proof through the host API
+            # (on a context of its own: `ctx` may carry the communicator, and these proofs run on rank 0 only)
+            ctx_x = lb.Context(local_rank)
             try:
                 from labrador_b200 import synth
                 c2 = lb.RuntimeConstants.new(2, 2)
                 S2 = synth.generate_witness(2, 2, c2.BETA_BOUND, PRG_SEED)
-                st2 = lb.State.new(S2, c2, PRG_SEED, ctx)
+                st2 = lb.State.new(S2, c2, PRG_SEED, ctx_x)
                 ver = lb.Verifier.new(st2.b_prime_k, c2, seed=PRG_SEED, n_attempts=6)
-                prover = lb.Prover.new(S2, ver, c2, ctx)
-                crs = lb.CRS.from_seed(c2, SEED32, ctx)
+                prover = lb.Prover.new(S2, ver, c2, ctx_x)
+                crs = lb.CRS.from_seed(c2, SEED32, ctx_x)
                 for _ in range(3):       # warm-up (the scratch arena is sized after the first call)
                     prover.proof_gen(st2, crs)
                 t0 = time.perf_counter()
@@ -869,20 +874,23 @@ def main():
                 extra["prove_default_N2_R2_ms"] = (time.perf_counter() - t0) / 5 * 1e3
                 tr2 = prover.proof_gen(st2, crs)
                 t0 = time.perf_counter()
-                okv = ctx.verify(c2, SEED32, st2.phi_k[0], st2.a_k[0], st2.b_k[0], ver.challenges, tr2.as_oracle_dict())
+                okv = ctx_x.verify(c2, SEED32, st2.phi_k[0], st2.a_k[0], st2.b_k[0], ver.challenges, tr2.as_oracle_dict())
                 extra["verify_default_N2_R2_ms"] = (time.perf_counter() - t0) * 1e3
                 extra["verify_default_accepts"] = bool(okv[0])
                 # BASELINE config 5 flavour: independent default-size statements on this GPU (per-statement CRS seeds)
                 nb = 128
                 Sb = np.stack([S2] * nb); phib = np.stack([st2.phi_k[0]] * nb); ab_ = np.stack([st2.a_k[0]] * nb); bb = np.stack([st2.b_k[0]] * nb)
                 seeds = [bytes([i]) * 32 for i in range(nb)]
-                ctx.prove_batch(c2, seeds, False, Sb[:8], phib[:8], ab_[:8], bb[:8], [ver.challenges] * 8)
-                ctx.prove_batch(c2, seeds, False, Sb[:8], phib[:8], ab_[:8], bb[:8], [ver.challenges] * 8)
+                ctx_x.prove_batch(c2, seeds, False, Sb[:8], phib[:8], ab_[:8], bb[:8], [ver.challenges] * 8)
+                ctx_x.prove_batch(c2, seeds, False, Sb[:8], phib[:8], ab_[:8], bb[:8], [ver.challenges] * 8)
                 t0 = time.perf_counter()
-                ctx.prove_batch(c2, seeds, False, Sb, phib, ab_, bb, [ver.challenges] * nb)
+                ctx_x.prove_batch(c2, seeds, False, Sb, phib, ab_, bb, [ver.challenges] * nb)
                 extra["batch_default_proofs_per_s_per_gpu"] = nb / (time.perf_counter() - t0)
+                extra["proof_graphs"] = ctx_x.graph_stats()
             except Exception as e:       # reported, never hidden
                 extra["prove_default_error"] = repr(e)
+            finally:
+                ctx_x.close()
 
         if cfg4_checks is not None:
             extra["cfg4_checks"] = cfg4_checks

@@ -106,6 +106,7 @@ struct lab_ctx {
     // shard the CRS-regenerating stages by output rows and complete them with in-place all-gathers on the ctx stream
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
+    bool batch_cache = false;          // worker context whose CRS cache was switched on by a shared-seed batch
 };
 
 #define CK(call)                                                                                     \
@@ -754,19 +755,21 @@ struct MvSeg {
     uint64_t row_stride, sp, sk;
     uint32_t nk, count, vec_off;
 };
-// out[x] for x in [x0, x0 + n_rows): builds the item list, runs K_MV and the finishing kernel
-static int d_crs_matvec(lab_ctx *ctx, const LabSeed &seed, const std::vector<MvSeg> &segs, uint64_t x0, uint64_t n_rows,
-                        const uint32_t *V, uint32_t *out) {
-    if (!n_rows) return LAB_OK;
+// work-item list of a K_MV call (depends on the shape only; kept on the device per ctx)
+struct MvLaunch { MvItem *d_items = nullptr; uint32_t ipr = 0; uint64_t total_polys = 0; std::vector<MvItem> items; };
+static int mv_prepare(lab_ctx *ctx, const std::vector<MvSeg> &segs, uint64_t n_rows, MvLaunch &L) {
     uint64_t total_polys = 0;
     for (const MvSeg &s : segs) total_polys += s.count;
-    if (!total_polys) { CK(cudaMemsetAsync(out, 0, n_rows * 64 * sizeof(uint32_t), ctx->stream)); return LAB_OK; }
+    L.total_polys = total_polys;
+    if (!total_polys) return LAB_OK;
     // chunk so that there are ~24 warps of work per SM sub-partition, chunks between 4 and 2048 polys
-    const uint64_t target_items = (uint64_t)ctx->sms * 4 * 24;
+    static const uint64_t target_per_sm = [] { const char *e = std::getenv("LAB_MV_WARPS_PER_SM"); return e ? std::max<uint64_t>(1, std::strtoull(e, nullptr, 10)) : (uint64_t)96; }();
+    const uint64_t target_items = (uint64_t)ctx->sms * target_per_sm;
     uint64_t ch = (total_polys * n_rows + target_items - 1) / target_items;
     if (ch < 4) ch = 4;
     if (ch > 2048) ch = 2048;
-    std::vector<MvItem> items;
+    std::vector<MvItem> &items = L.items;
+    items.clear();
     for (const MvSeg &s : segs)
         for (uint32_t y = 0; y < s.count; y += (uint32_t)ch) {
             MvItem it;
@@ -776,13 +779,12 @@ static int d_crs_matvec(lab_ctx *ctx, const LabSeed &seed, const std::vector<MvS
             it.y0 = y; it.cnt = (uint32_t)std::min<uint64_t>(ch, s.count - y); it.vec_off = s.vec_off;
             items.push_back(it);
         }
-    const uint32_t ipr = (uint32_t)items.size();
+    L.ipr = (uint32_t)items.size();
     {   // position of every item inside a row of the CRS cache
         uint32_t off = 0;
         for (MvItem &it : items) { it.poff = off; off += it.cnt; }
     }
     MvItem *d_items = nullptr;
-    uint32_t *partial;
     const size_t ibytes = items.size() * sizeof(MvItem);
     for (auto &p : ctx->mv_plans)
         if (p.host.size() == ibytes && std::memcmp(p.host.data(), items.data(), ibytes) == 0) { d_items = (MvItem *)p.dev; break; }
@@ -803,6 +805,27 @@ static int d_crs_matvec(lab_ctx *ctx, const LabSeed &seed, const std::vector<MvS
         ctx->mv_plans.push_back(std::move(plan));
         d_items = (MvItem *)dev;
     }
+    L.d_items = d_items;
+    return LAB_OK;
+}
+static int d_finish_rows(lab_ctx *ctx, const uint32_t *partial, uint32_t ipr, uint64_t n_rows, uint32_t *out) {
+    if (ipr >= 32 && n_rows <= (uint64_t)ctx->sms * 16) LAUNCH(k_finish_rows_cta, (unsigned)n_rows, 256, partial, ipr, n_rows, out);
+    else LAUNCH(k_finish_rows, (unsigned)((n_rows + 7) / 8), 256, partial, ipr, n_rows, out);
+    return LAB_OK;
+}
+// out[x] for x in [x0, x0 + n_rows): builds the item list, runs K_MV and the finishing kernel
+static int d_crs_matvec(lab_ctx *ctx, const LabSeed &seed, const std::vector<MvSeg> &segs, uint64_t x0, uint64_t n_rows,
+                        const uint32_t *V, uint32_t *out) {
+    if (!n_rows) return LAB_OK;
+    MvLaunch L;
+    TRY(mv_prepare(ctx, segs, n_rows, L));
+    const uint64_t total_polys = L.total_polys;
+    if (!total_polys) { CK(cudaMemsetAsync(out, 0, n_rows * 64 * sizeof(uint32_t), ctx->stream)); return LAB_OK; }
+    std::vector<MvItem> &items = L.items;
+    const uint32_t ipr = L.ipr;
+    MvItem *d_items = L.d_items;
+    const size_t ibytes = items.size() * sizeof(MvItem);
+    uint32_t *partial;
     TRY(arena_alloc(ctx, (size_t)n_rows * ipr * 32, &partial));
     const uint64_t warps = n_rows * ipr;
     // CRS cache: key = seed, row range, item list
@@ -833,7 +856,7 @@ static int d_crs_matvec(lab_ctx *ctx, const LabSeed &seed, const std::vector<MvS
         crs_cache_commit(ctx, std::move(fill_key), cache_fill, fill_bytes);      // registered only once the fill was accepted
     }
     else LAUNCH(k_crs_matvec<false>, (unsigned)((warps + 7) / 8), 256, seed, d_items, ipr, n_rows, x0, V, partial, (uint32_t *)nullptr, total_polys);
-    LAUNCH(k_finish_rows, (unsigned)((n_rows + 7) / 8), 256, partial, ipr, n_rows, out);
+    TRY(d_finish_rows(ctx, partial, ipr, n_rows, out));
     return LAB_OK;
 }
 
@@ -846,10 +869,18 @@ __global__ void k_gather_pairs(const uint32_t *__restrict__ M, uint32_t R, uint3
 }
 
 // u_1 (proofgen.rs:101-153) from device T [R][KAPPA][64] and G [R][R][64]
-// rows [x0, x0 + nx) only; du1 points at row 0 of the full u_1
-static int d_outer_u1(lab_ctx *ctx, const lab_constants *c, const LabSeed &seed, const uint32_t *dT, const uint32_t *dG, uint32_t *du1,
-                      uint64_t x0 = 0, uint64_t nx = ~0ull) {
-    const uint64_t R = c->R, K = c->KAPPA, K1 = c->KAPPA_1, K2 = c->KAPPA_2, T1 = (uint64_t)c->T_1, T2 = (uint64_t)c->T_2;
+// the CRS side: B_ik rows and C_ijk with the reference's literal offsets (structs.rs:74-114)
+static void u1_segs(const lab_constants *c, std::vector<MvSeg> &segs) {
+    const uint64_t R = c->R, K = c->KAPPA, K2 = c->KAPPA_2, T1 = (uint64_t)c->T_1, T2 = (uint64_t)c->T_2;
+    const uint64_t npairs = R * (R + 1) / 2;
+    for (uint64_t i = 0; i < R; i++)
+        for (uint64_t k = 0; k < T1; k++)
+            segs.push_back(MvSeg{off_B(c, i, k, 0), K * LAB_D, LAB_D, 0, 1u, (uint32_t)K, (uint32_t)((i * T1 + k) * K)});
+    segs.push_back(MvSeg{off_C(c, 0, 0, 0), LAB_D, T1 * K2 * LAB_D, K2 * LAB_D, (uint32_t)T2, (uint32_t)(npairs * T2), (uint32_t)(R * T1 * K)});
+}
+// the witness side: transformed digits of t (base B_1) and of the upper triangle of g (base B_2)
+static int u1_build_V(lab_ctx *ctx, const lab_constants *c, const uint32_t *dT, const uint32_t *dG, uint32_t **Vout) {
+    const uint64_t R = c->R, K = c->KAPPA, T1 = (uint64_t)c->T_1, T2 = (uint64_t)c->T_2;
     const uint64_t npairs = R * (R + 1) / 2;
     if (R * T1 * K + npairs * T2 >= (1ull << 32)) FAIL(LAB_ERR_PARAMS, "u_1 vector too long for 32-bit indexing");
     uint32_t *V, *Gp;
@@ -858,12 +889,17 @@ static int d_outer_u1(lab_ctx *ctx, const lab_constants *c, const LabSeed &seed,
     LAUNCH(k_decomp_fwd, grid_for(R * K, 8, ctx->sms * 16), 256, dT, V, (size_t)(R * K), (size_t)K, (uint32_t)c->B_1, (int)T1);
     LAUNCH(k_gather_pairs, dim3((unsigned)R, (unsigned)R), 64, dG, (uint32_t)R, Gp);
     LAUNCH(k_decomp_fwd, grid_for(npairs, 8, ctx->sms * 16), 256, Gp, V + R * T1 * K * 32, (size_t)npairs, (size_t)1, (uint32_t)c->B_2, (int)T2);
+    *Vout = V;
+    return LAB_OK;
+}
+// rows [x0, x0 + nx) only; du1 points at row 0 of the full u_1
+static int d_outer_u1(lab_ctx *ctx, const lab_constants *c, const LabSeed &seed, const uint32_t *dT, const uint32_t *dG, uint32_t *du1,
+                      uint64_t x0 = 0, uint64_t nx = ~0ull) {
+    uint32_t *V;
+    TRY(u1_build_V(ctx, c, dT, dG, &V));
     std::vector<MvSeg> segs;
-    for (uint64_t i = 0; i < R; i++)
-        for (uint64_t k = 0; k < T1; k++)
-            segs.push_back(MvSeg{off_B(c, i, k, 0), K * LAB_D, LAB_D, 0, 1u, (uint32_t)K, (uint32_t)((i * T1 + k) * K)});
-    segs.push_back(MvSeg{off_C(c, 0, 0, 0), LAB_D, T1 * K2 * LAB_D, K2 * LAB_D, (uint32_t)T2, (uint32_t)(npairs * T2), (uint32_t)(R * T1 * K)});
-    if (nx == ~0ull) nx = K1;
+    u1_segs(c, segs);
+    if (nx == ~0ull) nx = c->KAPPA_1;
     return d_crs_matvec(ctx, seed, segs, x0, nx, V, du1 + x0 * 64);
 }
 // u_2 (proofgen.rs:364-378) from device H [R][R][64]
@@ -1317,10 +1353,13 @@ static bool graph_eligible(const lab_ctx *ctx, const lab_constants *c) {
     if (ctx->comm || ctx->crs_cache_max || std::getenv("LAB_NO_GRAPH") || std::getenv("LAB_NO_FORK") || std::getenv("LAB_GEN_CONTRACT_MIN_POLYS")) return false;
     const uint64_t R = c->R, N = c->N, K = c->KAPPA;
     const uint64_t bytes = (2 * R * N + R * R + R * K + 3 * K) * 256 + R * LAB_JL_ROWS * N * LAB_D;
-    return bytes <= ((uint64_t)6 << 20) && K * N < ((uint64_t)1 << 22) && R <= 64;      // fused-K_A regime only (no generate-then-contract chunks)
+    // the generated CRS side of u_1 waits in HBM / L2 between its two kernels: K_1 rows x (R T_1 K + pairs T_2) hats of 128 bytes
+    const uint64_t hats = c->KAPPA_1 * (R * (uint64_t)c->T_1 * K + R * (R + 1) / 2 * (uint64_t)c->T_2) * 128;
+    return bytes <= ((uint64_t)6 << 20) && hats <= ((uint64_t)2 << 30) && K * N < ((uint64_t)1 << 22) && R <= 64;      // fused-K_A regime only
 }
 static int number_of_args(const void *func) {
     if (func == (const void *)k_crs_matvec<false>) return 9;
+    if (func == (const void *)k_crs_gen_hats) return 7;
     if (func == (const void *)k_commit_inner<1, LAB_RM_COMMIT, LAB_KA_PP> || func == (const void *)k_commit_inner<2, LAB_RM_COMMIT, LAB_KA_PP> ||
         func == (const void *)k_commit_inner<4, LAB_RM_COMMIT, LAB_KA_PP> || func == (const void *)k_commit_inner<8, LAB_RM_COMMIT, LAB_KA_PP> ||
         func == (const void *)k_commit_inner<16, LAB_RM_COMMIT, LAB_KA_PP>)
@@ -1337,31 +1376,47 @@ static int graph_record(lab_ctx *ctx, const lab_constants *c, const LabSeed &see
     char *din, *dout;
     TRY(arena_alloc(ctx, g.in_bytes, &din));
     TRY(arena_alloc(ctx, g.out_bytes, &dout));
-    CK(cudaMemcpyAsync(din, g.h_in, g.in_bytes, cudaMemcpyHostToDevice, ctx->stream));
     const uint32_t *dS = (const uint32_t *)(din + g.in.S), *dphi = (const uint32_t *)(din + g.in.phi), *da = (const uint32_t *)(din + g.in.a),
                    *dab = (const uint32_t *)(din + g.in.ab), *dom = (const uint32_t *)(din + g.in.om), *dc = (const uint32_t *)(din + g.in.c);
     uint32_t *du1 = (uint32_t *)(dout + g.out.u1), *dz = (uint32_t *)(dout + g.out.z), *dT = (uint32_t *)(dout + g.out.T), *dG = (uint32_t *)(dout + g.out.G),
              *dsums = (uint32_t *)(dout + g.out.sums), *dpf = (uint32_t *)(dout + g.out.pf), *du2 = (uint32_t *)(dout + g.out.u2), *dH = (uint32_t *)(dout + g.out.H);
     unsigned long long *dnorm = (unsigned long long *)(dout + g.out.norm), *dp = (unsigned long long *)(dout + g.out.p);
     // (psi, a kernel ARGUMENT of k_phi_pp in the ordinary path, is read from the input block here: k_phi_pp_dev)
-    uint32_t *What;
+    uint32_t *What, *Ghat;
     TRY(arena_alloc(ctx, what_hats(N, R) * 32, &What));
-    TRY(d_fwd_hat(ctx, dS, What, R * N, N, R));
-    uint32_t *Ghat;
     TRY(arena_alloc(ctx, R * R * 32, &Ghat));
-    // ---- forked branch: S1 inner commitment, S2 g, S3 u_1 (all of a small proof's ChaCha20) ----
+    struct StreamSwap {
+        lab_ctx *c; cudaStream_t saved;
+        StreamSwap(lab_ctx *cx, cudaStream_t to) : c(cx), saved(cx->stream) { cx->stream = to; }
+        ~StreamSwap() { c->stream = saved; }
+    };
+    // ---- forked branch: the CRS side of u_1 -- all of a small proof's ChaCha20 -- starts at time zero (the CRS does not depend on
+    //      the witness): B_ik rows and C_ijk are generated into `hats`; the multiply follows once the digits of t and g exist ----
+    std::vector<MvSeg> segs;
+    u1_segs(c, segs);
+    MvLaunch L;
+    uint32_t *hats = nullptr, *partial = nullptr, *V = nullptr;
     CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
     {
-        struct StreamSwap {
-            lab_ctx *c; cudaStream_t saved;
-            ~StreamSwap() { c->stream = saved; }
-        } swap{ctx, ctx->stream};
-        ctx->stream = ctx->stream2;
-        TRY(d_commit_inner(ctx, seed, What, N, R, 0, K, dT, K, 0));
-        TRY(d_gram(ctx, What, N, R, 0, R, Ghat, dG));
-        CK(cudaEventRecord(ctx->ev_tg, ctx->stream));
-        TRY(d_outer_u1(ctx, c, seed, dT, dG, du1, 0, K1));
+        StreamSwap swap(ctx, ctx->stream2);
+        TRY(mv_prepare(ctx, segs, K1, L));
+        TRY(arena_alloc(ctx, (size_t)K1 * L.total_polys * 32, &hats));
+        TRY(arena_alloc(ctx, (size_t)K1 * L.ipr * 32, &partial));
+        LAUNCH(k_crs_gen_hats, (unsigned)((K1 * L.ipr + 7) / 8), 256, seed, L.d_items, L.ipr, K1, (uint64_t)0, hats, L.total_polys);
+    }
+    // ---- main branch: inputs (one copy of the pinned block), S1 inner commitment, S2 g, digits of t and g ----
+    CK(cudaMemcpyAsync(din, g.h_in, g.in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(d_fwd_hat(ctx, dS, What, R * N, N, R));
+    TRY(d_commit_inner(ctx, seed, What, N, R, 0, K, dT, K, 0));
+    TRY(d_gram(ctx, What, N, R, 0, R, Ghat, dG));
+    TRY(u1_build_V(ctx, c, dT, dG, &V));
+    CK(cudaEventRecord(ctx->ev_tg, ctx->stream));
+    {   // S3: u_1 = (generated CRS) x (digits), an L2-resident stream, on the forked branch
+        StreamSwap swap(ctx, ctx->stream2);
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_tg, 0));
+        LAUNCH(k_cached_matvec, (unsigned)((K1 * L.ipr + 7) / 8), 256, hats, L.total_polys, L.d_items, L.ipr, K1, V, partial);
+        TRY(d_finish_rows(ctx, partial, L.ipr, K1, du1));
         CK(cudaEventRecord(ctx->ev_join, ctx->stream));
     }
     // ---- main branch ----
@@ -1401,7 +1456,6 @@ static int graph_record(lab_ctx *ctx, const lab_constants *c, const LabSeed &see
     TRY(d_fwd_hat(ctx, dpp, PPhat, R * N, N, R));
     LAUNCH(k_ip_hat, (unsigned)R, 256, PPhat, (size_t)R, (size_t)1, What, (size_t)R, (size_t)1, (size_t)N, (size_t)0, 1u, 2, diag);
     LAUNCH(k_sum_hats, 1, 32, diag, (size_t)R, (size_t)1, sums + 32, (size_t)1);
-    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_tg, 0));                                        // T and g are complete
     LAUNCH(k_pointwise, grid_for(R * R * 32, 256, ctx->sms * 16), 256, Ahat, (size_t)1, (size_t)(R * R), Ghat, (const uint32_t *)nullptr, (size_t)1,
            (size_t)0, (const uint32_t *)nullptr, AG, (size_t)(R * R));
     LAUNCH(k_sum_hats, 1, 32, AG, (size_t)(R * R), (size_t)1, sums, (size_t)1);
@@ -1436,7 +1490,8 @@ static ProofGraph *graph_build(lab_ctx *ctx, const lab_constants *c, const LabSe
     g->out_bytes = o;
     if (cudaMallocHost(&g->h_in, g->in_bytes) != cudaSuccess || cudaMallocHost(&g->h_out, g->out_bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     std::memset(g->h_in, 0, g->in_bytes);
-    g->dev_bytes = ctx->arena_size + g->in_bytes + g->out_bytes + ((size_t)1 << 20);
+    const size_t hats_bytes = (size_t)K1 * (R * (size_t)c->T_1 * K + R * (R + 1) / 2 * (size_t)c->T_2) * 128;
+    g->dev_bytes = ctx->arena_size + g->in_bytes + g->out_bytes + hats_bytes + ((size_t)4 << 20);
     if (cudaMalloc(&g->dev, g->dev_bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     if (ensure_stream2(ctx) != LAB_OK) return nullptr;
     // record with the graph's own memory as the arena; an allocation that does not fit aborts the recording
@@ -1979,11 +2034,15 @@ extern "C" int lab_prove_batch(lab_ctx *ctx, const lab_constants *c, size_t n_st
         ctx->workers.push_back(w);
     }
     // one CRS for the whole batch: each worker keeps the transformed CRS polynomials of its first statement in HBM (CRS
-    // cache) and the remaining statements stream them back instead of re-running ChaCha20; dropped again at the end
+    // cache) and the remaining statements -- of this and of later shared-seed batches -- stream them back instead of re-running
+    // ChaCha20.  The worker caches stay until a per-statement batch, lab_crs_cache_configure(ctx, 0) or lab_ctx_destroy: freeing
+    // and re-filling them per call made the batch time erratic (device-wide synchronisation of every cudaFree).
     const size_t worker_cache = (size_t)8 << 30;
-    if (shared_crs)
-        for (size_t t = 0; t < nw; t++)
-            if (!ctx->workers[t]->crs_cache_max) lab_crs_cache_configure(ctx->workers[t], worker_cache);
+    for (size_t t = 0; t < nw; t++) {
+        lab_ctx *w = ctx->workers[t];
+        if (shared_crs && !w->crs_cache_max) { lab_crs_cache_configure(w, worker_cache); w->batch_cache = true; }
+        if (!shared_crs && w->batch_cache) { lab_crs_cache_configure(w, 0); w->batch_cache = false; }
+    }
     std::vector<int> status(nw, LAB_OK);
     std::vector<std::thread> threads;
     for (size_t t = 0; t < nw; t++)
@@ -1997,8 +2056,6 @@ extern "C" int lab_prove_batch(lab_ctx *ctx, const lab_constants *c, size_t n_st
             }
         });
     for (auto &th : threads) th.join();
-    if (shared_crs)
-        for (size_t t = 0; t < nw; t++) lab_crs_cache_configure(ctx->workers[t], 0);
     for (size_t t = 0; t < nw; t++) {
         ctx->launches += ctx->workers[t]->launches;
         ctx->workers[t]->launches = 0;
@@ -2018,6 +2075,9 @@ extern "C" int lab_crs_cache_configure(lab_ctx *ctx, size_t max_bytes) {
         ctx->crs_cache_used = 0;
     }
     ctx->crs_cache_max = max_bytes;
+    if (!max_bytes)                                 // "give the memory back" reaches the batch workers too
+        for (lab_ctx *w : ctx->workers)
+            if (w->batch_cache) { lab_crs_cache_configure(w, 0); w->batch_cache = false; }
     return LAB_OK;
 }
 // whole-proof graphs of this ctx and of its batch workers: graphs built, replays so far, 1 if a recording was abandoned

@@ -776,6 +776,38 @@ __global__ void __launch_bounds__(256) k_crs_matvec(LabSeed seed, const MvItem *
     }
     partial[wid * 32 + lane] = lab_pack(lab_canon(accr), lab_canon(acci));
 }
+// generation only: the hats of the same work items into `hats[(xr * row_polys + poff + y - y0)]`, no multiply.  The whole-proof
+// graph of a small shape starts this at time zero -- the CRS does not depend on the witness -- and multiplies with
+// k_cached_matvec once the digits of T and g exist, so that a default-size proof's 8.4e6 ChaCha20 blocks no longer wait for
+// the inner commitment.
+__global__ void __launch_bounds__(256) k_crs_gen_hats(LabSeed seed, const MvItem *__restrict__ items, uint32_t items_per_row, uint64_t n_rows, uint64_t x0,
+                                                      uint32_t *__restrict__ hats, uint64_t row_polys) {
+    const int lane = threadIdx.x & 31;
+    const LabWarpTw tw = lab_warp_tw(lane);
+    uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t total = n_rows * items_per_row;
+    if (wid >= total) return;
+    const uint64_t xr = wid / items_per_row;
+    const MvItem it = items[wid % items_per_row];
+    uint64_t lo, hi;
+    {
+        unsigned __int128 b = ((unsigned __int128)it.base_hi << 64) | it.base_lo;
+        b += (unsigned __int128)(x0 + xr) * it.row_stride;
+        lo = (uint64_t)b; hi = (uint64_t)(b >> 64);
+    }
+    LabHoist h;
+    lab_hoist_invalidate(h);
+    uint32_t *co = hats + (xr * row_polys + it.poff) * 32 + lane;
+    for (uint32_t y = it.y0; y < it.y0 + it.cnt; y++) {
+        const uint64_t add = (uint64_t)(y / it.nk) * it.sp + (uint64_t)(y % it.nk) * it.sk;
+        const uint64_t plo = lo + add;
+        const uint64_t phi = hi + (plo < lo);
+        uint32_t re, im;
+        crs_poly_hat<LAB_RM_MATVEC>(seed, h, plo, phi, tw, lane, re, im);
+        *co = lab_pack(re, im);
+        co += 32;
+    }
+}
 // the same mat-vec from cached hats: HBM-bound stream of 128 B per CRS polynomial, no ChaCha20
 __global__ void __launch_bounds__(256) k_cached_matvec(const uint32_t *__restrict__ cache, uint64_t row_polys, const MvItem *__restrict__ items,
                                                        uint32_t items_per_row, uint64_t n_rows, const uint32_t *__restrict__ V, uint32_t *__restrict__ partial) {
@@ -824,6 +856,31 @@ __global__ void __launch_bounds__(256) k_finish_rows(const uint32_t *__restrict_
     lab_ntt32_inv_warp(r, i, tw, lane);
     out[x * 64 + lane] = r;
     out[x * 64 + 32 + lane] = i;
+}
+// the same with one CTA per row: its 8 warps split the items (few rows, many items per row: the outer commitments of small proofs)
+__global__ void __launch_bounds__(256) k_finish_rows_cta(const uint32_t *__restrict__ partial, uint32_t items_per_row, uint64_t n_rows, uint32_t *__restrict__ out) {
+    __shared__ uint32_t sre[8][32], sim[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint64_t x = blockIdx.x;
+    uint32_t r = 0, i = 0, cnt = 0;
+    for (uint32_t t = w; t < items_per_row; t += 8) {
+        uint32_t v = partial[(x * items_per_row + t) * 32 + lane];
+        r += lab_re(v); i += lab_im(v);
+        if ((++cnt & 1023) == 0) { r = lab_fold(r); i = lab_fold(i); }
+    }
+    sre[w][lane] = lab_canon(r);
+    sim[w][lane] = lab_canon(i);
+    __syncthreads();
+    if (w == 0) {
+        r = 0; i = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { r += sre[k][lane]; i += sim[k][lane]; }
+        r = lab_canon(r); i = lab_canon(i);
+        const LabWarpTw tw = lab_warp_tw(lane);
+        lab_ntt32_inv_warp(r, i, tw, lane);
+        out[x * 64 + lane] = r;
+        out[x * 64 + 32 + lane] = i;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -800,7 +800,11 @@ class Prover:
         tr = _lib.CTranscript(_p(out["u_1"]), 0, _p(out["projection_int"]), _p(out["projection"]), _p(out["b_prime_prime"]),
                               _p(out["u_2"]), _p(out["z"]), _p(out["t"]), _p(out["g"]), _p(out["h"]), _p(out["phi_final"]), 0)
         S = self.witness
-        rc = ctx.L.lab_prove(ctx._h, C.byref(c), _p(_seed_buf(crs.base_seed)), _p(S), C.byref(cst), C.byref(cch), C.byref(tr))
+        seedbuf = _seed_buf(crs.base_seed)
+        import time as _time
+        t0 = _time.perf_counter()
+        rc = ctx.L.lab_prove(ctx._h, C.byref(c), _p(seedbuf), _p(S), C.byref(cst), C.byref(cch), C.byref(tr))
+        ctx.last_prove_seconds = _time.perf_counter() - t0           # the C call alone (host buffers in, transcript out), without this method's marshalling
         if rc == 1:
             raise LabError(rc, "failed JL...")                                     # proofgen.rs:176
         ctx._ck(rc)
