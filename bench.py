@@ -344,8 +344,9 @@ def run_cfg1(args, rank, world, local_rank):
     from labrador_b200 import synth
     torch.cuda.set_device(local_rank)
     ctx = lb.Context(local_rank)
-    sizes = [(2, 2), (4, 4), (8, 8), (16, 16), (32, 32)]
-    cpu_sizes = {(2, 2), (4, 4)}
+    # benches/labrador_perf.rs:19-28: n and r double alternately from (1, 2); size_pow 2 .. 10 are the shapes whose constants are sane
+    sizes = [(2, 2), (2, 4), (4, 4), (4, 8), (8, 8), (8, 16), (16, 16), (16, 32), (32, 32)]
+    cpu_sizes = {(2, 2), (2, 4), (4, 4)}
     oracle = None
     if rank == 0 and not args.no_cpu:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))

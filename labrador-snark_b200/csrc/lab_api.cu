@@ -1822,9 +1822,13 @@ extern "C" int lab_prove(lab_ctx *ctx, const lab_constants *c, const uint8_t see
 // Verifier::verify (verification.rs:25-438) on the GPU.  Checks 15, 19, 20 re-run the prover's commitment kernels;
 // 16-18 are slot-wise sums in the transform domain; 14 is the exact-integer norm; 8-9 are host comparisons.
 // ---------------------------------------------------------------------------------------------
-static int dev_equal(lab_ctx *ctx, const uint32_t *x, const uint32_t *y, size_t n_words, unsigned long long *dcount, bool *equal) {
+// lazy: only enqueue the comparison (the count stays in *dcount on the device, *equal is reported as true); the caller reads all
+// counts back with one synchronisation at the end.  Small proofs are latency-bound: six host round trips cost more than the work
+// an early exit would save.  Large shapes keep the early exit (a rejected (32,32) proof skips seconds of u_1 recomputation).
+static int dev_equal(lab_ctx *ctx, const uint32_t *x, const uint32_t *y, size_t n_words, unsigned long long *dcount, bool *equal, bool lazy = false) {
     CK(cudaMemsetAsync(dcount, 0, sizeof *dcount, ctx->stream));
     LAUNCH(k_count_diff, grid_for(n_words, 1024, ctx->sms * 8), 256, x, y, n_words, dcount);
+    if (lazy) { *equal = true; return LAB_OK; }
     unsigned long long h = 0;
     CK(cudaMemcpyAsync(&h, dcount, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     TRY(lab_sync(ctx));
@@ -1876,7 +1880,8 @@ static int verify_core(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_
     std::memcpy(small + 128, st->b, 256); std::memcpy(small + 192, tr->b_prime_prime, 256);
     TRY(upload(ctx, small, (size_t)256, &dsmall));
     unsigned long long *dcnt;
-    TRY(arena_alloc(ctx, (size_t)2, &dcnt));
+    TRY(arena_alloc(ctx, (size_t)8, &dcnt));                    // [1] = norm, [2..7] = difference counts of Checks 15..20 (lazy mode)
+    const bool lazy = R * K * 256 <= ((uint64_t)4 << 20);       // small proofs: one synchronisation for all equality checks
     // lines 10-14: exact integer norm of every digit (verification.rs:185-267)
     CK(cudaMemsetAsync(dcnt + 1, 0, sizeof *dcnt, ctx->stream));
     LAUNCH(k_digit_norm_sq, grid_for(N * 64, 2048, ctx->sms * 8), 256, dz, (size_t)(N * 64), (uint32_t)c->B, 2, dcnt + 1);
@@ -1930,7 +1935,7 @@ static int verify_core(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_
             if (sharded) TRY(allgather_rows(ctx, lhs, 1, 0, K, 64));
         }
         TRY(d_amortize(ctx, Chat, That, K, R, 0, R, rhs_h, rhs));
-        TRY(dev_equal(ctx, lhs, rhs, K * 64, dcnt, &eq));
+        TRY(dev_equal(ctx, lhs, rhs, K * 64, dcnt + 2, &eq, lazy));
         if (!eq) fc = 15;
     }
     uint32_t *scal;                                              // a handful of single hats
@@ -1949,7 +1954,7 @@ static int verify_core(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_
     if (!fc) {   // check 16: <z,z> == sum g_ij c_i c_j (verification.rs:303-314)
         LAUNCH(k_ip_hat, 1, 256, zhat, (size_t)1, (size_t)0, zhat, (size_t)1, (size_t)0, (size_t)N, (size_t)1, 1u, 0, scal);
         TRY(gcc_sum(Ghat, scal + 32));
-        TRY(dev_equal(ctx, scal, scal + 32, 32, dcnt, &eq));
+        TRY(dev_equal(ctx, scal, scal + 32, 32, dcnt + 3, &eq, lazy));
         if (!eq) fc = 16;
     }
     if (!fc) {   // check 17: sum_i <phi_i, z> c_i == sum h_ij c_i c_j (verification.rs:320-334)
@@ -1961,7 +1966,7 @@ static int verify_core(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_
                (const uint32_t *)nullptr, pzc, (size_t)R);
         LAUNCH(k_sum_hats, 1, 32, pzc, (size_t)R, (size_t)1, scal + 64, (size_t)1);
         TRY(gcc_sum(Hhat, scal + 96));
-        TRY(dev_equal(ctx, scal + 64, scal + 96, 32, dcnt, &eq));
+        TRY(dev_equal(ctx, scal + 64, scal + 96, 32, dcnt + 4, &eq, lazy));
         if (!eq) fc = 17;
     }
     if (!fc) {   // check 18: sum a_ij g_ij + sum h_ii - b == 0 with a = alpha a + beta psi a, b = alpha b + beta b'' (lines 5, 7; :340-352)
@@ -1983,7 +1988,7 @@ static int verify_core(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_
         LAUNCH(k_pointwise, 1, 32, alpha_h, (size_t)1, (size_t)0, b_h, beta_h, (size_t)1, (size_t)0, bpp_h, scal + 192, (size_t)1);   // b
         LAUNCH(k_addsub_hats, 1, 32, scal + 128, scal + 160, scal + 192, scal + 224, (size_t)32);
         CK(cudaMemsetAsync(scal + 256, 0, 32 * sizeof(uint32_t), ctx->stream));
-        TRY(dev_equal(ctx, scal + 224, scal + 256, 32, dcnt, &eq));
+        TRY(dev_equal(ctx, scal + 224, scal + 256, 32, dcnt + 5, &eq, lazy));
         if (!eq) fc = 18;
     }
     if (!fc) {   // check 19: u_1 (verification.rs:372-415)
@@ -1995,7 +2000,7 @@ static int verify_core(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_
             TRY(d_outer_u1(ctx, c, seed, dT, dG, cand, x0, nx));
             if (sharded) TRY(allgather_rows(ctx, cand, 1, 0, K1, 64));
         }
-        TRY(dev_equal(ctx, cand, du1, K1 * 64, dcnt, &eq));
+        TRY(dev_equal(ctx, cand, du1, K1 * 64, dcnt + 6, &eq, lazy));
         if (!eq) fc = 19;
     }
     if (!fc) {   // check 20: u_2 (verification.rs:421-435)
@@ -2007,8 +2012,15 @@ static int verify_core(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_
             TRY(d_outer_u2(ctx, c, seed, dH, cand, x0, nx));
             if (sharded) TRY(allgather_rows(ctx, cand, 1, 0, K2, 64));
         }
-        TRY(dev_equal(ctx, cand, du2, K2 * 64, dcnt, &eq));
+        TRY(dev_equal(ctx, cand, du2, K2 * 64, dcnt + 7, &eq, lazy));
         if (!eq) fc = 20;
+    }
+    if (lazy && !fc) {            // all comparisons are enqueued: one read-back, the first failing check in the reference's order counts
+        unsigned long long hc[6] = {0, 0, 0, 0, 0, 0};
+        CK(cudaMemcpyAsync(hc, dcnt + 2, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
+        TRY(lab_sync(ctx));
+        for (int k = 0; k < 6 && !fc; k++)
+            if (hc[k]) fc = 15 + k;
     }
     if (failed_check) *failed_check = fc;
     *accepted = fc == 0;
