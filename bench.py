@@ -982,7 +982,7 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle
         cores = oracle.num_threads()
-        rows = max(cores, 4) * 32                     # about 20 s of CPU work at cfg 3 on 16 cores (0.2 % of the rows; 1 % would take 90 s)
+        rows = max(cores, 4) * (32 if N <= 4096 else 1)   # about 20 s of CPU work at cfg 3 on 16 cores (0.2 % of the rows; 1 % would take 90 s); cfg 4: one row per thread
         dt, _ = cpu_sample(N, R, rows, cores)
         cpu_step = dt * kappa / rows
         # parity spot check of the very rows the CPU just computed

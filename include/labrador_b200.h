@@ -248,7 +248,11 @@ int lab_verify(lab_ctx *ctx, const lab_constants *c, const uint8_t seed[32], con
  * and serves every later use of that A -- more than 64 witness vectors, the verifier's A z (verification.rs:274-279), the
  * next proof -- with a tcgen05 int8 contraction that streams A once from HBM (cfg 3: 34 ms instead of 3 s).  Results are
  * bit-identical.  Off by default (max_bytes = 0): a single proof then regenerates its CRS exactly like the reference.
- * Entries that do not fit stay uncached.
+ * Entries that do not fit stay uncached; when there is no room, entries of other seeds are dropped first.
+ * Small shapes that replay lab_prove as a CUDA graph (lab_graph_stats) keep the generated CRS side of u_1 inside the graph's own
+ * memory: with the cache on, a replay whose seed equals the previous replay's skips the generation (counted as a hit).
+ * lab_prove_batch(shared_crs = 1) switches the cache on for its worker contexts; they keep it until a per-statement batch or
+ * lab_crs_cache_configure(ctx, 0).
  * Any call also releases the few GB of transient limb planes the cold large-shape commitment keeps in the ctx
  * between calls (lab_crs_cache_configure(ctx, 0) is the "give the memory back" call). */
 int lab_crs_cache_configure(lab_ctx *ctx, size_t max_bytes);

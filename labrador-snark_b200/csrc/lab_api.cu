@@ -47,6 +47,11 @@ struct ProofGraph {
     struct { size_t u1, z, T, G, sums, pf, u2, H, norm, p; } out{};
     struct SeedNode { cudaGraphNode_t node; cudaKernelNodeParams params; std::vector<void *> args; };
     std::vector<SeedNode> seed_nodes;
+    // With the CRS cache switched on (lab_crs_cache_configure) the generated CRS side of u_1 is kept between replays: when the
+    // seed of a replay equals the previous one's, the generation node is disabled and the multiply reads the hats already there.
+    cudaGraphNode_t gen_node = nullptr;
+    bool gen_enabled = true, hats_valid = false;
+    uint8_t last_seed[32] = {0};
     uint64_t launches = 0;                        // kernels per replay
     ~ProofGraph() {
         if (exec) cudaGraphExecDestroy(exec);
@@ -1224,6 +1229,13 @@ extern "C" int lab_commit_outer_u2(lab_ctx *ctx, const lab_constants *c, const u
     TRY(download(ctx, u2, du2, c->KAPPA_2 * 64));
     return lab_sync(ctx);
 }
+// v = Pi^T omega over `total` coefficients (total / 16 packed words per row set): warp per word for small shapes, thread per word otherwise
+static int d_piT_omega(lab_ctx *ctx, const uint32_t *dPi2, const uint32_t *domega, uint64_t total, uint64_t ND, uint32_t *v) {
+    const uint64_t words = total / 16;
+    if (words < 65536) LAUNCH(k_piT_omega2_warp, (unsigned)((words + 7) / 8), 256, dPi2, domega, words, (uint32_t)(ND / 16), v);
+    else LAUNCH(k_piT_omega2, (unsigned)((words + 255) / 256), 256, dPi2, domega, words, (uint32_t)(ND / 16), v);
+    return LAB_OK;
+}
 // phi''_i for vectors [i0, i0 + ni): dphi, dpp point at vector i0 ([ni][N][64]); dPi2 holds the rows of those vectors
 static int d_aggregate_phi(lab_ctx *ctx, const lab_constants *c, const uint32_t *dphi, const uint32_t *dPi2, uint32_t psi, const uint32_t *domega, uint32_t *dpp,
                            uint64_t ni = ~0ull) {
@@ -1232,7 +1244,7 @@ static int d_aggregate_phi(lab_ctx *ctx, const lab_constants *c, const uint32_t 
     if (!total) return LAB_OK;
     uint32_t *v;
     TRY(arena_alloc(ctx, total, &v));
-    LAUNCH(k_piT_omega2, (unsigned)((total / 16 + 255) / 256), 256, dPi2, domega, total / 16, (uint32_t)(ND / 16), v);
+    TRY(d_piT_omega(ctx, dPi2, domega, total, ND, v));
     LAUNCH(k_phi_pp, (unsigned)((total + 255) / 256), 256, dphi, v, psi % LAB_Q, (size_t)total, dpp);
     return LAB_OK;
 }
@@ -1350,7 +1362,7 @@ static int finish_transcript(lab_ctx *ctx, const lab_state *st, const lab_challe
 // ordinary path bit for bit (tests/test_gpu_parity.py::test_graph_path_matches_plain_path).
 static size_t pg_align(size_t x) { return (x + 255) & ~(size_t)255; }
 static bool graph_eligible(const lab_ctx *ctx, const lab_constants *c) {
-    if (ctx->comm || ctx->crs_cache_max || std::getenv("LAB_NO_GRAPH") || std::getenv("LAB_NO_FORK") || std::getenv("LAB_GEN_CONTRACT_MIN_POLYS")) return false;
+    if (ctx->comm || std::getenv("LAB_NO_GRAPH") || std::getenv("LAB_NO_FORK") || std::getenv("LAB_GEN_CONTRACT_MIN_POLYS")) return false;
     const uint64_t R = c->R, N = c->N, K = c->KAPPA;
     const uint64_t bytes = (2 * R * N + R * R + R * K + 3 * K) * 256 + R * LAB_JL_ROWS * N * LAB_D;
     // the generated CRS side of u_1 waits in HBM / L2 between its two kernels: K_1 rows x (R T_1 K + pairs T_2) hats of 128 bytes
@@ -1450,7 +1462,7 @@ static int graph_record(lab_ctx *ctx, const lab_constants *c, const LabSeed &see
         const uint64_t total = R * ND;
         uint32_t *v;
         TRY(arena_alloc(ctx, total, &v));
-        LAUNCH(k_piT_omega2, (unsigned)((total / 16 + 255) / 256), 256, dPi2, dom, total / 16, (uint32_t)(ND / 16), v);
+        TRY(d_piT_omega(ctx, dPi2, dom, total, ND, v));
         LAUNCH(k_phi_pp_dev, (unsigned)((total + 255) / 256), 256, dphi, v, dab + 128, (size_t)total, dpp);    // psi sits behind alpha, beta in the input block
     }
     TRY(d_fwd_hat(ctx, dpp, PPhat, R * N, N, R));
@@ -1531,6 +1543,7 @@ static ProofGraph *graph_build(lab_ctx *ctx, const lab_constants *c, const LabSe
         if (cudaGraphKernelNodeGetParams(nd, &kp) != cudaSuccess) continue;
         const int na = number_of_args(kp.func);
         if (!na) continue;
+        if (kp.func == (const void *)k_crs_gen_hats) g->gen_node = nd;
         ProofGraph::SeedNode sn;
         sn.node = nd; sn.params = kp;
         sn.args.assign(kp.kernelParams, kp.kernelParams + na);
@@ -1558,6 +1571,14 @@ static int prove_graph(lab_ctx *ctx, ProofGraph &g, const lab_constants *c, cons
         kp.kernelParams = sn.args.data();
         CK(cudaGraphExecKernelNodeSetParams(g.exec, sn.node, &kp));
     }
+    // CRS cache on: the hats of u_1's CRS side generated by the previous replay are reused when the seed is the same
+    const bool reuse = ctx->crs_cache_max && g.gen_node && g.hats_valid && std::memcmp(seed_bytes, g.last_seed, 32) == 0;
+    if (g.gen_node && reuse == g.gen_enabled) {
+        CK(cudaGraphNodeSetEnabled(g.exec, g.gen_node, reuse ? 0u : 1u));
+        g.gen_enabled = !reuse;
+    }
+    if (ctx->crs_cache_max) { if (reuse) ctx->crs_cache_hits++; else ctx->crs_cache_misses++; }
+    g.hats_valid = false;
     const size_t pi_bytes = g.packed ? R * LAB_JL_ROWS * ND / 4 : R * LAB_JL_ROWS * ND;
     int att = 0, rejections = 0;
     for (;;) {
@@ -1569,6 +1590,8 @@ static int prove_graph(lab_ctx *ctx, ProofGraph &g, const lab_constants *c, cons
         ctx->graph_replays++;
         TRY(lab_sync(ctx));
         std::memcpy(out->projection_int, g.h_out + g.out.p, LAB_JL_ROWS * sizeof(int64_t));
+        std::memcpy(g.last_seed, seed_bytes, 32);
+        g.hats_valid = true;
         if (valid_projection(c, out->projection_int)) break;
         if (++rejections > 5) FAIL(LAB_ERR_JL_REJECTED, "failed JL... (proofgen.rs:175-176)");
         att++;
@@ -2056,6 +2079,7 @@ extern "C" int lab_prove_batch(lab_ctx *ctx, const lab_constants *c, size_t n_st
         if (!shared_crs && w->batch_cache) { lab_crs_cache_configure(w, 0); w->batch_cache = false; }
     }
     std::vector<int> status(nw, LAB_OK);
+    std::vector<size_t> failed_at(nw, (size_t)-1);
     std::vector<std::thread> threads;
     for (size_t t = 0; t < nw; t++)
         threads.emplace_back([&, t]() {
@@ -2064,14 +2088,19 @@ extern "C" int lab_prove_batch(lab_ctx *ctx, const lab_constants *c, size_t n_st
                 CallScope cs(w);
                 const uint8_t *seed = shared_crs ? seeds : seeds + 32 * b;
                 int rc = prove_one(w, c, seed, S + b * wsz, &st[b], &ch[b], &out[b]);
-                if (rc != LAB_OK) { status[t] = rc; return; }
+                if (rc != LAB_OK) { status[t] = rc; failed_at[t] = b; return; }
             }
         });
     for (auto &th : threads) th.join();
+    size_t first = (size_t)-1, who = 0;              // the failing statement with the lowest index is the one reported
     for (size_t t = 0; t < nw; t++) {
         ctx->launches += ctx->workers[t]->launches;
         ctx->workers[t]->launches = 0;
-        if (status[t] != LAB_OK) { ctx->err = "statement failed in batch worker: " + ctx->workers[t]->err; return status[t]; }
+        if (status[t] != LAB_OK && failed_at[t] < first) { first = failed_at[t]; who = t; }
+    }
+    if (first != (size_t)-1) {
+        ctx->err = "statement " + std::to_string(first) + " failed in a batch worker: " + ctx->workers[who]->err;
+        return status[who];
     }
     return LAB_OK;
 }

@@ -242,6 +242,60 @@ __global__ void __launch_bounds__(256) k_piT_omega2(const uint32_t *__restrict__
     for (int q = 0; q < 4; q++) dst[q] = make_uint4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
 }
 
+// The same for small shapes (a default-size proof has 16 words: 16 threads walking 256 rows each would be one long dependent
+// chain): one WARP per word, lane = 8 of the 256 rows, the 32 packed sums reduced across the lanes with shuffles.
+__global__ void __launch_bounds__(256) k_piT_omega2_warp(const uint32_t *__restrict__ pi2, const uint32_t *__restrict__ omega, uint64_t total_words, uint32_t W,
+                                                         uint32_t *__restrict__ v) {
+    __shared__ uint32_t som[2][256];
+    {
+        const uint32_t o = lab_canon(omega[threadIdx.x]);
+        som[0][threadIdx.x] = o & 127u;
+        som[1][threadIdx.x] = o >> 7;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint64_t idx = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (idx >= total_words) return;
+    const uint64_t i = idx / W, wq = idx % W;
+    const uint32_t *col = pi2 + i * 256 * (uint64_t)W + wq;
+    uint32_t lo[16], hi[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) { lo[k] = 0; hi[k] = 0; }
+    uint32_t x[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) x[jj] = __ldg(col + (uint64_t)(lane * 8 + jj) * W);
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) {
+        const uint32_t ol = som[0][lane * 8 + jj], oh = som[1][lane * 8 + jj];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const uint32_t t = (x[jj] >> k) & 0x00010001u;
+            lo[k] += ol * t;
+            hi[k] += oh * t;
+        }
+    }
+    // each 16-bit half stays below 2^15 over all 256 rows, so packed words add without carries between halves
+#pragma unroll
+    for (int k = 0; k < 16; k++)
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            lo[k] += __shfl_xor_sync(0xffffffffu, lo[k], o);
+            hi[k] += __shfl_xor_sync(0xffffffffu, hi[k], o);
+        }
+    if (lane == 0) {
+        uint32_t out[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const uint32_t pos = (lo[k] & 0xFFFFu) + 128u * (hi[k] & 0xFFFFu);
+            const uint32_t neg = (lo[k] >> 16) + 128u * (hi[k] >> 16);
+            out[k] = lab_canon(pos + 257u * LABQ - neg);
+        }
+        uint4 *dst = reinterpret_cast<uint4 *>(v + idx * 16);
+#pragma unroll
+        for (int q = 0; q < 4; q++) dst[q] = make_uint4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+    }
+}
+
 // JL matrix entries straight into the packed form, same PRG stream and values as k_synth_pi (two bits per entry from PRG
 // word e / 32: 0 -> -1, 3 -> +1, 1 and 2 -> 0; verification.rs:553-566).  Thread per PRG word = two packed words.
 __device__ __forceinline__ uint64_t jl2_prg_u64(uint64_t base, uint64_t idx) {

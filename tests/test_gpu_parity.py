@@ -450,16 +450,26 @@ def test_crs_cache_is_transparent(ctx, orc):
         ok = c2.verify(c, SEED32, phi, a, b, ch, tr1)
         s2 = c2.crs_cache_stats()
         assert ok[0] and s2["hits"] == 3                                          # Checks 15 (A z), 19, 20 from the cache
+        # the second proof of a small shape is recorded as a CUDA graph, which keeps its own copy of u_1's CRS side: generated by
+        # this replay (a miss), reused by the next one under the same seed (a hit: the generation node is disabled)
         tr2 = prover.proof_gen(st, crs).as_oracle_dict()
-        assert c2.crs_cache_stats()["hits"] == 6
+        s3 = c2.crs_cache_stats()
+        assert (s3["hits"], s3["misses"]) == (3, 4) and c2.graph_stats()["graphs"] == 1
+        tr2b = prover.proof_gen(st, crs).as_oracle_dict()
+        s4 = c2.crs_cache_stats()
+        assert (s4["hits"], s4["misses"]) == (4, 4)
         for k in ("t", "g", "u_1", "projection_int", "b_prime_prime", "h", "u_2", "z"):
             assert np.array_equal(tr1[k], ref[k]), k
             assert np.array_equal(tr2[k], ref[k]), k
+            assert np.array_equal(tr2b[k], ref[k]), k
         # a different seed must not hit
         other = bytes(range(1, 33))
         rc, ref_o = orc.prove(co, other, S, phi, a, b, ch, ntt=True, nthreads=8)
         tr3 = prover.proof_gen(st, lb.CRS.from_seed(c, other, c2)).as_oracle_dict()
         assert np.array_equal(tr3["u_1"], ref_o["u_1"]) and np.array_equal(tr3["u_2"], ref_o["u_2"])
+        assert c2.crs_cache_stats()["misses"] == 5
+        tr3b = prover.proof_gen(st, crs).as_oracle_dict()                          # back to the first seed: generated again, not served stale
+        assert np.array_equal(tr3b["u_1"], ref["u_1"]) and c2.crs_cache_stats()["misses"] == 6
         # a tampered transcript is still rejected at the same check when the verifier reads the cache
         bad = dict(tr1); bad["u_1"] = np.array(tr1["u_1"], copy=True); bad["u_1"][0, 0] ^= 1
         assert c2.verify(c, SEED32, phi, a, b, ch, bad)[:2] == (False, 19)
@@ -923,3 +933,27 @@ def test_cpp_header_runs_a_proof(ctx, orc, tmp_path):
     import subprocess
     out = subprocess.run([exe, str(case)], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
+
+
+def test_aggregate_phi_large_shape_uses_thread_per_word_kernel(ctx):
+    """lab_aggregate_phi2 at (N, R) = (512, 32): 65536 packed words, the shape from which Pi^T omega runs one thread per word
+    (k_piT_omega2) instead of one warp per word; reference = the definition in numpy, vector by vector."""
+    N, R = 512, 32
+    c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
+    dpi = ctx.malloc(R * 256 * N * D // 4)
+    ctx.synth_pi2_dev(synth.SEED, 3, 0, R * 256 * N * D, dpi)
+    pi2 = np.empty((R, 256, N * 4), np.uint32)
+    ctx.d2h(pi2, dpi); ctx.sync()
+    ctx.free(dpi)
+    phi = rand_polys(R * N, 18).reshape(R, N, D)
+    omega = synth.prg_zq(9, 7, 256)
+    psi = 8000
+    got = ctx.aggregate_phi2(c, phi, pi2, psi, omega)
+    for i in (0, 7, R - 1):
+        pi = lb.api.unpack_pi(pi2[i]).astype(np.int64)                      # [256][N*64]
+        v = (omega.astype(np.int64) @ pi % Q).reshape(N, D)
+        conj = np.empty_like(v)
+        conj[:, 0] = v[:, 0]
+        conj[:, 1:] = (Q - v[:, :0:-1]) % Q
+        want = ((phi[i].astype(np.int64) * psi + conj) % Q).astype(np.uint32)
+        assert np.array_equal(got[i], want), i
