@@ -1512,8 +1512,13 @@ static ProofGraph *graph_build(lab_ctx *ctx, const lab_constants *c, const LabSe
     const size_t saved_size = ctx->arena_size, saved_off = ctx->arena_off, saved_want = ctx->arena_want;
     const uint64_t l0 = ctx->launches;
     ctx->arena = g->dev; ctx->arena_size = g->dev_bytes; ctx->arena_off = 0;
+    // the recorded kernels must not reference CRS-cache entries (they belong to one seed and can be dropped): K_A and u_2 -- 1.4 % of a
+    // small proof's ChaCha20 -- always regenerate inside the graph; the CRS side of u_1 has the graph's own reuse rule (prove_graph)
+    const size_t saved_cache_max = ctx->crs_cache_max;
+    ctx->crs_cache_max = 0;
     bool ok = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
     int rc = ok ? graph_record(ctx, c, seed, *g) : LAB_ERR_CUDA;
+    ctx->crs_cache_max = saved_cache_max;
     cudaGraph_t graph = nullptr;
     if (ok && cudaStreamEndCapture(ctx->stream, &graph) != cudaSuccess) { graph = nullptr; cudaGetLastError(); }
     const bool overflowed = !ctx->overflow.empty();
