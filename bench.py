@@ -18,7 +18,7 @@ only distributes the NCCL id, synchronises the ranks around the timed region and
   value        inputs resident in HBM, CUDA-event timed on the library's stream, max over ranks
   e2e          same step through the host-buffer C ABI (pinned host buffers, H2D/D2H inside the timed region)
   roofline     dominant kernel k_commit_inner against the MEASURED ALU-pipe ceiling (ChaCha20 xor+rotate
-               cannot leave the ALU pipe: 596 ALU-pipe lane-ops per CRS coefficient); roofline_ntt is the
+               cannot leave the ALU pipe: 576 ALU-pipe lane-ops per CRS coefficient); roofline_ntt is the
                HBM roofline of the batched NTT kernel (512 algorithmic bytes per polynomial)
   cpu_baseline the oracle (restatement of the reference algorithm, NTT multiplication path) on the host
                cores, on a bounded sample of commitment rows, extrapolated to the whole step
@@ -49,8 +49,9 @@ PRG_SEED = 0x4C61425241444F52
 D, Q, JL = 64, 8191, 256
 # ALU-pipe lane-ops (xor + rotate) one CRS coefficient needs: 20 rounds x 4 quarter-rounds x 4 steps x 2 = 640 for a full
 # ChaCha20 block, minus 28 in the first double round (the part that does not depend on key word 7 is computed once per
-# 2^32 counters) minus 16 in the last diagonal round (only keystream words 0..3 are consumed) = 596 (lab_chacha.cuh)
-ALU_OPS_PER_BLOCK = 596
+# 2^32 counters) minus 36 in the last double round (keystream word 3 alone decides the sample except with probability 2^-13,
+# so only the cone of x3 is computed) = 576 (lab_chacha.cuh; counted by tests/test_host.py).  Rounds 1 and early 2 used 596.
+ALU_OPS_PER_BLOCK = 576
 
 
 def workload_shape(name):
@@ -446,7 +447,7 @@ def run_cfg1(args, rank, world, local_rank):
             "gpu_launches": first["launches_per_proof"] * args.steps, "clocks": clocks,
             "roofline": {"kernel": "k_crs_matvec", "bound": "int32_alu", "achieved": first["chacha_blocks_per_s_prove"] * ALU_OPS_PER_BLOCK / 1e9, "peak": ctx.alu_peak() / 1e9,
                          "unit": "Gop/s", "frac": first["chacha_blocks_per_s_prove"] * ALU_OPS_PER_BLOCK / ctx.alu_peak(), "traffic": None,
-                         "note": "whole-proof CRS coefficients x 596 ALU ops over the whole prove() wall time (launch latency included)"},
+                         "note": "whole-proof CRS coefficients x 576 ALU ops over the whole prove() wall time (launch latency included)"},
             "cpu_baseline": cpu, "extra": {"sweep": tab, "proof_graphs": ctx.graph_stats()}}
     _finish_line(line, rank, world)
     ctx.close()
@@ -528,7 +529,7 @@ def run_prove(args, rank, world, local_rank):
             "gpu_launches": launches, "clocks": clocks,
             "roofline": {"kernel": "k_crs_matvec", "bound": "int32_alu", "achieved": blocks / world * ALU_OPS_PER_BLOCK / tp / 1e9, "peak": alu / 1e9, "unit": "Gop/s",
                          "frac": blocks / world * ALU_OPS_PER_BLOCK / tp / alu, "traffic": None,
-                         "note": "per-GPU share of the proof's CRS coefficients x 596 ALU ops over the whole prove() wall time"},
+                         "note": "per-GPU share of the proof's CRS coefficients x 576 ALU ops over the whole prove() wall time"},
             "cpu_baseline": None,
             "extra": {"prove_ms": tp * 1e3, "verify_ms": tv * 1e3, "verify_accepts": bool(ok[0]), "crs_coefficients_per_proof": blocks,
                       "chacha_blocks_per_s_whole_job": blocks / tp,
@@ -823,7 +824,7 @@ def main():
         roof = {"kernel": "inner commitment: k_gen_planes (ChaCha20 + transform -> int8 limb planes, 99 % of it) + k_umma_commit (tcgen05 contraction)", "bound": "int32_alu", "achieved": achieved / 1e9, "peak": alu_peak / 1e9, "unit": "Gop/s",
                 "frac": achieved / alu_peak,
                 "frac_survey_8d": blocks * 964 / (k_ms * 1e-3) / 3.7e13,
-                "frac_note": "frac = 596 ALU-pipe lane-ops per coefficient against the MEASURED LOP3+SHF ceiling; frac_survey_8d = SURVEY 8(d)'s own "
+                "frac_note": "frac = 576 ALU-pipe lane-ops per coefficient against the MEASURED LOP3+SHF ceiling; frac_survey_8d = SURVEY 8(d)'s own "
                              "definition, 964 u32 ops per ChaCha20 block against the nominal 148 SM x 128 lanes x 1.965 GHz = 3.7e13 op/s",
                 "traffic": (lambda d: d and (d["dram_bytes_read_per_call"] + d["dram_bytes_write_per_call"]))(traffic_db.get("inner_commitment_cfg3"))
                 if (args.workload == "cfg3" and world == 1) else None,
@@ -832,7 +833,7 @@ def main():
                                 "through HBM as int8 limb planes between the ChaCha20 kernel and the tensor-core contraction (1.6 % of the HBM bandwidth)",
                 "share_of_step": k_ms / ms_step,
                 "chacha_blocks_per_s": blocks / (k_ms * 1e-3), "kernel_ms": k_ms,
-                "note": "algorithmic ops = 596 ALU-pipe lane-ops (xor + rotate) per CRS coefficient = one ChaCha20 block minus the hoisted part "
+                "note": "algorithmic ops = 576 ALU-pipe lane-ops (xor + rotate) per CRS coefficient = one ChaCha20 block minus the hoisted part "
                         "of its first double round and the dead tail of its last; "
                         "peak = LOP3+SHF microbenchmark measured in this run (no driver-measured INT32 peak exists); HBM is idle here"}
         # CRS-resident variant (reported beside the cold headline, never instead of it): with lab_crs_cache_configure the

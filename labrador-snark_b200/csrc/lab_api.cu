@@ -104,6 +104,10 @@ struct lab_ctx {
     // lab_crs_cache_configure and lab_ctx_destroy
     void *gc_chunk = nullptr;
     size_t gc_chunk_bytes = 0;
+    // its contraction stream: the tensor-core contraction of chunk k (and the download of its rows) runs beside the ChaCha20
+    // generation of chunk k + 1, which needs neither the tensor pipe nor HBM; two chunk buffers, one event pair each
+    cudaStream_t gc_stream = nullptr;
+    cudaEvent_t gc_gen[2] = {nullptr, nullptr}, gc_con[2] = {nullptr, nullptr}, gc_join = nullptr;
     // worker contexts (own stream + arena each) for lab_prove_batch: independent statements overlap host-side
     // enqueueing of one proof with the GPU work of the others
     std::vector<lab_ctx *> workers;
@@ -257,6 +261,12 @@ extern "C" void lab_ctx_destroy(lab_ctx *ctx) {
     if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->ev_tg); }
     for (auto &p : ctx->mv_plans) cudaFree(p.dev);
     for (auto &e : ctx->crs_cache) cudaFree(e.dev);
+    if (ctx->gc_stream) {
+        cudaStreamSynchronize(ctx->gc_stream);
+        cudaStreamDestroy(ctx->gc_stream);
+        for (int b = 0; b < 2; b++) { cudaEventDestroy(ctx->gc_gen[b]); cudaEventDestroy(ctx->gc_con[b]); }
+        cudaEventDestroy(ctx->gc_join);
+    }
     if (ctx->gc_chunk) cudaFree(ctx->gc_chunk);
     for (lab_ctx *w : ctx->workers) lab_ctx_destroy(w);
     lab_comm_destroy(ctx);
@@ -591,6 +601,24 @@ struct Stream2Guard {
     void disarm() { armed = false; }
     ~Stream2Guard() { if (armed && s2) cudaStreamSynchronize(s2); }
 };
+static int ensure_gc_stream(lab_ctx *ctx) {
+    if (ctx->gc_stream) return LAB_OK;
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));          // hi = numerically lowest = greatest priority: the short contraction's
+    CK(cudaStreamCreateWithPriority(&ctx->gc_stream, cudaStreamNonBlocking, hi));   // CTAs go ahead of the generator's later waves
+    for (int b = 0; b < 2; b++) {
+        CK(cudaEventCreateWithFlags(&ctx->gc_gen[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->gc_con[b], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&ctx->gc_join, cudaEventDisableTiming));
+    return LAB_OK;
+}
+// launches of a scope go to another stream of the ctx
+struct CtxStreamSwap {
+    lab_ctx *c; cudaStream_t saved;
+    CtxStreamSwap(lab_ctx *cx, cudaStream_t to) : c(cx), saved(cx->stream) { cx->stream = to; }
+    ~CtxStreamSwap() { c->stream = saved; }
+};
 // transient limb planes for `rows_c` rows of `per_row` bytes (kept in the ctx between calls); nullptr when there is no room
 static void *gc_chunk_get(lab_ctx *ctx, size_t bytes) {
     if (ctx->gc_chunk && ctx->gc_chunk_bytes >= bytes) return ctx->gc_chunk;
@@ -707,28 +735,54 @@ static int d_commit_inner(lab_ctx *ctx, const LabSeed &seed, const uint32_t *Wha
         uint64_t rows_c = budget / per_row / 64 * 64;
         if (rows_c > nrows) rows_c = (nrows + 63) / 64 * 64;
         if (rows_c >= 64) {
-            uint8_t *chunk = (uint8_t *)gc_chunk_get(ctx, rows_c * per_row);
+            // more than one chunk: two buffers, the contraction of chunk k on its own stream beside the generation of chunk k + 1
+            // (LAB_GC_OVERLAP=0: one buffer, one stream)
+            const char *ov = std::getenv("LAB_GC_OVERLAP");
+            const bool overlap_on = !(ov && ov[0] == '0');
+            bool overlap = overlap_on && nrows > rows_c;
+            const size_t chunk_bytes = rows_c * per_row;
+            uint8_t *chunk = (uint8_t *)gc_chunk_get(ctx, overlap ? 2 * chunk_bytes : chunk_bytes);
+            if (!chunk && overlap) { overlap = false; chunk = (uint8_t *)gc_chunk_get(ctx, chunk_bytes); }
             if (chunk) {
                 UmmaScratch sc;              // first use is the largest (rows_c rows): the arena allocation fits every chunk
                 const bool stream_out = T_host && host_done && t_stride == nrows && t_row_off == 0;
-                if (stream_out) TRY(ensure_stream2(ctx));
-                Stream2Guard s2guard(stream_out ? ctx->stream2 : nullptr);
-                for (uint64_t r0 = 0; r0 < nrows; r0 += rows_c) {
+                if (stream_out && !overlap) TRY(ensure_stream2(ctx));
+                if (overlap) TRY(ensure_gc_stream(ctx));
+                cudaStream_t side = overlap ? ctx->gc_stream : (stream_out ? ctx->stream2 : nullptr);
+                Stream2Guard s2guard(side);
+                cudaStream_t main_stream = ctx->stream;
+                uint64_t k = 0;
+                for (uint64_t r0 = 0; r0 < nrows; r0 += rows_c, k++) {
                     const uint64_t nr = std::min<uint64_t>(rows_c, nrows - r0);
                     const uint32_t nt = (uint32_t)((nr + 63) / 64);
-                    TRY(gen_planes(chunk, r0, nr, nt));
-                    TRY(contract(chunk, r0, nr, nt, sc));
-                    if (stream_out) {            // rows [r0, r0 + nr) of every t_i: R strips of nr * 256 bytes
-                        CK(cudaEventRecord(ctx->ev_tg, ctx->stream));
-                        CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_tg, 0));
-                        CK(cudaMemcpy2DAsync(T_host + r0 * 64, nrows * 64 * sizeof(uint32_t), T + r0 * 64, nrows * 64 * sizeof(uint32_t), nr * 64 * sizeof(uint32_t), R,
-                                             cudaMemcpyDeviceToHost, ctx->stream2));
+                    const int b = overlap ? (int)(k & 1) : 0;
+                    uint8_t *buf = chunk + (size_t)b * chunk_bytes;
+                    if (overlap && k >= 2) CK(cudaStreamWaitEvent(main_stream, ctx->gc_con[b], 0));     // buffer b contracted
+                    TRY(gen_planes(buf, r0, nr, nt));
+                    if (overlap) {
+                        CK(cudaEventRecord(ctx->gc_gen[b], main_stream));
+                        CK(cudaStreamWaitEvent(side, ctx->gc_gen[b], 0));
+                        {
+                            CtxStreamSwap swap(ctx, side);
+                            TRY(contract(buf, r0, nr, nt, sc));
+                        }
+                    } else {
+                        TRY(contract(buf, r0, nr, nt, sc));
+                        if (stream_out) {
+                            CK(cudaEventRecord(ctx->ev_tg, ctx->stream));
+                            CK(cudaStreamWaitEvent(side, ctx->ev_tg, 0));
+                        }
                     }
+                    if (stream_out)              // rows [r0, r0 + nr) of every t_i: R strips of nr * 256 bytes
+                        CK(cudaMemcpy2DAsync(T_host + r0 * 64, nrows * 64 * sizeof(uint32_t), T + r0 * 64, nrows * 64 * sizeof(uint32_t), nr * 64 * sizeof(uint32_t), R,
+                                             cudaMemcpyDeviceToHost, side));
+                    if (overlap) CK(cudaEventRecord(ctx->gc_con[b], side));
                 }
-                if (stream_out) {
-                    CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
-                    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-                    *host_done = true;
+                if (side) {
+                    cudaEvent_t ej = overlap ? ctx->gc_join : ctx->ev_join;
+                    CK(cudaEventRecord(ej, side));
+                    CK(cudaStreamWaitEvent(main_stream, ej, 0));
+                    if (stream_out) *host_done = true;
                 }
                 s2guard.disarm();
                 return LAB_OK;

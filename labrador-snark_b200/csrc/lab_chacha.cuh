@@ -10,7 +10,9 @@
 // trimmed to what the result depends on:
 //   * only key word 7 (the byte-swapped low 32 bits of seed + counter) differs between neighbouring coefficients, so the
 //     part of the first double round that does not depend on it is computed once per 2^32 counters (LabHoist);
-//   * only keystream words 0..3 of block 0 are consumed, so the last diagonal round stops at the second `a` update;
+//   * the sample is decided by keystream word 3 alone except with probability 2^-13 (lab_sample_w3), so only the cone of
+//     x3 is computed: the last diagonal round is one quarter round cut at its second `a` update, and the last column round
+//     stops at the four words that quarter round reads (b of column 0, c of column 1, d of column 2, a of column 3);
 //   * xor and rotate exist only on the ALU pipe; the additions are written b * one + a (IMAD, FMA pipe) and a
 //     compile-time mask moves selected rotations to the FMA pipe as rotl(x, n) = hi32(x * 2^n) + lo32(x * 2^n)
 //     (IMAD + IMAD.HI) until both pipes carry the same load.
@@ -61,6 +63,21 @@ __device__ __forceinline__ void lab_qr_a_only(uint32_t &a, uint32_t b, uint32_t 
     a = lab_addf(a, b, s.one); d = lab_rot<16, (M & 1u) != 0>(d ^ a, s);
     c = lab_addf(c, d, s.one); b = lab_rot<12, (M & 2u) != 0>(b ^ c, s);
     a = lab_addf(a, b, s.one);
+}
+
+// the same, stopping once `c` is final (skips the last update of b) / once `d` is final (skips the last c and b)
+template <uint32_t M>
+__device__ __forceinline__ void lab_qr_c_only(uint32_t a, uint32_t b, uint32_t &c, uint32_t d, const LabSeed &s) {
+    a = lab_addf(a, b, s.one); d = lab_rot<16, (M & 1u) != 0>(d ^ a, s);
+    c = lab_addf(c, d, s.one); b = lab_rot<12, (M & 2u) != 0>(b ^ c, s);
+    a = lab_addf(a, b, s.one); d = lab_rot<8, (M & 4u) != 0>(d ^ a, s);
+    c = lab_addf(c, d, s.one);
+}
+template <uint32_t M>
+__device__ __forceinline__ void lab_qr_d_only(uint32_t a, uint32_t b, uint32_t c, uint32_t &d, const LabSeed &s) {
+    a = lab_addf(a, b, s.one); d = lab_rot<16, (M & 1u) != 0>(d ^ a, s);
+    c = lab_addf(c, d, s.one); b = lab_rot<12, (M & 2u) != 0>(b ^ c, s);
+    a = lab_addf(a, b, s.one); d = lab_rot<8, (M & 4u) != 0>(d ^ a, s);
 }
 
 // one double round on NB interleaved states; RM = 32-bit mask, nibble q = lab_qr mask of quarter round q
@@ -149,9 +166,9 @@ __device__ __forceinline__ void lab_hoist_update(const LabSeed &seed, uint64_t c
     if (tag != h.tag_lo || chi != h.tag_hi) lab_hoist_compute(seed, clo, chi, h);
 }
 
-// keystream words 0..3 of block 0 for NB keys that share h and differ in key word 7
+// keystream word 3 of block 0 (the top 32 bits of the 128-bit draw) for NB keys that share h and differ in key word 7
 template <int NB, uint32_t RM>
-__device__ __forceinline__ void lab_chacha_w03(const LabSeed &s, const LabHoist &h, const uint32_t (&k7)[NB], uint32_t (&w)[NB][4]) {
+__device__ __forceinline__ void lab_chacha_w3(const LabSeed &s, const LabHoist &h, const uint32_t (&k7)[NB], uint32_t (&w3)[NB]) {
     uint32_t x[NB][16];
     const uint32_t one = s.one;
     // ---- first double round, hoisted ----
@@ -195,24 +212,20 @@ __device__ __forceinline__ void lab_chacha_w03(const LabSeed &s, const LabHoist 
     // ---- double rounds 2..9 ----
 #pragma unroll 1
     for (int r = 0; r < 8; r++) lab_double_round<NB, RM>(x, s);
-    // ---- double round 10: full column round, diagonal round only as far as x0..x3 need ----
+    // ---- double round 10, only the cone of x3: the diagonal quarter round (x3, x4, x9, x14) up to its second `a` update, and
+    //      of the column round what that reads -- column 0 up to b (all of it), column 1 up to c, column 2 up to d, column 3 up to a.
+    //      576 xor / rotate operations per block depend on key word 7 in this form (640 in the plain block).
 #pragma unroll
     for (int b = 0; b < NB; b++) {
         lab_qr<(RM >> 0) & 15u>(x[b][0], x[b][4], x[b][8], x[b][12], s);
-        lab_qr<(RM >> 4) & 15u>(x[b][1], x[b][5], x[b][9], x[b][13], s);
-        lab_qr<(RM >> 8) & 15u>(x[b][2], x[b][6], x[b][10], x[b][14], s);
-        lab_qr<(RM >> 12) & 15u>(x[b][3], x[b][7], x[b][11], x[b][15], s);
+        lab_qr_c_only<(RM >> 4) & 15u>(x[b][1], x[b][5], x[b][9], x[b][13], s);
+        lab_qr_d_only<(RM >> 8) & 15u>(x[b][2], x[b][6], x[b][10], x[b][14], s);
+        lab_qr_a_only<(RM >> 12) & 15u>(x[b][3], x[b][7], x[b][11], x[b][15], s);
     }
 #pragma unroll
     for (int b = 0; b < NB; b++) {
-        lab_qr_a_only<(RM >> 16) & 15u>(x[b][0], x[b][5], x[b][10], x[b][15], s);
-        lab_qr_a_only<(RM >> 20) & 15u>(x[b][1], x[b][6], x[b][11], x[b][12], s);
-        lab_qr_a_only<(RM >> 24) & 15u>(x[b][2], x[b][7], x[b][8], x[b][13], s);
         lab_qr_a_only<(RM >> 28) & 15u>(x[b][3], x[b][4], x[b][9], x[b][14], s);
-        w[b][0] = lab_addf(x[b][0], LAB_CC0, one);
-        w[b][1] = lab_addf(x[b][1], LAB_CC1, one);
-        w[b][2] = lab_addf(x[b][2], LAB_CC2, one);
-        w[b][3] = lab_addf(x[b][3], LAB_CC3, one);
+        w3[b] = lab_addf(x[b][3], LAB_CC3, one);
     }
 }
 
@@ -238,6 +251,17 @@ __device__ __forceinline__ bool lab_sample_u128(uint32_t w0, uint32_t w1, uint32
     t = (uint64_t)w3 * LABQ + (t >> 32);
     out = (uint32_t)(t >> 32);
     return ((uint32_t)t) < 0xFFF80000u;      // top 13 bits of the low half not all ones
+}
+
+// The same decision from the TOP keystream word alone.  v * Q = (w3 * Q) * 2^96 + rest * Q with rest = w2:w1:w0 < 2^96, so
+// floor(rest * Q / 2^96) <= Q - 1: with L = lo32(w3 * Q) the top 32 bits of the low half of the product lie in
+// [L, L + Q - 1].  When that interval ends below the rejection zone 0xFFF80000 (and therefore below 2^32: no carry into the
+// high half) the draw is accepted with the value hi32(w3 * Q) whatever words 0..2 are.  Otherwise -- probability
+// 2^-13 (1 + 2^-6) -- the caller recomputes the coefficient on the generic path from draw 0.
+__device__ __forceinline__ bool lab_sample_w3(uint32_t w3, uint32_t &out) {
+    const uint64_t t = (uint64_t)w3 * LABQ;
+    out = (uint32_t)(t >> 32);
+    return (uint32_t)t < 0xFFF80000u - (LABQ - 1u);
 }
 
 // generic path: any counter, any number of rejected draws (`first_attempt` of them already known to be rejected).
@@ -268,12 +292,12 @@ __device__ __noinline__ uint32_t lab_crs_coeff_slow(const LabSeed &seed, uint64_
 
 // NB coefficients at counters (chi:clo) + off[b].  h is the caller's hoist cache (lab_hoist_invalidate once, then reuse
 // across calls: it is refreshed here when the high part of seed + counter changes).  A block whose offset carries out
-// of the low 32 bits of seed + clo, or whose first draw is rejected, is recomputed by the generic path.
+// of the low 32 bits of seed + clo, or whose first draw word 3 alone does not decide, is recomputed by the generic path.
 template <int NB, uint32_t RM>
 __device__ __forceinline__ void lab_crs_coeffs(const LabSeed &seed, LabHoist &h, uint64_t clo, uint64_t chi, const uint32_t (&off)[NB], uint32_t (&out)[NB]) {
     lab_hoist_update(seed, clo, chi, h);
     const uint32_t lo32 = (uint32_t)seed.limb[0] + (uint32_t)clo;
-    uint32_t k7[NB], w[NB][4];
+    uint32_t k7[NB], w3[NB];
     bool slow[NB];
 #pragma unroll
     for (int b = 0; b < NB; b++) {
@@ -281,14 +305,14 @@ __device__ __forceinline__ void lab_crs_coeffs(const LabSeed &seed, LabHoist &h,
         slow[b] = t < off[b];
         k7[b] = lab_bswap32(t);
     }
-    lab_chacha_w03<NB, RM>(seed, h, k7, w);
+    lab_chacha_w3<NB, RM>(seed, h, k7, w3);
 #pragma unroll
     for (int b = 0; b < NB; b++) {
-        const bool ok = lab_sample_u128(w[b][0], w[b][1], w[b][2], w[b][3], out[b]);
+        const bool ok = lab_sample_w3(w3[b], out[b]);
         if (slow[b] || !ok) {
             uint64_t lo = clo + off[b];
             uint64_t hi = chi + (lo < clo);
-            out[b] = lab_crs_coeff_slow(seed, lo, hi, slow[b] ? 0u : 1u);
+            out[b] = lab_crs_coeff_slow(seed, lo, hi, 0u);
         }
     }
 }

@@ -1,6 +1,6 @@
 // One CRS polynomial per warp, straight into the transform domain -- the producer step shared by the CRS-regenerating
 // kernels (k_gen_planes, k_crs_matvec): trimmed ChaCha20 for coefficients lane and lane + 32 (lab_chacha.cuh), rand-0.8.5
-// sampling, generic path for rejected draws and for polynomials that straddle a 2^32 boundary of seed + counter, warp
+// sampling from keystream word 3 (lab_sample_w3), generic path for draws it does not decide and for polynomials that straddle a 2^32 boundary of seed + counter, warp
 // transform with the constants in shared memory.  The hoisted part of the first double round lives in a per-warp shared-
 // memory slot (15 words) and is recomputed when the high part of seed + counter changes, so a producer thread carries
 // two ChaCha20 states and little else (72 registers, three CTAs of 256 threads per SM).
@@ -41,19 +41,19 @@ __device__ __forceinline__ void lab_crs_poly_hat_warp(const LabSeed &seed, LabWa
     LabHoist h;
     lab_hoist_load(hoist_slot, h);
     const uint32_t k7[2] = {lab_bswap32(lo32 + (uint32_t)lane), lab_bswap32(lo32 + (uint32_t)lane + 32u)};
-    uint32_t wd[2][4], c[2];
-    lab_chacha_w03<2, 0u>(seed, h, k7, wd);
+    uint32_t w3[2], c[2];
+    lab_chacha_w3<2, 0u>(seed, h, k7, w3);
     uint32_t slow = straddle ? 3u : 0u;
-    slow |= lab_sample_u128(wd[0][0], wd[0][1], wd[0][2], wd[0][3], c[0]) ? 0u : 1u;
-    slow |= lab_sample_u128(wd[1][0], wd[1][1], wd[1][2], wd[1][3], c[1]) ? 0u : 2u;
+    slow |= lab_sample_w3(w3[0], c[0]) ? 0u : 1u;
+    slow |= lab_sample_w3(w3[1], c[1]) ? 0u : 2u;
     if (slow) {
         if (slow & 1u) {
             const uint64_t l0 = clo + (uint64_t)lane;
-            c[0] = lab_crs_coeff_generic(seed, l0, chi + (l0 < clo), straddle ? 0u : 1u);
+            c[0] = lab_crs_coeff_generic(seed, l0, chi + (l0 < clo), 0u);
         }
         if (slow & 2u) {
             const uint64_t l1 = clo + (uint64_t)lane + 32u;
-            c[1] = lab_crs_coeff_generic(seed, l1, chi + (l1 < clo), straddle ? 0u : 1u);
+            c[1] = lab_crs_coeff_generic(seed, l1, chi + (l1 < clo), 0u);
         }
     }
     re = c[0]; im = c[1];

@@ -587,23 +587,23 @@ __global__ void __launch_bounds__(ka_threads(PP), 1) k_commit_inner(LabSeed seed
                 }
                 const uint32_t lo32 = (uint32_t)s0;
                 // a tile slice that straddles a 2^32 boundary of seed + counter (key word 6 differs from the hoisted one for
-                // some lanes; once per 2^26 polynomials) takes the generic path, and so do coefficients whose first draw is rejected
+                // some lanes; once per 2^26 polynomials) takes the generic path, and so do coefficients whose first draw word 3 does not decide
                 const bool straddle = lo32 > 0xFFFFFFFFu - (PSTEP * (PP - 1) + 63u);
                 LabHoist h;
                 const uint32_t *q = hoist[w];
                 h.k3 = q[0]; h.P0 = q[1]; h.P1 = q[2]; h.Q0 = q[3]; h.A5 = q[4]; h.A10 = q[5]; h.Q1 = q[6]; h.Q2 = q[7];
                 h.A6 = q[8]; h.A2 = q[9]; h.A8 = q[10]; h.A13 = q[11]; h.A4 = q[12]; h.A9 = q[13]; h.A14 = q[14];
-                uint32_t k7[NB], wd[NB][4];
+                uint32_t k7[NB], w3[NB];
 #pragma unroll
                 for (int b = 0; b < NB; b++) k7[b] = lab_bswap32(lo32 + (uint32_t)lane + 32u * (b & 1) + PSTEP * (b >> 1));
-                lab_chacha_w03<NB, RM>(seed, h, k7, wd);
+                lab_chacha_w3<NB, RM>(seed, h, k7, w3);
                 uint32_t slow = straddle ? (1u << NB) - 1u : 0u;
 #pragma unroll
-                for (int b = 0; b < NB; b++) slow |= lab_sample_u128(wd[b][0], wd[b][1], wd[b][2], wd[b][3], c[b]) ? 0u : 1u << b;
+                for (int b = 0; b < NB; b++) slow |= lab_sample_w3(w3[b], c[b]) ? 0u : 1u << b;
                 if (slow) {      // inlined: a call here would pin the ChaCha state to the ABI's registers
 #pragma unroll
                     for (int b = 0; b < NB; b++)
-                        if (slow >> b & 1u) c[b] = lab_crs_coeff_generic(seed, ctr + lane + 32u * (b & 1) + PSTEP * (b >> 1), 0ull, straddle ? 0u : 1u);
+                        if (slow >> b & 1u) c[b] = lab_crs_coeff_generic(seed, ctr + lane + 32u * (b & 1) + PSTEP * (b >> 1), 0ull, 0u);
                 }
 #pragma unroll
                 for (int p = 0; p < PP; p++) {

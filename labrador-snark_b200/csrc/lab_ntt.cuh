@@ -16,11 +16,15 @@ static __constant__ uint32_t LAB_TW_INV[32] = LAB_TW_INV_INIT;
 
 // per-lane multipliers: stage s (len = 16 >> s) uses tree node (1 << s) + (lane >> (5 - s)).
 // Lower lanes of a butterfly multiply by 1 so that the code is branch-free.  The forward constants are kept
-// unpacked (re, im, -im) together with the butterfly sign and offset, so that a stage costs only 8 ALU-pipe
-// instructions (6 fold shifts + 2 unpacks); everything else is IMAD on the FMA pipe.
+// unpacked (re, im, -im) together with the butterfly sign and offset, so that a stage costs only 6 ALU-pipe
+// instructions (4 fold shifts + 2 unpacks); everything else is IMAD on the FMA pipe.
+// Bounds of a forward stage (asserted on the host in tests/test_host.py): values enter < Q + 16, the twiddle parts are
+// <= Q, so a product sum is < 2^27.01 and ONE fold leaves it <= 24595 < 4Q -- small enough for the 16-bit halves of the
+// shuffled word and for the upper lanes' lo - t + 4Q to stay positive; the sum of a butterfly is < 2^16, and one more fold
+// brings it back below Q + 16.
 struct LabWarpTw {
-    uint32_t fr[5], fi[5], nfi[5];   // forward: upper lanes zeta^(e/2), lower lanes 1; nfi = 2Q - fi
-    uint32_t sgn[5], off[5];         // forward butterfly: out = p * sgn + (recv + off); upper: (-1, 2Q), lower: (1, 0)
+    uint32_t fr[5], fi[5], nfi[5];   // forward: upper lanes zeta^(e/2), lower lanes 1; nfi = Q - fi
+    uint32_t sgn[5], off[5];         // forward butterfly: out = p * sgn + (recv + off); upper: (-1, 4Q), lower: (1, 0)
     uint32_t g[5];                   // inverse: upper lanes zeta^-(e/2), lower lanes 1; last level also carries 2^8 = 32^-1
 };
 
@@ -34,9 +38,9 @@ __device__ __forceinline__ LabWarpTw lab_warp_tw(int lane) {
         const uint32_t f = upper ? LAB_TW_FWD[node] : 1u;
         t.fr[s] = lab_re(f);
         t.fi[s] = lab_im(f);
-        t.nfi[s] = 2u * LABQ - lab_im(f);
+        t.nfi[s] = LABQ - lab_im(f);
         t.sgn[s] = upper ? 0xFFFFFFFFu : 1u;
-        t.off[s] = upper ? 2u * LABQ : 0u;
+        t.off[s] = upper ? 4u * LABQ : 0u;
         uint32_t g = upper ? LAB_TW_INV[node] : 1u;
         if (s == 0) {   // len == 16 is the LAST inverse level: fold in 32^-1 = 256
             uint32_t gr = lab_canon(lab_re(g) * 256u), gi = lab_canon(lab_im(g) * 256u);
@@ -54,13 +58,13 @@ __device__ __forceinline__ void lab_ntt32_fwd_warp(uint32_t &re, uint32_t &im, c
 #pragma unroll
     for (int s = 0; s < 5; s++) {
         const int len = 16 >> s;
-        uint32_t pr = re * tw.fr[s] + im * tw.nfi[s];                        // < 2^29
+        uint32_t pr = re * tw.fr[s] + im * tw.nfi[s];                        // < 2^27.01
         uint32_t pi = re * tw.fi[s] + im * tw.fr[s];
-        pr = lab_fold(lab_fold(pr));                                         // < 2Q
-        pi = lab_fold(lab_fold(pi));
+        pr = lab_fold(pr);                                                   // <= 24595 < 4Q
+        pi = lab_fold(pi);
         const uint32_t recv = __shfl_xor_sync(0xffffffffu, pi * 65536u + pr, len);
-        // lower: lo + t ; upper: lo - t + 2Q  (t is the upper lane's product, lo the lower lane's value)
-        re = lab_fold(pr * tw.sgn[s] + (lab_re(recv) * one + tw.off[s]));    // < Q + 4
+        // lower: lo + t ; upper: lo - t + 4Q  (t is the upper lane's product, lo the lower lane's value)
+        re = lab_fold(pr * tw.sgn[s] + (lab_re(recv) * one + tw.off[s]));    // < Q + 16
         im = lab_fold(pi * tw.sgn[s] + (lab_im(recv) * one + tw.off[s]));
     }
     re = lab_csub(re);
@@ -88,8 +92,8 @@ __device__ __forceinline__ void lab_ntt32_fwd_warp_smem(uint32_t &re, uint32_t &
         const uint32_t fr = tws[s][lane], fi = tws[5 + s][lane], nfi = tws[10 + s][lane], sgn = tws[15 + s][lane], off = tws[20 + s][lane];
         uint32_t pr = re * fr + im * nfi;
         uint32_t pi = re * fi + im * fr;
-        pr = lab_fold(lab_fold(pr));
-        pi = lab_fold(lab_fold(pi));
+        pr = lab_fold(pr);
+        pi = lab_fold(pi);
         const uint32_t recv = __shfl_xor_sync(0xffffffffu, pi * 65536u + pr, len);
         re = lab_fold(pr * sgn + (lab_re(recv) * one + off));
         im = lab_fold(pi * sgn + (lab_im(recv) * one + off));

@@ -128,6 +128,36 @@ def test_crs_rejection_path(ctx, orc):
     assert np.array_equal(got, orc.crs_polys(SEED32, 7, 2048))
 
 
+def test_crs_draws_the_top_keystream_word_does_not_decide(ctx, orc):
+    """The device samples from keystream word 3 alone (lab_sample_w3) and sends a coefficient to the generic path when
+    L = lo32(w3 * Q) >= 0xFFF80000 - (Q - 1): there words 0..2 decide between accept (most of the band) and reject.  2^22
+    coefficients, classified with the independent numpy ChaCha20 of oracle/pyref.py, contain both kinds; all of them must equal
+    the oracle's literal sample_single."""
+    import pyref
+    n_polys, start = 1 << 16, 11
+    n = n_polys * D
+    low = int.from_bytes(SEED32[24:], "big") + start
+    ctr = np.uint64(low) + np.arange(n, dtype=np.uint64)
+    keys = np.empty((n, 8), np.uint32)
+    keys[:, :6] = np.frombuffer(SEED32[:24], "<u4")
+    keys[:, 6] = (ctr >> np.uint64(32)).astype(np.uint32).byteswap()
+    keys[:, 7] = (ctr & np.uint64(0xFFFFFFFF)).astype(np.uint32).byteswap()
+    w = pyref.chacha20_blocks(keys)[:, :4].astype(np.uint64)
+    L = (w[:, 3] * np.uint64(Q)) & np.uint64(0xFFFFFFFF)
+    band = np.nonzero(L >= np.uint64(0xFFF80000 - (Q - 1)))[0]
+    zone = (Q << 115) - 1
+    rejected = 0
+    for t in band:
+        v = int(w[t, 0]) | int(w[t, 1]) << 32 | int(w[t, 2]) << 64 | int(w[t, 3]) << 96
+        rejected += ((v * Q) & ((1 << 128) - 1)) > zone
+    assert rejected >= 100 and len(band) - rejected >= 1, (len(band), rejected)
+    ref = orc.crs_polys(SEED32, start, n_polys)
+    fast = np.ones(n, bool); fast[band] = False
+    assert np.array_equal(ref.reshape(-1)[fast], ((w[:, 3] * np.uint64(Q)) >> np.uint64(32)).astype(np.uint32)[fast])
+    got = ctx.crs_expand(SEED32, start, n_polys)
+    assert np.array_equal(got, ref)
+
+
 def test_crs_fetch_offsets(ctx, orc):
     c = lb.RuntimeConstants.new(2, 3)
     co, _ = orc.constants(2, 3)
@@ -504,11 +534,13 @@ def test_commit_inner_more_than_64_vectors_uses_one_chacha_pass(ctx, orc, N, R, 
     assert np.array_equal(got, ref)
 
 
-@pytest.mark.parametrize("N,R,row0,nrows", [(1, 1, 0, 5), (3, 2, 1, 21), (5, 130, 0, 70), (33, 64, 3, 130), (16400, 3, 2, 3)])
+@pytest.mark.parametrize("N,R,row0,nrows", [(1, 1, 0, 5), (3, 2, 1, 21), (5, 130, 0, 70), (33, 64, 3, 130), (16400, 3, 2, 3), (33, 5, 2, 450)])
 def test_commit_inner_generate_then_contract(ctx, orc, N, R, row0, nrows, monkeypatch):
     """The large-shape cold path (k_gen_planes: every warp regenerates A into int8 limb planes; k_umma_commit: tensor-core
     contraction with all witness vectors), forced on small shapes the oracle can check: ragged rows and columns (zero
-    padding of planes), R = 1 (N' = 16), several passes of 64 vectors, two K-segments."""
+    padding of planes), R = 1 (N' = 16), several passes of 64 vectors, two K-segments; 450 rows of N = 33 are four chunks, so
+    the two plane buffers are reused while the contraction of chunk k runs on its own stream beside the generation of
+    chunk k + 1 (LAB_GC_OVERLAP=0: one buffer, one stream -- same bits)."""
     monkeypatch.setenv("LAB_GEN_CONTRACT_MIN_POLYS", "1")
     monkeypatch.setenv("LAB_GC_CHUNK_MB", "1")          # 1 MB of limb planes per chunk: several row chunks, T streamed out per chunk
     c = lb.RuntimeConstants.new(N, R, allow_degenerate=True)
@@ -517,6 +549,8 @@ def test_commit_inner_generate_then_contract(ctx, orc, N, R, row0, nrows, monkey
     got = ctx.commit_inner(c, SEED32, S, row0=row0, nrows=nrows)
     ref = orc.commit_inner_rows(co, SEED32, S, row0, nrows, ntt=True, nthreads=8)
     assert np.array_equal(got, ref)
+    monkeypatch.setenv("LAB_GC_OVERLAP", "0")
+    assert np.array_equal(ctx.commit_inner(c, SEED32, S, row0=row0, nrows=nrows), ref)
     monkeypatch.setenv("LAB_GEN_CONTRACT_MIN_POLYS", "0")          # 0 = never: the warp-specialised K_A path
     assert np.array_equal(ctx.commit_inner(c, SEED32, S, row0=row0, nrows=nrows), ref)
 

@@ -328,10 +328,11 @@ def test_limb_split_contraction_identity():
     assert 32768 * 127 * 127 < OFF < (1 << 31) - 32768 * 127 * 127      # K-segment bound: accumulator + OFF stays a positive s32
 
 
-def test_trimmed_chacha20_equals_the_full_block_on_words_0_to_3(orc):
+def test_trimmed_chacha20_equals_the_full_block_on_word_3(orc):
     """lab_chacha.cuh restated in Python: the part of the first double round that does not see key word 7 (LabHoist) and the
-    last diagonal round cut after the second `a` update give exactly keystream words 0..3 of the full 20-round block
-    (oracle.chacha20_block, itself pinned by the RFC 7539 / rand_chacha vectors)."""
+    last double round cut down to the cone of x3 -- column 0 complete, column 1 up to c, column 2 up to d, column 3 up to a, then
+    the one diagonal quarter round (x3, x4, x9, x14) up to its second `a` update -- give exactly keystream word 3 of the full
+    20-round block (oracle.chacha20_block, itself pinned by the RFC 7539 / rand_chacha vectors)."""
     M = 0xFFFFFFFF
     rotl = lambda x, n: ((x << n) | (x >> (32 - n))) & M
 
@@ -343,6 +344,16 @@ def test_trimmed_chacha20_equals_the_full_block_on_words_0_to_3(orc):
     def qr_a_only(a, b, c, d):
         a = (a + b) & M; d = rotl(d ^ a, 16); c = (c + d) & M; b = rotl(b ^ c, 12)
         return (a + b) & M
+
+    def qr_c_only(a, b, c, d):
+        a = (a + b) & M; d = rotl(d ^ a, 16); c = (c + d) & M; b = rotl(b ^ c, 12)
+        a = (a + b) & M; d = rotl(d ^ a, 8)
+        return (c + d) & M
+
+    def qr_d_only(a, b, c, d):
+        a = (a + b) & M; d = rotl(d ^ a, 16); c = (c + d) & M; b = rotl(b ^ c, 12)
+        a = (a + b) & M
+        return rotl(d ^ a, 8)
     CC = (0x61707865, 0x3320646e, 0x79622d32, 0x6b206574)
     rng = np.random.default_rng(11)
     for _ in range(8):
@@ -368,14 +379,139 @@ def test_trimmed_chacha20_equals_the_full_block_on_words_0_to_3(orc):
             for _r in range(8):
                 for (i, j, k, l) in ((0, 4, 8, 12), (1, 5, 9, 13), (2, 6, 10, 14), (3, 7, 11, 15), (0, 5, 10, 15), (1, 6, 11, 12), (2, 7, 8, 13), (3, 4, 9, 14)):
                     x[i], x[j], x[k], x[l] = qr(x[i], x[j], x[k], x[l])
-            for (i, j, k, l) in ((0, 4, 8, 12), (1, 5, 9, 13), (2, 6, 10, 14), (3, 7, 11, 15)):
-                x[i], x[j], x[k], x[l] = qr(x[i], x[j], x[k], x[l])
-            w = [qr_a_only(x[0], x[5], x[10], x[15]), qr_a_only(x[1], x[6], x[11], x[12]), qr_a_only(x[2], x[7], x[8], x[13]), qr_a_only(x[3], x[4], x[9], x[14])]
-            w = [(w[i] + CC[i]) & M for i in range(4)]
+            x4 = qr(x[0], x[4], x[8], x[12])[1]
+            x9 = qr_c_only(x[1], x[5], x[9], x[13])
+            x14 = qr_d_only(x[2], x[6], x[10], x[14])
+            x3 = qr_a_only(x[3], x[7], x[11], x[15])
+            w3 = (qr_a_only(x3, x4, x9, x14) + CC[3]) & M
             full = orc.chacha20_block(key[:7] + [k7], 0, 0)
-            assert [int(v) for v in full[:4]] == w
-    # operation count the roofline uses: 20 rounds x 4 quarter rounds x 4 (xor + rotate) = 640; hoisted 28, dead tail 16
-    assert 640 - 28 - 16 == 596
+            assert int(full[3]) == w3
+
+
+def test_chacha20_operation_count_of_the_roofline():
+    """bench.py's ALU_OPS_PER_BLOCK: the xor / rotate operations of one ChaCha20 block that lie in the dependency cone of
+    keystream word 3 AND depend on key word 7 (everything else is hoisted, lab_chacha.cuh), counted by dead-code
+    elimination over the operation list of the plain 20-round block."""
+    ops, dep = [], {("in", i): i == 11 for i in range(16)}
+    cur = {i: ("in", i) for i in range(16)}
+
+    def new(kind, srcs):
+        n = ("t", len(ops))
+        ops.append((kind, n, srcs))
+        dep[n] = any(dep[v] for v in srcs)
+        return n
+
+    def qr(a, b, c, d):
+        for (x, y, z) in ((a, b, d), (c, d, b), (a, b, d), (c, d, b)):
+            cur[x] = new("add", [cur[x], cur[y]])
+            cur[z] = new("rot", [new("xor", [cur[z], cur[x]])])
+    for _ in range(10):
+        for q in ((0, 4, 8, 12), (1, 5, 9, 13), (2, 6, 10, 14), (3, 7, 11, 15), (0, 5, 10, 15), (1, 6, 11, 12), (2, 7, 8, 13), (3, 4, 9, 14)):
+            qr(*q)
+
+    def count(outs):
+        need, alu = {cur[o] for o in outs}, 0
+        for kind, n, srcs in reversed(ops):
+            if n in need:
+                need.update(srcs)
+                alu += dep[n] and kind != "add"
+        return alu
+    assert sum(k != "add" for k, _, _ in ops) == 640
+    assert count([0, 1, 2, 3]) == 596          # round 1 / early round 2: words 0..3
+    assert count([3]) == 576                   # now: word 3 decides the sample
+    import bench
+    assert bench.ALU_OPS_PER_BLOCK == 576
+
+
+def test_sample_from_the_top_keystream_word_alone():
+    """lab_sample_w3: rand 0.8.5 sample_single on the 128-bit draw v = w3:w2:w1:w0 for the range 0..Q accepts iff the low half
+    of v * Q is <= (Q << 115) - 1 and returns the high half.  With L = lo32(w3 * Q) < 0xFFF80000 - (Q - 1) that decision and the
+    value follow from w3 alone; the band above it must go to the generic path (which the device then takes from draw 0)."""
+    zone = (Q << 115) - 1
+    LIM = 0xFFF80000 - (Q - 1)
+    rng = np.random.default_rng(3)
+
+    def full(v):
+        p = v * Q
+        return (p & ((1 << 128) - 1)) <= zone, p >> 128
+    inv = pow(Q, -1, 1 << 32)
+    cases = [int(x) for x in rng.integers(0, 1 << 32, 2000, dtype=np.uint64)]
+    # words whose L sits just below / at / above the limit, at the rejection zone, and at the wrap
+    for L in (LIM - 1, LIM, LIM + 1, 0xFFF80000 - 1, 0xFFF80000, 0xFFFFFFFF, 0, 1, LIM - Q, 0xFFFFE001):
+        cases.append((L * inv) & 0xFFFFFFFF)
+    n_fast = n_band = 0
+    for w3 in cases:
+        L = (w3 * Q) & 0xFFFFFFFF
+        for rest in (0, (1 << 96) - 1, int(rng.integers(0, 1 << 62)) << 34, 1 << 95):
+            ok, val = full((w3 << 96) | rest)
+            if L < LIM:
+                n_fast += 1
+                assert ok and val == (w3 * Q) >> 32
+            else:
+                n_band += 1                     # undecided by w3 alone: both outcomes occur in the band
+    assert n_fast and n_band
+    # the band is exactly where some `rest` could reach the rejection zone or carry
+    w3 = (LIM * inv) & 0xFFFFFFFF
+    assert not full((w3 << 96) | ((1 << 96) - 1))[0] and full(w3 << 96)[0]
+    w3 = ((LIM - 1) * inv) & 0xFFFFFFFF
+    assert full((w3 << 96) | ((1 << 96) - 1))[0]
+
+
+def test_warp_transform_bounds_with_one_fold_per_product():
+    """lab_ntt32_fwd_warp (lab_ntt.cuh) restated lane by lane in numpy: one fold after the twiddle product, one after the
+    butterfly.  Checks the bounds the code relies on (32-bit sums, 16-bit halves of the shuffled word, positive upper-lane
+    differences, result < 2Q before the final conditional subtraction) at the largest inputs it accepts, and that the values are
+    those of the reference network (gen_ntt.tables: the slot order of the oracle)."""
+    sys.path.insert(0, os.path.join(PKG, "tools"))
+    import gen_ntt
+    fwd, _, slot = gen_ntt.tables()
+    lanes = np.arange(32)
+    fold = lambda x: x - (x >> 13) * Q
+
+    def run(re, im, track):
+        re, im = re.astype(np.uint64), im.astype(np.uint64)
+        for s in range(5):
+            ln = 16 >> s
+            upper = (lanes & ln) != 0
+            node = (1 << s) + (lanes >> (5 - s))
+            f = [fwd[int(n)] if u else (1, 0) for n, u in zip(node, upper)]
+            fr = np.array([v[0] for v in f], np.uint64); fi = np.array([v[1] for v in f], np.uint64)
+            nfi = Q - fi
+            off = np.where(upper, 4 * Q, 0).astype(np.uint64)
+            pr, pi = re * fr + im * nfi, re * fi + im * fr
+            track["prod"] = max(track.get("prod", 0), int(pr.max()), int(pi.max()))
+            pr, pi = fold(pr), fold(pi)
+            track["half"] = max(track.get("half", 0), int(pr.max()), int(pi.max()))
+            rr, ri = pr[lanes ^ ln], pi[lanes ^ ln]
+            sr = np.where(upper, rr + off - pr, rr + pr); si = np.where(upper, ri + off - pi, ri + pi)
+            assert (np.where(upper, rr + off, pr) >= np.where(upper, pr, 0)).all()
+            track["sum"] = max(track.get("sum", 0), int(sr.max()), int(si.max()))
+            re, im = fold(sr), fold(si)
+            track["out"] = max(track.get("out", 0), int(re.max()), int(im.max()))
+        return np.where(re >= Q, re - Q, re), np.where(im >= Q, im - Q, im)
+
+    def direct(coef):                          # slot j = f(zeta^e_j) over F_q[i], f_d + i f_{d+32} packed
+        out = []
+        for j in range(32):
+            z, acc, p = gen_ntt.cpow(gen_ntt.ZETA, slot[j]), (0, 0), (1, 0)
+            for d in range(32):
+                t = gen_ntt.cmul((int(coef[d]) % Q, int(coef[d + 32]) % Q), p)
+                acc = ((acc[0] + t[0]) % Q, (acc[1] + t[1]) % Q)
+                p = gen_ntt.cmul(p, z)
+            out.append(acc)
+        return np.array(out, np.uint64)
+    rng = np.random.default_rng(9)
+    track = {}
+    for coef in (rng.integers(0, Q, 64), np.full(64, Q - 1), np.full(64, 12286), rng.integers(0, 12287, 64), np.arange(64) * 191 % 12287):
+        re, im = run(coef[:32], coef[32:], track)
+        want = direct(coef)
+        assert np.array_equal(re, want[:, 0]) and np.array_equal(im, want[:, 1])
+    assert track["prod"] < 1 << 32 and track["half"] <= 4 * Q and track["half"] < 1 << 16 and track["sum"] < 1 << 26 and track["out"] < 2 * Q
+    # worst case by interval arithmetic: inputs <= 12286 at stage 0, <= Q + 16 afterwards, twiddle parts <= Q
+    for vin in (12286, Q + 16):
+        prod = vin * (Q - 1) + vin * Q
+        half = Q + (prod >> 13)
+        assert half <= 4 * Q and Q + ((half + 4 * Q) >> 13) <= Q + 16 and Q + ((2 * half) >> 13) <= Q + 16
 
 
 def test_pi_pack_roundtrip_on_host():
