@@ -686,7 +686,7 @@ static int d_commit_inner(lab_ctx *ctx, const LabSeed &seed, const uint32_t *Wha
     const size_t per_row = (size_t)32 * 2 * kpad;                  // bytes of limb planes per row of A
     auto gen_planes = [&](uint8_t *planes, uint64_t r0, uint64_t nr, uint32_t nt) -> int {
         if ((nr & 63) || (2 * N) % 128) CK(cudaMemsetAsync(planes, 0, (size_t)nt * 64 * per_row, ctx->stream));   // padding rows / K read as zero
-        LAUNCH(k_gen_planes<LAB_GP_MINB>, (unsigned)(ctx->sms * LAB_GP_MINB * 4), 32 * GP_WARPS,   /* 4 waves of CTAs even out the tail: +1.5 % */
+        LAUNCH(k_gen_planes<LAB_GP_MINB>, (unsigned)(ctx->sms * LAB_GP_MINB * 8), 32 * GP_WARPS,   /* 8 waves of CTAs even out the tail: +1.3 % over one wave */
                seed, (uint32_t)N, row0 + r0, nr, planes, nt, kpad);
         return LAB_OK;
     };

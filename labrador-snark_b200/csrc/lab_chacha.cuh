@@ -167,7 +167,8 @@ __device__ __forceinline__ void lab_hoist_update(const LabSeed &seed, uint64_t c
 }
 
 // keystream word 3 of block 0 (the top 32 bits of the 128-bit draw) for NB keys that share h and differ in key word 7
-template <int NB, uint32_t RM>
+// UNR: unroll factor of the loop over double rounds 2..9 (1, 2, 4 or 8)
+template <int NB, uint32_t RM, int UNR = 1>
 __device__ __forceinline__ void lab_chacha_w3(const LabSeed &s, const LabHoist &h, const uint32_t (&k7)[NB], uint32_t (&w3)[NB]) {
     uint32_t x[NB][16];
     const uint32_t one = s.one;
@@ -210,7 +211,7 @@ __device__ __forceinline__ void lab_chacha_w3(const LabSeed &s, const LabHoist &
         lab_qr<(RM >> 28) & 15u>(x[b][3], x[b][4], x[b][9], x[b][14], s);
     }
     // ---- double rounds 2..9 ----
-#pragma unroll 1
+#pragma unroll UNR
     for (int r = 0; r < 8; r++) lab_double_round<NB, RM>(x, s);
     // ---- double round 10, only the cone of x3: the diagonal quarter round (x3, x4, x9, x14) up to its second `a` update, and
     //      of the column round what that reads -- column 0 up to b (all of it), column 1 up to c, column 2 up to d, column 3 up to a.
@@ -293,7 +294,7 @@ __device__ __noinline__ uint32_t lab_crs_coeff_slow(const LabSeed &seed, uint64_
 // NB coefficients at counters (chi:clo) + off[b].  h is the caller's hoist cache (lab_hoist_invalidate once, then reuse
 // across calls: it is refreshed here when the high part of seed + counter changes).  A block whose offset carries out
 // of the low 32 bits of seed + clo, or whose first draw word 3 alone does not decide, is recomputed by the generic path.
-template <int NB, uint32_t RM>
+template <int NB, uint32_t RM, int UNR = 1>
 __device__ __forceinline__ void lab_crs_coeffs(const LabSeed &seed, LabHoist &h, uint64_t clo, uint64_t chi, const uint32_t (&off)[NB], uint32_t (&out)[NB]) {
     lab_hoist_update(seed, clo, chi, h);
     const uint32_t lo32 = (uint32_t)seed.limb[0] + (uint32_t)clo;
@@ -305,7 +306,7 @@ __device__ __forceinline__ void lab_crs_coeffs(const LabSeed &seed, LabHoist &h,
         slow[b] = t < off[b];
         k7[b] = lab_bswap32(t);
     }
-    lab_chacha_w3<NB, RM>(seed, h, k7, w3);
+    lab_chacha_w3<NB, RM, UNR>(seed, h, k7, w3);
 #pragma unroll
     for (int b = 0; b < NB; b++) {
         const bool ok = lab_sample_w3(w3[b], out[b]);

@@ -23,26 +23,35 @@ __device__ __forceinline__ void lab_hoist_load(const uint32_t *q, LabHoist &h) {
 
 // polynomial whose coefficient 0 sits at counter (chi:clo); all lanes of the warp call with the same arguments.
 // hoist_slot: 16 words of shared memory owned by this warp; tws: lab_warp_tw_to_smem table.  Returns the packed slots.
+// VAR bits 2-3: log2 of the unroll factor of the double-round loop; VAR bit 0: split shuffles in the transform; VAR bit 1: the caller walks consecutive polynomials (clo advances by 64) and has
+// called this function for the previous one, so the hoist slot can only have become stale if the low 32 bits of seed + counter
+// wrapped -- one 32-bit compare instead of the 64-bit tag comparison (`first` = first polynomial of a run: full check)
+template <int VAR = 0>
 __device__ __forceinline__ void lab_crs_poly_hat_warp(const LabSeed &seed, LabWarpGen &g, uint32_t *hoist_slot, const uint32_t (*tws)[32], uint64_t clo,
-                                                      uint64_t chi, int lane, uint32_t &re, uint32_t &im) {
-    const uint64_t s0 = seed.limb[0] + clo;
-    const uint64_t ntag = ((uint64_t)(s0 < clo) << 32) | (s0 >> 32);
-    if (ntag != g.tag_lo || chi != g.tag_hi) {                   // warp-uniform, once per 2^32 counters
-        LabHoist hh;
-        lab_hoist_compute(seed, clo, chi, hh);
-        __syncwarp();
-        if (lane == 0) lab_hoist_store(hoist_slot, hh);
-        __syncwarp();
-        g.tag_lo = ntag;
-        g.tag_hi = chi;
+                                                      uint64_t chi, int lane, uint32_t &re, uint32_t &im, bool first = true) {
+    uint32_t lo32;
+    if ((VAR & 2) && !first && (lo32 = (uint32_t)seed.limb[0] + (uint32_t)clo) >= 64u) {
+        // same 2^32 window as the previous polynomial: the slot is current
+    } else {
+        const uint64_t s0 = seed.limb[0] + clo;
+        const uint64_t ntag = ((uint64_t)(s0 < clo) << 32) | (s0 >> 32);
+        if (ntag != g.tag_lo || chi != g.tag_hi) {                   // warp-uniform, once per 2^32 counters
+            LabHoist hh;
+            lab_hoist_compute(seed, clo, chi, hh);
+            __syncwarp();
+            if (lane == 0) lab_hoist_store(hoist_slot, hh);
+            __syncwarp();
+            g.tag_lo = ntag;
+            g.tag_hi = chi;
+        }
+        lo32 = (uint32_t)s0;
     }
-    const uint32_t lo32 = (uint32_t)s0;
     const bool straddle = lo32 > 0xFFFFFFFFu - 63u;
     LabHoist h;
     lab_hoist_load(hoist_slot, h);
     const uint32_t k7[2] = {lab_bswap32(lo32 + (uint32_t)lane), lab_bswap32(lo32 + (uint32_t)lane + 32u)};
     uint32_t w3[2], c[2];
-    lab_chacha_w3<2, 0u>(seed, h, k7, w3);
+    lab_chacha_w3<2, 0u, 1 << ((VAR >> 2) & 3)>(seed, h, k7, w3);
     uint32_t slow = straddle ? 3u : 0u;
     slow |= lab_sample_w3(w3[0], c[0]) ? 0u : 1u;
     slow |= lab_sample_w3(w3[1], c[1]) ? 0u : 2u;
@@ -57,5 +66,45 @@ __device__ __forceinline__ void lab_crs_poly_hat_warp(const LabSeed &seed, LabWa
         }
     }
     re = c[0]; im = c[1];
-    lab_ntt32_fwd_warp_smem(re, im, tws, lane, seed.one);
+    lab_ntt32_fwd_warp_smem<(VAR & 1) != 0>(re, im, tws, lane, seed.one);
+}
+
+// The polynomials at counters (chi:clo) and (chi:clo) + 64 together: four interleaved ChaCha20 states per lane (the round
+// function alone runs 6 % faster with four independent blocks per thread than with two, profiles/kbench_r1_pipe_ceilings.jsonl)
+// and two interleaved transforms.  VAR as above.
+template <int VAR = 0>
+__device__ __forceinline__ void lab_crs_poly_hat_warp_x2(const LabSeed &seed, LabWarpGen &g, uint32_t *hoist_slot, const uint32_t (*tws)[32], uint64_t clo,
+                                                         uint64_t chi, int lane, uint32_t (&re)[2], uint32_t (&im)[2]) {
+    const uint64_t s0 = seed.limb[0] + clo;
+    const uint64_t ntag = ((uint64_t)(s0 < clo) << 32) | (s0 >> 32);
+    if (ntag != g.tag_lo || chi != g.tag_hi) {                   // warp-uniform, once per 2^32 counters
+        LabHoist hh;
+        lab_hoist_compute(seed, clo, chi, hh);
+        __syncwarp();
+        if (lane == 0) lab_hoist_store(hoist_slot, hh);
+        __syncwarp();
+        g.tag_lo = ntag;
+        g.tag_hi = chi;
+    }
+    const uint32_t lo32 = (uint32_t)s0;
+    const bool straddle = lo32 > 0xFFFFFFFFu - 127u;             // some of the 128 counters lie in the next 2^32 window: generic path
+    LabHoist h;
+    lab_hoist_load(hoist_slot, h);
+    uint32_t k7[4], w3[4], c[4];
+#pragma unroll
+    for (int b = 0; b < 4; b++) k7[b] = lab_bswap32(lo32 + (uint32_t)lane + 32u * b);
+    lab_chacha_w3<4, 0u, 1 << ((VAR >> 2) & 3)>(seed, h, k7, w3);
+    uint32_t slow = straddle ? 15u : 0u;
+#pragma unroll
+    for (int b = 0; b < 4; b++) slow |= lab_sample_w3(w3[b], c[b]) ? 0u : 1u << b;
+    if (slow) {
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+            if (slow >> b & 1u) {
+                const uint64_t l = clo + (uint64_t)lane + 32u * b;
+                c[b] = lab_crs_coeff_generic(seed, l, chi + (l < clo), 0u);
+            }
+    }
+    re[0] = c[0]; im[0] = c[1]; re[1] = c[2]; im[1] = c[3];
+    lab_ntt32_fwd_warp_smem_x2<(VAR & 1) != 0>(re, im, tws, lane, seed.one);
 }

@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(256) k_digit_norm_sq(const uint32_t *__restric
 // worth of pipe time -- it gains 3 % in k_crs_expand with two of the 32 rotations of a double round moved and loses
 // everywhere else, hence 0 for the kernels that also multiply.
 #ifndef LAB_RM_EXPAND
-#define LAB_RM_EXPAND 0x00010001u
+#define LAB_RM_EXPAND 0x00000000u
 #endif
 #ifndef LAB_RM_COMMIT
 #define LAB_RM_COMMIT 0x00000000u
@@ -441,6 +441,11 @@ __global__ void __launch_bounds__(256) k_digit_norm_sq(const uint32_t *__restric
 #define LAB_RM_MATVEC 0x00000000u
 #endif
 
+// LAB_KA_VAR (K_A producers and k_crs_expand): bit 0 = split shuffles in the transform, bits 2-3 = log2 of the unroll factor of the
+// double-round loop (see LAB_MV_VAR below and LAB_GP_VAR in lab_umma.cuh)
+#ifndef LAB_KA_VAR
+#define LAB_KA_VAR 0         /* measured (profiles/kbench_r2b_ka_variants.jsonl): 13 is 3 % slower in K_A (80-register producers) and no faster in k_crs_expand */
+#endif
 template <uint32_t RM>
 __global__ void __launch_bounds__(256) k_crs_expand(LabSeed seed, uint64_t start_lo, uint64_t start_hi, size_t n_coeffs, uint32_t *__restrict__ out) {
     size_t idx = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
@@ -452,20 +457,25 @@ __global__ void __launch_bounds__(256) k_crs_expand(LabSeed seed, uint64_t start
         uint64_t hi = start_hi + (lo < start_lo);
         const uint32_t off[2] = {0u, 1u};
         uint32_t c[2];
-        lab_crs_coeffs<2, RM>(seed, h, lo, hi, off, c);
+        lab_crs_coeffs<2, RM, 1 << ((LAB_KA_VAR >> 2) & 3)>(seed, h, lo, hi, off, c);
         if (idx + 1 < n_coeffs) *reinterpret_cast<uint2 *>(out + idx) = make_uint2(c[0], c[1]);
         else out[idx] = c[0];
     }
 }
 
 // one CRS polynomial per warp, in the transform domain: lane j produces coefficients j and j+32
+// LAB_MV_VAR (K_MV and the hat generator of the proof graphs): bit 0 = split shuffles in the transform, bits 2-3 = log2 of the
+// unroll factor of the double-round loop
+#ifndef LAB_MV_VAR
+#define LAB_MV_VAR 13        /* measured on cfg 5 (1024 default statements): 0 -> 2984, 1 -> 3005, 5 -> 3043, 13 -> 3122 proofs/s */
+#endif
 template <uint32_t RM>
 __device__ __forceinline__ void crs_poly_hat(const LabSeed &seed, LabHoist &h, uint64_t lo, uint64_t hi, const LabWarpTw &tw, int lane, uint32_t &re, uint32_t &im) {
     const uint32_t off[2] = {(uint32_t)lane, (uint32_t)lane + 32u};
     uint32_t c[2];
-    lab_crs_coeffs<2, RM>(seed, h, lo, hi, off, c);
+    lab_crs_coeffs<2, RM, 1 << ((LAB_MV_VAR >> 2) & 3)>(seed, h, lo, hi, off, c);
     re = c[0]; im = c[1];
-    lab_ntt32_fwd_warp(re, im, tw, lane, seed.one);
+    lab_ntt32_fwd_warp<(LAB_MV_VAR & 1) != 0>(re, im, tw, lane, seed.one);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -596,7 +606,7 @@ __global__ void __launch_bounds__(ka_threads(PP), 1) k_commit_inner(LabSeed seed
                 uint32_t k7[NB], w3[NB];
 #pragma unroll
                 for (int b = 0; b < NB; b++) k7[b] = lab_bswap32(lo32 + (uint32_t)lane + 32u * (b & 1) + PSTEP * (b >> 1));
-                lab_chacha_w3<NB, RM>(seed, h, k7, w3);
+                lab_chacha_w3<NB, RM, 1 << ((LAB_KA_VAR >> 2) & 3)>(seed, h, k7, w3);
                 uint32_t slow = straddle ? (1u << NB) - 1u : 0u;
 #pragma unroll
                 for (int b = 0; b < NB; b++) slow |= lab_sample_w3(w3[b], c[b]) ? 0u : 1u << b;
@@ -609,7 +619,7 @@ __global__ void __launch_bounds__(ka_threads(PP), 1) k_commit_inner(LabSeed seed
                 for (int p = 0; p < PP; p++) {
                     if (PP > 1 && !(COLS * t + gcol + p * (PROD / 4) < N)) { c[2 * p] = 0; c[2 * p + 1] = 0; }   // column past N: zero polynomial
                     else {
-                        lab_ntt32_fwd_warp_smem(c[2 * p], c[2 * p + 1], tws, lane, seed.one);
+                        lab_ntt32_fwd_warp_smem<(LAB_KA_VAR & 1) != 0>(c[2 * p], c[2 * p + 1], tws, lane, seed.one);
                     }
                 }
             }

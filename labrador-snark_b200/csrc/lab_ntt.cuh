@@ -53,6 +53,7 @@ __device__ __forceinline__ LabWarpTw lab_warp_tw(int lane) {
 
 // lane j holds g_j = f_j + i f_{j+32} (residues < 2Q); returns slot j = f(zeta^{e_j}), canonical.
 // `one` == 1 at run time (LabSeed::one): additions written as x * one + y issue on the FMA pipe.
+template <bool SPLIT = false>
 __device__ __forceinline__ void lab_ntt32_fwd_warp(uint32_t &re, uint32_t &im, const LabWarpTw &tw, int lane, uint32_t one = 1u) {
     (void)lane;
 #pragma unroll
@@ -62,10 +63,16 @@ __device__ __forceinline__ void lab_ntt32_fwd_warp(uint32_t &re, uint32_t &im, c
         uint32_t pi = re * tw.fi[s] + im * tw.fr[s];
         pr = lab_fold(pr);                                                   // <= 24595 < 4Q
         pi = lab_fold(pi);
-        const uint32_t recv = __shfl_xor_sync(0xffffffffu, pi * 65536u + pr, len);
         // lower: lo + t ; upper: lo - t + 4Q  (t is the upper lane's product, lo the lower lane's value)
-        re = lab_fold(pr * tw.sgn[s] + (lab_re(recv) * one + tw.off[s]));    // < Q + 16
-        im = lab_fold(pi * tw.sgn[s] + (lab_im(recv) * one + tw.off[s]));
+        if (SPLIT) {                                                         // two shuffles, no pack / unpack (see lab_ntt32_fwd_warp_smem)
+            const uint32_t rr = __shfl_xor_sync(0xffffffffu, pr, len), ri = __shfl_xor_sync(0xffffffffu, pi, len);
+            re = lab_fold(pr * tw.sgn[s] + (rr * one + tw.off[s]));          // < Q + 16
+            im = lab_fold(pi * tw.sgn[s] + (ri * one + tw.off[s]));
+        } else {
+            const uint32_t recv = __shfl_xor_sync(0xffffffffu, pi * 65536u + pr, len);
+            re = lab_fold(pr * tw.sgn[s] + (lab_re(recv) * one + tw.off[s]));
+            im = lab_fold(pi * tw.sgn[s] + (lab_im(recv) * one + tw.off[s]));
+        }
     }
     re = lab_csub(re);
     im = lab_csub(im);
@@ -85,6 +92,9 @@ __device__ __forceinline__ void lab_warp_tw_to_smem(uint32_t (*tws)[32], int lan
         tws[20 + s][lane] = t.off[s];
     }
 }
+// SPLIT: re and im travel in two shuffles instead of one packed word: two unpack operations less on the ALU pipe and one
+// pack multiply less on the FMA pipe per stage, for one more SHFL
+template <bool SPLIT = false>
 __device__ __forceinline__ void lab_ntt32_fwd_warp_smem(uint32_t &re, uint32_t &im, const uint32_t (*tws)[32], int lane, uint32_t one) {
 #pragma unroll
     for (int s = 0; s < 5; s++) {
@@ -94,12 +104,55 @@ __device__ __forceinline__ void lab_ntt32_fwd_warp_smem(uint32_t &re, uint32_t &
         uint32_t pi = re * fi + im * fr;
         pr = lab_fold(pr);
         pi = lab_fold(pi);
-        const uint32_t recv = __shfl_xor_sync(0xffffffffu, pi * 65536u + pr, len);
-        re = lab_fold(pr * sgn + (lab_re(recv) * one + off));
-        im = lab_fold(pi * sgn + (lab_im(recv) * one + off));
+        if (SPLIT) {
+            const uint32_t rr = __shfl_xor_sync(0xffffffffu, pr, len), ri = __shfl_xor_sync(0xffffffffu, pi, len);
+            re = lab_fold(pr * sgn + (rr * one + off));
+            im = lab_fold(pi * sgn + (ri * one + off));
+        } else {
+            const uint32_t recv = __shfl_xor_sync(0xffffffffu, pi * 65536u + pr, len);
+            re = lab_fold(pr * sgn + (lab_re(recv) * one + off));
+            im = lab_fold(pi * sgn + (lab_im(recv) * one + off));
+        }
     }
     re = lab_csub(re);
     im = lab_csub(im);
+}
+
+// two polynomials at once (independent butterflies interleaved: twice the instruction-level parallelism around each shuffle)
+template <bool SPLIT = true>
+__device__ __forceinline__ void lab_ntt32_fwd_warp_smem_x2(uint32_t (&re)[2], uint32_t (&im)[2], const uint32_t (*tws)[32], int lane, uint32_t one) {
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        const int len = 16 >> s;
+        const uint32_t fr = tws[s][lane], fi = tws[5 + s][lane], nfi = tws[10 + s][lane], sgn = tws[15 + s][lane], off = tws[20 + s][lane];
+        uint32_t pr[2], pi[2];
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+            pr[p] = lab_fold(re[p] * fr + im[p] * nfi);
+            pi[p] = lab_fold(re[p] * fi + im[p] * fr);
+        }
+        if (SPLIT) {
+            uint32_t rr[2], ri[2];
+#pragma unroll
+            for (int p = 0; p < 2; p++) { rr[p] = __shfl_xor_sync(0xffffffffu, pr[p], len); ri[p] = __shfl_xor_sync(0xffffffffu, pi[p], len); }
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                re[p] = lab_fold(pr[p] * sgn + (rr[p] * one + off));
+                im[p] = lab_fold(pi[p] * sgn + (ri[p] * one + off));
+            }
+        } else {
+            uint32_t recv[2];
+#pragma unroll
+            for (int p = 0; p < 2; p++) recv[p] = __shfl_xor_sync(0xffffffffu, pi[p] * 65536u + pr[p], len);
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                re[p] = lab_fold(pr[p] * sgn + (lab_re(recv[p]) * one + off));
+                im[p] = lab_fold(pi[p] * sgn + (lab_im(recv[p]) * one + off));
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 2; p++) { re[p] = lab_csub(re[p]); im[p] = lab_csub(im[p]); }
 }
 
 // lane j holds slot j (residues < 2Q); returns g_j = f_j + i f_{j+32}, canonical, scaled by 1/32.

@@ -54,9 +54,14 @@ __device__ __forceinline__ uint64_t um_desc(uint32_t saddr) {
 // sectors in L2 before they reach HBM.
 constexpr int GP_WARPS = 8;
 #ifndef LAB_GP_MINB
-#define LAB_GP_MINB 3
+#define LAB_GP_MINB 2
 #endif
-template <int MINB>
+#ifndef LAB_GP_VAR
+#define LAB_GP_VAR 21         /* measured, profiles/kbench_r2b_gen_variants.jsonl: split shuffles (+0.6 %), two polynomials = four ChaCha20 states per lane and
+                                 iteration with the middle double rounds unrolled x2 (+2.9 % together; x8 of the one-polynomial form +2.3 %, x8 of this form
+                                 overflows the instruction cache: -25 %); bit 1 (32-bit window check) measured equal */
+#endif
+template <int MINB, int VAR = LAB_GP_VAR>
 __global__ void __launch_bounds__(32 * GP_WARPS, MINB) k_gen_planes(LabSeed seed, uint32_t N, uint64_t row0, uint64_t nrows, uint8_t *__restrict__ planes,
                                                                  uint32_t ntiles, uint32_t kpad) {
     __shared__ uint32_t tws[LAB_TWS_ROWS][32];
@@ -71,10 +76,23 @@ __global__ void __launch_bounds__(32 * GP_WARPS, MINB) k_gen_planes(LabSeed seed
         const uint64_t row = run / runs_per_row;
         const uint32_t n0 = (uint32_t)(run % runs_per_row) * 16, n1 = min(n0 + 16u, N);
         uint8_t *q8 = planes + (((uint64_t)lane * ntiles + (row >> 6)) * 128 + (row & 63)) * kpad;
-        for (uint32_t n = n0; n < n1; n++) {
+        uint32_t n = n0;
+        if (VAR & 16) {                                                              // two polynomials per iteration
+            for (; n + 1 < n1; n += 2) {
+                const uint64_t ctr = ((row0 + row) * (uint64_t)N + n) * 64ull;          // structs.rs:55-72
+                uint32_t re[2], im[2];
+                lab_crs_poly_hat_warp_x2<VAR>(seed, g, hoist[w], tws, ctr, 0ull, lane, re, im);
+#pragma unroll
+                for (int p = 0; p < 2; p++) {
+                    *reinterpret_cast<uint16_t *>(q8 + 2 * (n + p)) = (uint16_t)((re[p] & 127u) | ((im[p] & 127u) << 8));
+                    *reinterpret_cast<uint16_t *>(q8 + 64 * (uint64_t)kpad + 2 * (n + p)) = (uint16_t)((re[p] >> 7) | ((im[p] >> 7) << 8));
+                }
+            }
+        }
+        for (; n < n1; n++) {
             const uint64_t ctr = ((row0 + row) * (uint64_t)N + n) * 64ull;          // structs.rs:55-72
             uint32_t re, im;
-            lab_crs_poly_hat_warp(seed, g, hoist[w], tws, ctr, 0ull, lane, re, im);
+            lab_crs_poly_hat_warp<VAR>(seed, g, hoist[w], tws, ctr, 0ull, lane, re, im, n == n0);
             *reinterpret_cast<uint16_t *>(q8 + 2 * n) = (uint16_t)((re & 127u) | ((im & 127u) << 8));
             *reinterpret_cast<uint16_t *>(q8 + 64 * (uint64_t)kpad + 2 * n) = (uint16_t)((re >> 7) | ((im >> 7) << 8));
         }

@@ -4,6 +4,7 @@
 // the untrimmed generic ChaCha20 path (bit-exact) and prints one JSON line per measurement.
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 #include "lab_kernels.cuh"
 #include "lab_umma.cuh"
@@ -162,7 +163,8 @@ static void bench_commit(Timer &tm, const LabSeed &seed, const uint32_t *What, u
 int main(int argc, char **argv) {
     const LabSeed seed = mk_seed();
     Timer tm;
-    {   // pipe rates
+    const bool only_gen = argc > 1 && std::string(argv[1]) == "gen";      // `kbench gen`: only the limb-plane generator variants
+    if (!only_gen) {   // pipe rates
         uint32_t *o;
         CK(cudaMalloc(&o, 148 * 16 * 256 * 4));
         const int iters = 4096;
@@ -193,7 +195,7 @@ int main(int argc, char **argv) {
         }
         cudaFree(o);
     }
-    {   // expansion
+    if (!only_gen) {   // expansion
         const size_t n = (size_t)1 << 26, n_small = (size_t)1 << 20;
         // start chosen so that low32(seed + counter) crosses a 2^32 boundary inside the small range
         const uint64_t low = (uint32_t)seed.limb[0];
@@ -233,16 +235,43 @@ int main(int argc, char **argv) {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb4, k_gen_planes<4>, 32 * GP_WARPS, 0);
             printf("{\"kernel\": \"k_gen_planes\", \"resident_ctas_per_sm\": {\"minblocks2\": %d, \"minblocks3\": %d, \"minblocks4\": %d}}\n", nb2, nb3, nb4);
         }
-        report("minblocks 3, grid 148 x 6", tm.run([&] { k_gen_planes<3><<<148 * 6, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); }, 2));
-        report("minblocks 3, grid 148 x 12", tm.run([&] { k_gen_planes<3><<<148 * 12, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); }, 2));
-        report("minblocks 2 (16 warps/SM)", tm.run([&] { k_gen_planes<2><<<148 * 2, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); }, 2));
-        report("minblocks 3 (24 warps/SM)", tm.run([&] { k_gen_planes<3><<<148 * 3, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); }, 2));
-        report("minblocks 4 (32 warps/SM)", tm.run([&] { k_gen_planes<4><<<148 * 4, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); }, 2));
-        report("minblocks 5 (40 warps/SM)", tm.run([&] { k_gen_planes<5><<<148 * 5, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); }, 2));
+        const size_t plane_words = (size_t)nt * 64 * 32 * 2 * kpad / 4;
+        auto sum = [&]() { return checksum((const uint32_t *)planes, plane_words); };
+        report("reference for the checksums: var 0, minblocks 3, grid 148 x 12", tm.run([&] { k_gen_planes<3, 0><<<148 * 12, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); }, 2));
+        const unsigned long long ref = sum();
+        auto variant = [&](const char *name, auto launch) {
+            CK(cudaMemset(planes, 0, plane_words * 4));
+            const float ms = tm.run(launch, 2);
+            const bool same = sum() == ref;
+            printf("{\"kernel\": \"k_gen_planes\", \"variant\": \"%s\", \"ms\": %.4f, \"blocks_per_s\": %.4e, \"same_planes\": %s}\n", name, ms,
+                   (double)rows * N * 64 / (ms * 1e-3), same ? "true" : "false");
+            fflush(stdout);
+        };
+        variant("library launch (LAB_GP_VAR, LAB_GP_MINB, 8 waves)", [&] { k_gen_planes<LAB_GP_MINB><<<148 * LAB_GP_MINB * 8, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); });
+        variant("var 0 (packed shuffle, 64-bit tag check per polynomial)", [&] { k_gen_planes<3, 0><<<148 * 12, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); });
+        variant("var 1 (split shuffles)", [&] { k_gen_planes<3, 1><<<148 * 12, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); });
+        variant("var 2 (32-bit window check inside a run)", [&] { k_gen_planes<3, 2><<<148 * 12, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); });
+        variant("var 3 (both)", [&] { k_gen_planes<3, 3><<<148 * 12, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); });
+        variant("var 5 (split shuffles, double rounds unrolled x2)", [&] { k_gen_planes<3, 5><<<148 * 12, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); });
+        variant("var 9 (split shuffles, double rounds unrolled x4)", [&] { k_gen_planes<3, 9><<<148 * 12, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); });
+        variant("var 13 (split shuffles, double rounds unrolled x8)", [&] { k_gen_planes<3, 13><<<148 * 12, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); });
+        variant("var 29 (two polynomials per warp iteration: 4 ChaCha20 states per lane), minblocks 2", [&] { k_gen_planes<2, 29><<<148 * 8, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); });
+        variant("var 29, minblocks 3", [&] { k_gen_planes<3, 29><<<148 * 12, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); });
+        variant("var 21 (x2, unroll x2), minblocks 2", [&] { k_gen_planes<2, 21><<<148 * 8, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); });
+        variant("var 25 (x2, unroll x4), minblocks 2", [&] { k_gen_planes<2, 25><<<148 * 8, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); });
+        variant("var 21 (x2, unroll x2), minblocks 3", [&] { k_gen_planes<3, 21><<<148 * 12, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); });
+        variant("var 25 (x2, unroll x4), minblocks 3", [&] { k_gen_planes<3, 25><<<148 * 12, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); });
+        variant("var 21 (x2, unroll x2), minblocks 2, grid 148 x 2", [&] { k_gen_planes<2, 21><<<148 * 2, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); });
+        variant("var 21 (x2, unroll x2), minblocks 2, grid 148 x 16", [&] { k_gen_planes<2, 21><<<148 * 16, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); });
+        variant("var 17 (x2, rolled), minblocks 2", [&] { k_gen_planes<2, 17><<<148 * 8, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); });
+        variant("var 0, minblocks 4 (32 warps/SM)", [&] { k_gen_planes<4, 0><<<148 * 16, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); });
+        variant("var 3, minblocks 4 (32 warps/SM)", [&] { k_gen_planes<4, 3><<<148 * 16, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); });
+        variant("var 0, minblocks 2 (16 warps/SM)", [&] { k_gen_planes<2, 0><<<148 * 8, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); });
+        variant("var 3, minblocks 2 (16 warps/SM)", [&] { k_gen_planes<2, 3><<<148 * 8, 32 * GP_WARPS>>>(seed, N, 0ull, rows, planes, nt, kpad); });
         CK(cudaGetLastError());
         cudaFree(planes);
     }
-    {   // inner commitment
+    if (!only_gen) {   // inner commitment
         const uint32_t N = argc > 1 ? atoi(argv[1]) : 1024, R = 64;
         const uint64_t rows = 148 * 4 * 4;
         const size_t hats = (size_t)(N + KA_PAD_COLS) * R + KA_PAD_VECS;
