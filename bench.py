@@ -664,7 +664,7 @@ def main():
     ntt_res = roof_ntt = None
     if rank == 0 and os.environ.get("LAB_BENCH_LIGHT") != "1":
         try:
-            tdb = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
+            tdb = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r2b.json")))
         except Exception:
             tdb = {}
         ntt_res, roof_ntt = measure_ntt(ctx, torch, dev, lambda k, ok: (lambda d: d["dram_bytes_read_per_launch"] + d["dram_bytes_write_per_launch"] if d and ok else None)(tdb.get(k)))
@@ -773,10 +773,10 @@ def main():
 
     # ---- per-kernel numbers for the roofline (rank 0, kernel timed alone, same shard) ----
     roof = extra = None
-    # DRAM bytes per launch from the committed ncu capture of this very command (profiles/ncu_traffic_r1.json);
+    # DRAM bytes per launch from the committed ncu capture of this very command (profiles/ncu_traffic_r2b.json);
     # only quoted when the launch shape is the captured one
     try:
-        traffic_db = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
+        traffic_db = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r2b.json")))
     except Exception:
         traffic_db = {}
 
@@ -824,13 +824,15 @@ def main():
         roof = {"kernel": "inner commitment: k_gen_planes (ChaCha20 + transform -> int8 limb planes, 99 % of it) + k_umma_commit (tcgen05 contraction)", "bound": "int32_alu", "achieved": achieved / 1e9, "peak": alu_peak / 1e9, "unit": "Gop/s",
                 "frac": achieved / alu_peak,
                 "frac_survey_8d": blocks * 964 / (k_ms * 1e-3) / 3.7e13,
+                "frac_at_596_ops": blocks * 596 / (k_ms * 1e-3) / alu_peak,
                 "frac_note": "frac = 576 ALU-pipe lane-ops per coefficient against the MEASURED LOP3+SHF ceiling; frac_survey_8d = SURVEY 8(d)'s own "
-                             "definition, 964 u32 ops per ChaCha20 block against the nominal 148 SM x 128 lanes x 1.965 GHz = 3.7e13 op/s",
+                             "definition, 964 u32 ops per ChaCha20 block against the nominal 148 SM x 128 lanes x 1.965 GHz = 3.7e13 op/s; "
+                             "frac_at_596_ops = the same speed in the op count of round 1 (words 0..3 of the block), only for comparing rounds",
                 "traffic": (lambda d: d and (d["dram_bytes_read_per_call"] + d["dram_bytes_write_per_call"]))(traffic_db.get("inner_commitment_cfg3"))
                 if (args.workload == "cfg3" and world == 1) else None,
                 "traffic_unit": "DRAM bytes per commitment (ncu dram__bytes_read.sum + dram__bytes_write.sum over its k_gen_planes + k_umma_commit launches); "
                                 f"algorithmic bytes = {R * N * 128 + R * nrows * 256} (transformed witness once + T once) -- the excess is A, spilled on purpose "
-                                "through HBM as int8 limb planes between the ChaCha20 kernel and the tensor-core contraction (1.6 % of the HBM bandwidth)",
+                                "through HBM as int8 limb planes between the ChaCha20 kernel and the tensor-core contraction (2 % of the HBM bandwidth)",
                 "share_of_step": k_ms / ms_step,
                 "chacha_blocks_per_s": blocks / (k_ms * 1e-3), "kernel_ms": k_ms,
                 "note": "algorithmic ops = 576 ALU-pipe lane-ops (xor + rotate) per CRS coefficient = one ChaCha20 block minus the hoisted part "
