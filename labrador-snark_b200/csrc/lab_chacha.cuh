@@ -4,7 +4,8 @@
 // sample = rand 0.8.5 UniformInt<i128>::sample_single for the range 0..Q: v = 128 keystream bits
 // (4 little-endian u32 words, low first), (hi, lo) = v * Q as 256 bits, accept iff lo <= (Q << 115) - 1,
 // i.e. iff the top 13 bits of lo are not all ones; return hi.  Rejected draws (probability 2^-13)
-// continue with the next 128 keystream bits.
+// continue with the next 128 keystream bits.  (lab_sample_u128 is this rule word for word; lab_sample_w3 is the
+// shortcut through the top word that the fast paths use, falling back to the former when word 3 does not decide.)
 //
 // One ChaCha20 block per 13-bit coefficient makes every CRS-regenerating kernel INT32-bound, so the block function is
 // trimmed to what the result depends on:

@@ -1,9 +1,10 @@
 // One CRS polynomial per warp, straight into the transform domain -- the producer step shared by the CRS-regenerating
 // kernels (k_gen_planes, k_crs_matvec): trimmed ChaCha20 for coefficients lane and lane + 32 (lab_chacha.cuh), rand-0.8.5
-// sampling from keystream word 3 (lab_sample_w3), generic path for draws it does not decide and for polynomials that straddle a 2^32 boundary of seed + counter, warp
-// transform with the constants in shared memory.  The hoisted part of the first double round lives in a per-warp shared-
-// memory slot (15 words) and is recomputed when the high part of seed + counter changes, so a producer thread carries
-// two ChaCha20 states and little else (72 registers, three CTAs of 256 threads per SM).
+// sampling from keystream word 3 (lab_sample_w3), generic path for draws it does not decide and for polynomials that
+// straddle a 2^32 boundary of seed + counter, warp transform with the constants in shared memory.  The hoisted part of the
+// first double round lives in a per-warp shared-memory slot (15 words) and is recomputed when the high part of seed + counter
+// changes, so a producer thread carries its ChaCha20 states and little else: two states in 72 registers (one polynomial per
+// call), four in 128 (lab_crs_poly_hat_warp_x2, what k_gen_planes runs: two CTAs of 256 threads per SM).
 #pragma once
 #include "lab_chacha.cuh"
 #include "lab_ntt.cuh"

@@ -48,10 +48,10 @@ __device__ __forceinline__ uint64_t um_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
-// CRS side, cold: rows [row0, row0 + nrows) of A regenerated from the seed (ChaCha20 + warp transform, exactly K_A's
-// producer) straight into int8 limb planes -- no multiply-accumulate in this kernel, every warp generates.  A warp takes
-// runs of 16 consecutive columns of one row, so that the two 16-bit stores per lane and polynomial fill whole 32-byte
-// sectors in L2 before they reach HBM.
+// CRS side, cold: rows [row0, row0 + nrows) of A regenerated from the seed (ChaCha20 + warp transform) straight into int8
+// limb planes -- no multiply-accumulate in this kernel, every warp generates, two polynomials (four ChaCha20 states per lane)
+// per iteration.  A warp takes runs of 16 consecutive columns of one row, so that the two 16-bit stores per lane and polynomial
+// fill whole 32-byte sectors in L2 before they reach HBM.
 constexpr int GP_WARPS = 8;
 #ifndef LAB_GP_MINB
 #define LAB_GP_MINB 2
