@@ -514,6 +514,23 @@ def test_warp_transform_bounds_with_one_fold_per_product():
         assert half <= 4 * Q and Q + ((half + 4 * Q) >> 13) <= Q + 16 and Q + ((2 * half) >> 13) <= Q + 16
 
 
+def test_traffic_record_matches_the_committed_launch_list(tmp_path):
+    """profiles/ncu_traffic_r2b.json (what bench.py quotes as roofline.traffic) is tools/ncu_traffic.py applied to the committed
+    ncu launch list of the bench command: regenerate it and compare the inner-commitment totals."""
+    out = tmp_path / "t.json"
+    subprocess.check_call([sys.executable, os.path.join(PKG, "tools", "ncu_traffic.py"), os.path.join(ROOT, "profiles", "ncu_launches_bench_r2b.csv"), "4", str(out)],
+                          stdout=subprocess.DEVNULL)
+    import json
+    new, old = json.load(open(out)), json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r2b.json")))
+    a, b = new["inner_commitment_cfg3"], old["inner_commitment_cfg3"]
+    for k in ("dram_bytes_read_per_call", "dram_bytes_write_per_call", "gpu_time_ms_per_call_under_ncu", "gen_time_share", "algorithmic_bytes"):
+        assert abs(a[k] - b[k]) <= 1e-9 * abs(b[k]), k
+    assert a["launches_per_call"] == b["launches_per_call"]
+    traffic = b["dram_bytes_read_per_call"] + b["dram_bytes_write_per_call"]
+    assert 2 * 137438953472 < traffic < 3 * 137438953472          # A written once and read once as limb planes, plus the 16-bit store overhead
+    assert b["gen_time_share"] > 0.98
+
+
 def test_pi_pack_roundtrip_on_host():
     """lab_pi_pack / lab_pi_unpack are host-side marshalling (no ctx): bit k = +1, bit 16 + k = -1 of the word of 16 entries."""
     pi = synth.sample_pi(2, 3, seed=4)
