@@ -347,6 +347,7 @@ def run_cfg1(args, rank, world, local_rank):
     ctx = lb.Context(local_rank)
     # benches/labrador_perf.rs:19-28: n and r double alternately from (1, 2); size_pow 2 .. 10 are the shapes whose constants are sane
     sizes = [(2, 2), (2, 4), (4, 4), (4, 8), (8, 8), (8, 16), (16, 16), (16, 32), (32, 32)]
+    sizes = [s_ for s_ in sizes if s_[0] <= int(os.environ.get("LAB_BENCH_CFG1_MAX_N", "32"))]      # quick runs: only the small shapes
     cpu_sizes = {(2, 2), (2, 4), (4, 4)}
     oracle = None
     if rank == 0 and not args.no_cpu:
