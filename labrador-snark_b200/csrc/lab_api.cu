@@ -108,6 +108,10 @@ struct lab_ctx {
     // generation of chunk k + 1, which needs neither the tensor pipe nor HBM; two chunk buffers, one event pair each
     cudaStream_t gc_stream = nullptr;
     cudaEvent_t gc_gen[2] = {nullptr, nullptr}, gc_con[2] = {nullptr, nullptr}, gc_join = nullptr;
+    // pinned staging block of lab_verify for small proofs: the transcript, statement and challenges travel in ONE copy instead
+    // of a dozen pageable ones (every call ends with a synchronisation, so the block is free again when the next call fills it)
+    char *vstage = nullptr;
+    size_t vstage_bytes = 0;
     // worker contexts (own stream + arena each) for lab_prove_batch: independent statements overlap host-side
     // enqueueing of one proof with the GPU work of the others
     std::vector<lab_ctx *> workers;
@@ -241,7 +245,14 @@ extern "C" int lab_ctx_create(int device, lab_ctx **out) {
     ctx->device = device;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sms = prop.multiProcessorCount;
-    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    // The main stream gets the greatest priority, the second stream (ensure_stream2) keeps the default = least one: when a proof or a
+    // verification forks its ChaCha20-heavy strand (u_1) to the second stream, the short dependent kernels of the main chain take
+    // the SM slots that strand's CTAs free up instead of queueing behind its remaining waves (LAB_STREAM_PRIO=0: both default)
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    const char *sp = std::getenv("LAB_STREAM_PRIO");
+    if (sp && sp[0] == '0') prio_hi = prio_lo;
+    if ((e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) {
         g_create_err = cudaGetErrorString(e);
         delete ctx;
         return LAB_ERR_CUDA;
@@ -261,6 +272,7 @@ extern "C" void lab_ctx_destroy(lab_ctx *ctx) {
     if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->ev_tg); }
     for (auto &p : ctx->mv_plans) cudaFree(p.dev);
     for (auto &e : ctx->crs_cache) cudaFree(e.dev);
+    if (ctx->vstage) cudaFreeHost(ctx->vstage);
     if (ctx->gc_stream) {
         cudaStreamSynchronize(ctx->gc_stream);
         cudaStreamDestroy(ctx->gc_stream);
@@ -1948,33 +1960,91 @@ static int verify_core(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_
         for (uint64_t j = 0; j < R; j++)
             if (std::memcmp(tr->h + (i * R + j) * 64, tr->h + (j * R + i) * 64, 256)) { fc = 9; break; }
     // uploads
-    uint32_t *dz, *dT, *dG, *dH, *du1, *du2, *dphi, *dom, *da, *dsmall, *dc, *dPi2;
+    uint32_t *dz, *dT, *dG, *dH, *du1, *du2, *dphi, *dom, *da, *dsmall, *dc, *dPi2, *dpsi = nullptr;
     int8_t *dPi8 = nullptr;
-    TRY(upload(ctx, tr->z, N * 64, &dz));
-    TRY(upload(ctx, tr->t, R * K * 64, &dT));
-    TRY(upload(ctx, tr->g, R * R * 64, &dG));
-    TRY(upload(ctx, tr->h, R * R * 64, &dH));
-    TRY(upload(ctx, tr->u_1, K1 * 64, &du1));
-    TRY(upload(ctx, tr->u_2, K2 * 64, &du2));
-    TRY(upload(ctx, st->phi, R * ND, &dphi));
-    TRY(upload(ctx, ch->omega, (size_t)LAB_JL_ROWS, &dom));
-    TRY(upload(ctx, st->a, R * R * 64, &da));
-    TRY(upload(ctx, ch->c, R * 64, &dc));
-    if (dPi2_ready) dPi2 = const_cast<uint32_t *>(dPi2_ready);
-    else {
-        if (!ch->pi && !ch->pi2) FAIL(LAB_ERR_PARAMS, "no JL matrix given (pi or pi2)");
-        TRY(arena_alloc(ctx, R * LAB_JL_ROWS * ND / 16, &dPi2));
-        if (!ch->pi2) TRY(arena_alloc(ctx, R * LAB_JL_ROWS * ND, &dPi8));
-        const size_t first = (size_t)tr->jl_attempt * R * LAB_JL_ROWS * ND;
-        TRY(upload_pi2(ctx, ch->pi2 ? nullptr : ch->pi + first, ch->pi2 ? ch->pi2 + first / 16 : nullptr, R, ND, dPi2, dPi8));
-    }
+    const bool lazy = R * K * 256 <= ((uint64_t)4 << 20);       // small proofs: one synchronisation for all equality checks
     uint32_t small[4 * 64];                                     // alpha, beta, b, b''
     std::memcpy(small, ch->alpha, 256); std::memcpy(small + 64, ch->beta, 256);
     std::memcpy(small + 128, st->b, 256); std::memcpy(small + 192, tr->b_prime_prime, 256);
-    TRY(upload(ctx, small, (size_t)256, &dsmall));
+    uint32_t psipoly[64] = {0};
+    psipoly[0] = psi;
+    if (!dPi2_ready && !ch->pi && !ch->pi2) FAIL(LAB_ERR_PARAMS, "no JL matrix given (pi or pi2)");
+    const size_t pi_first = dPi2_ready ? 0 : (size_t)tr->jl_attempt * R * LAB_JL_ROWS * ND;
+    // small proofs whose checks 8 / 9 passed: everything in one pinned block and one copy (a default-size proof's verifier is
+    // bound by its host-side calls, not by the GPU); otherwise one copy per array
+    const bool staged = lazy && !fc;
+    if (staged) {
+        struct Part { const void *src; size_t bytes; uint32_t **dst; };
+        const Part parts[] = {{tr->z, N * 256, &dz}, {tr->t, R * K * 256, &dT}, {tr->g, R * R * 256, &dG}, {tr->h, R * R * 256, &dH}, {tr->u_1, K1 * 256, &du1},
+                              {tr->u_2, K2 * 256, &du2}, {st->phi, R * ND * 4, &dphi}, {ch->omega, (size_t)LAB_JL_ROWS * 4, &dom}, {st->a, R * R * 256, &da},
+                              {ch->c, R * 256, &dc}, {small, sizeof small, &dsmall}, {psipoly, sizeof psipoly, &dpsi},
+                              {(!dPi2_ready && ch->pi2) ? ch->pi2 + pi_first / 16 : nullptr, (!dPi2_ready && ch->pi2) ? R * LAB_JL_ROWS * ND / 4 : 0, &dPi2}};
+        size_t total = 0;
+        for (const Part &pt : parts) total += (pt.bytes + 255) / 256 * 256;
+        if (ctx->vstage_bytes < total) {
+            if (ctx->vstage) cudaFreeHost(ctx->vstage);
+            ctx->vstage = nullptr; ctx->vstage_bytes = 0;
+            CK(cudaMallocHost(&ctx->vstage, total));
+            ctx->vstage_bytes = total;
+        }
+        char *dblock;
+        TRY(arena_alloc(ctx, total, &dblock));
+        CK(cudaStreamSynchronize(ctx->stream));                 // a call that ended in an error may have left its copy from the block in flight
+        size_t off = 0;
+        for (const Part &pt : parts) {
+            if (pt.bytes) std::memcpy(ctx->vstage + off, pt.src, pt.bytes);
+            *pt.dst = (uint32_t *)(dblock + off);
+            off += (pt.bytes + 255) / 256 * 256;
+        }
+        CK(cudaMemcpyAsync(dblock, ctx->vstage, total, cudaMemcpyHostToDevice, ctx->stream));
+        if (dPi2_ready) dPi2 = const_cast<uint32_t *>(dPi2_ready);
+        else if (!ch->pi2) {                                     // int8 entries: uploaded and packed on arrival
+            TRY(arena_alloc(ctx, R * LAB_JL_ROWS * ND / 16, &dPi2));
+            TRY(arena_alloc(ctx, R * LAB_JL_ROWS * ND, &dPi8));
+            TRY(upload_pi2(ctx, ch->pi + pi_first, nullptr, R, ND, dPi2, dPi8));
+        }
+    } else {
+        TRY(upload(ctx, tr->z, N * 64, &dz));
+        TRY(upload(ctx, tr->t, R * K * 64, &dT));
+        TRY(upload(ctx, tr->g, R * R * 64, &dG));
+        TRY(upload(ctx, tr->h, R * R * 64, &dH));
+        TRY(upload(ctx, tr->u_1, K1 * 64, &du1));
+        TRY(upload(ctx, tr->u_2, K2 * 64, &du2));
+        TRY(upload(ctx, st->phi, R * ND, &dphi));
+        TRY(upload(ctx, ch->omega, (size_t)LAB_JL_ROWS, &dom));
+        TRY(upload(ctx, st->a, R * R * 64, &da));
+        TRY(upload(ctx, ch->c, R * 64, &dc));
+        if (dPi2_ready) dPi2 = const_cast<uint32_t *>(dPi2_ready);
+        else {
+            TRY(arena_alloc(ctx, R * LAB_JL_ROWS * ND / 16, &dPi2));
+            if (!ch->pi2) TRY(arena_alloc(ctx, R * LAB_JL_ROWS * ND, &dPi8));
+            TRY(upload_pi2(ctx, ch->pi2 ? nullptr : ch->pi + pi_first, ch->pi2 ? ch->pi2 + pi_first / 16 : nullptr, R, ND, dPi2, dPi8));
+        }
+        TRY(upload(ctx, small, (size_t)256, &dsmall));
+    }
     unsigned long long *dcnt;
     TRY(arena_alloc(ctx, (size_t)8, &dcnt));                    // [1] = norm, [2..7] = difference counts of Checks 15..20 (lazy mode)
-    const bool lazy = R * K * 256 <= ((uint64_t)4 << 20);       // small proofs: one synchronisation for all equality checks
+    // Small proofs: Checks 19 and 20 recompute u_1 and u_2 -- all of the verifier's ChaCha20 -- and depend on nothing but the
+    // uploaded t, g, h.  They are enqueued on the second (low-priority) stream right here, so that the CRS generation runs beside the
+    // chain of some fifty short kernels of Checks 10-18 instead of after it.  The counts are read back together at the end; the first
+    // failing check in the reference's order still decides.
+    const bool forked = staged && !ctx->comm && !std::getenv("LAB_NO_FORK");
+    if (forked) TRY(ensure_stream2(ctx));
+    Stream2Guard s2guard(forked ? ctx->stream2 : nullptr);      // an early return must not leave the strand running into the next call's arena
+    if (forked) {
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));          // the upload is enqueued
+        CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+        CtxStreamSwap swap(ctx, ctx->stream2);
+        bool eq_unused = true;
+        uint32_t *cand1, *cand2;
+        TRY(arena_alloc(ctx, K1 * 64, &cand1));
+        TRY(d_outer_u1(ctx, c, seed, dT, dG, cand1, 0, K1));
+        TRY(dev_equal(ctx, cand1, du1, K1 * 64, dcnt + 6, &eq_unused, true));
+        TRY(arena_alloc(ctx, K2 * 64, &cand2));
+        TRY(d_outer_u2(ctx, c, seed, dH, cand2, 0, K2));
+        TRY(dev_equal(ctx, cand2, du2, K2 * 64, dcnt + 7, &eq_unused, true));
+        CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
+    }
     // lines 10-14: exact integer norm of every digit (verification.rs:185-267)
     CK(cudaMemsetAsync(dcnt + 1, 0, sizeof *dcnt, ctx->stream));
     LAUNCH(k_digit_norm_sq, grid_for(N * 64, 2048, ctx->sms * 8), 256, dz, (size_t)(N * 64), (uint32_t)c->B, 2, dcnt + 1);
@@ -1982,11 +2052,13 @@ static int verify_core(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_
     LAUNCH(k_digit_norm_sq, grid_for(R * R * 64, 2048, ctx->sms * 8), 256, dG, (size_t)(R * R * 64), (uint32_t)c->B_2, (int)T2, dcnt + 1);
     LAUNCH(k_digit_norm_sq, grid_for(R * R * 64, 2048, ctx->sms * 8), 256, dH, (size_t)(R * R * 64), (uint32_t)c->B_1, (int)T1, dcnt + 1);
     unsigned long long hnorm = 0;
-    CK(cudaMemcpyAsync(&hnorm, dcnt + 1, sizeof hnorm, cudaMemcpyDeviceToHost, ctx->stream));
-    TRY(lab_sync(ctx));
-    if (norm_sum) *norm_sum = hnorm;
-    if (!fc && (double)hnorm > c->BETA_PRIME) fc = 14;          // `sum > BETA_PRIME` (verification.rs:265)
-    if (fc) { if (failed_check) *failed_check = fc; return LAB_OK; }
+    if (!staged) {               // (small proofs read the norm back together with the comparison counts at the end)
+        CK(cudaMemcpyAsync(&hnorm, dcnt + 1, sizeof hnorm, cudaMemcpyDeviceToHost, ctx->stream));
+        TRY(lab_sync(ctx));
+        if (norm_sum) *norm_sum = hnorm;
+        if (!fc && (double)hnorm > c->BETA_PRIME) fc = 14;          // `sum > BETA_PRIME` (verification.rs:265)
+        if (fc) { if (failed_check) *failed_check = fc; return LAB_OK; }
+    }
     // transform-domain operands
     uint32_t *zhat, *That, *Ghat, *Hhat, *Ahat, *Chat, *SMhat, *Phihat, *PPhat, *PFhat, *dpp;
     TRY(arena_alloc(ctx, what_hats(N, 1) * 32, &zhat));
@@ -2065,10 +2137,7 @@ static int verify_core(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_
     if (!fc) {   // check 18: sum a_ij g_ij + sum h_ii - b == 0 with a = alpha a + beta psi a, b = alpha b + beta b'' (lines 5, 7; :340-352)
         uint32_t *psih;
         TRY(arena_alloc(ctx, (size_t)64, &psih));
-        uint32_t psipoly[64] = {0};
-        psipoly[0] = psi;
-        uint32_t *dpsi;
-        TRY(upload(ctx, psipoly, (size_t)64, &dpsi));
+        if (!dpsi) TRY(upload(ctx, psipoly, (size_t)64, &dpsi));
         TRY(d_fwd_hat(ctx, dpsi, psih, 1, 0, 0));
         // acon = alpha * a + (beta * psi) * a
         LAUNCH(k_pointwise, 1, 32, beta_h, (size_t)1, (size_t)0, psih, (const uint32_t *)nullptr, (size_t)1, (size_t)0, (const uint32_t *)nullptr, psih + 32, (size_t)1);
@@ -2084,7 +2153,7 @@ static int verify_core(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_
         TRY(dev_equal(ctx, scal + 224, scal + 256, 32, dcnt + 5, &eq, lazy));
         if (!eq) fc = 18;
     }
-    if (!fc) {   // check 19: u_1 (verification.rs:372-415)
+    if (!fc && !forked) {   // check 19: u_1 (verification.rs:372-415)
         uint32_t *cand;
         TRY(arena_alloc(ctx, K1 * 64, &cand));
         {
@@ -2096,7 +2165,7 @@ static int verify_core(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_
         TRY(dev_equal(ctx, cand, du1, K1 * 64, dcnt + 6, &eq, lazy));
         if (!eq) fc = 19;
     }
-    if (!fc) {   // check 20: u_2 (verification.rs:421-435)
+    if (!fc && !forked) {   // check 20: u_2 (verification.rs:421-435)
         uint32_t *cand;
         TRY(arena_alloc(ctx, K2 * 64, &cand));
         {
@@ -2108,12 +2177,21 @@ static int verify_core(lab_ctx *ctx, const lab_constants *c, const uint8_t seed_
         TRY(dev_equal(ctx, cand, du2, K2 * 64, dcnt + 7, &eq, lazy));
         if (!eq) fc = 20;
     }
+    if (forked) {                 // join the strand of Checks 19 and 20
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+        s2guard.disarm();
+    }
     if (lazy && !fc) {            // all comparisons are enqueued: one read-back, the first failing check in the reference's order counts
-        unsigned long long hc[6] = {0, 0, 0, 0, 0, 0};
-        CK(cudaMemcpyAsync(hc, dcnt + 2, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
+        unsigned long long hc[7] = {0, 0, 0, 0, 0, 0, 0};     // norm, then the difference counts of Checks 15..20
+        CK(cudaMemcpyAsync(hc, dcnt + 1, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
         TRY(lab_sync(ctx));
+        if (staged) {
+            hnorm = hc[0];
+            if (norm_sum) *norm_sum = hnorm;
+            if ((double)hnorm > c->BETA_PRIME) fc = 14;         // `sum > BETA_PRIME` (verification.rs:265) precedes Checks 15..20
+        }
         for (int k = 0; k < 6 && !fc; k++)
-            if (hc[k]) fc = 15 + k;
+            if (hc[1 + k]) fc = 15 + k;
     }
     if (failed_check) *failed_check = fc;
     *accepted = fc == 0;
