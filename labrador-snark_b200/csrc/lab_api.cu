@@ -245,14 +245,16 @@ extern "C" int lab_ctx_create(int device, lab_ctx **out) {
     ctx->device = device;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sms = prop.multiProcessorCount;
-    // The main stream gets the greatest priority, the second stream (ensure_stream2) keeps the default = least one: when a proof or a
+    // The main stream gets a high priority, the second stream (ensure_stream2) keeps the default = least one: when a proof or a
     // verification forks its ChaCha20-heavy strand (u_1) to the second stream, the short dependent kernels of the main chain take
     // the SM slots that strand's CTAs free up instead of queueing behind its remaining waves (LAB_STREAM_PRIO=0: both default)
+    // (one step below the greatest, which the contraction stream of the generate-then-contract path keeps: ensure_gc_stream)
     int prio_lo = 0, prio_hi = 0;
-    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);     // numerically: lo = least (0), hi = greatest (negative)
+    int prio_main = prio_hi < prio_lo - 1 ? prio_hi + 1 : prio_hi;
     const char *sp = std::getenv("LAB_STREAM_PRIO");
-    if (sp && sp[0] == '0') prio_hi = prio_lo;
-    if ((e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) {
+    if (sp && sp[0] == '0') prio_main = prio_lo;
+    if ((e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_main)) != cudaSuccess) {
         g_create_err = cudaGetErrorString(e);
         delete ctx;
         return LAB_ERR_CUDA;
